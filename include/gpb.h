@@ -1,0 +1,103 @@
+/*
+ * gpb.h -- C ABI of the B200-native Gaussian-process backend (libgpb.so).
+ *
+ * This is the drop-in boundary for proFit's Custom-GP numerics.  The reference has no FFI on this path (it is
+ * numpy/scipy called in-process), so each entry point names the reference *function* it replaces; paths are
+ * relative to the reference root.  The Python host layer (profit_b200/) binds these with ctypes and mirrors the
+ * reference's operator interface on top (see INTEGRATION.md for the reference-side stub).
+ *
+ * Conventions
+ *   - All matrices are C-order (row-major) IEEE fp64, exactly like the numpy arrays the reference passes.
+ *   - Every pointer may be a host pointer (numpy) or a device pointer (torch CUDA tensor); the library detects
+ *     which.  Caller owns all buffers passed in; the library owns its device workspaces inside the handle.
+ *   - Return value: 0 = ok; > 0 = LAPACK-style info (1-based index of the first non-positive pivot: the
+ *     matrix is not SPD -> the Python layer raises numpy.linalg.LinAlgError like gp_functions.py:143 would);
+ *     < 0 = bad argument (-1), CUDA failure (-2), not ready (-3).  gpb_error_string() describes the last error.
+ *   - One handle = one device + one stream; calls on a handle must be serialised by the caller.
+ *   - There is no CPU fallback anywhere behind this interface.
+ */
+#ifndef GPB_H_
+#define GPB_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gpb_handle_s* gpb_handle_t;
+
+enum { GPB_KERNEL_RBF = 0, GPB_KERNEL_MATERN52 = 1 };
+
+/* stage indices for gpb_stage_ms() */
+enum {
+  GPB_STAGE_ASSEMBLE = 0, /* prescale + K assembly (+ y rows)                       */
+  GPB_STAGE_POTRF = 1,    /* blocked Cholesky incl. forward substitution of y        */
+  GPB_STAGE_TRTRI = 2,    /* U = L^-T by recursive tile GEMMs                        */
+  GPB_STAGE_SYRK = 3,     /* K^-1 = U U^T                                            */
+  GPB_STAGE_GRAD = 4,     /* alpha, gradient contraction, reductions                 */
+  GPB_STAGE_CROSS = 5,    /* predict: K(X*,X) + mean                                 */
+  GPB_STAGE_VAR = 6,      /* predict: ||L^-1 k*||^2 tile GEMM + finish               */
+  GPB_STAGE_TOTAL = 7,
+  GPB_NUM_STAGES = 8
+};
+
+int gpb_version(void);
+
+int gpb_create(int device, gpb_handle_t* out);
+int gpb_destroy(gpb_handle_t h);
+const char* gpb_error_string(gpb_handle_t h);
+
+/* Upload the training set once; it stays resident across optimiser iterations.
+ * Replaces the (X, y) arguments threaded through gp_functions.optimize (gp_functions.py:8-69) and the
+ * surrogate's Xtrain/ytrain (custom_surrogate.py:122-142).  X: (n, d), y: (n, n_out), n_out <= 128. */
+int gpb_set_train(gpb_handle_t h, const double* X, const double* y, long long n, int d, int n_out);
+
+/* Negative log marginal likelihood and its gradient w.r.t. theta = [length_scale(n_ell), sigma_f, sigma_n]
+ * on the LINEAR scale -- gp_functions.negative_log_likelihood_cholesky (gp_functions.py:103-187) with
+ * log_scale_hyp=False, fixed_sigma_n=False; the host layer applies the log10 chain rule and the sigma_n slicing
+ * (:181-186).  grad has n_ell + 2 entries and may be NULL when want_grad == 0.
+ * After a call with want_grad != 0 the handle also holds alpha and L^-1 (usable by gpb_predict). */
+int gpb_nll(gpb_handle_t h, int kind, const double* theta, int n_ell, int want_grad, double* nll, double* grad);
+
+/* Factorise K(theta) and cache alpha = K^-1 y and W = L^-1 for prediction.  Replaces the per-call
+ * GPSurrogate.Ky / .alpha / gp_functions.invert(Ky) of custom_surrogate.py:24-45,114-116. */
+int gpb_factorize(gpb_handle_t h, int kind, const double* theta, int n_ell);
+
+/* Predictive mean (M, n_out) and variance (M) -- GPSurrogate.predict (custom_surrogate.py:95-120):
+ * mean = K*^T alpha, var = max(sf^2 - diag(K*^T K^-1 K*), 1e-10) (+ sn^2 if add_data_variance == 1).
+ * add_data_variance == 2 adds sn^2 before the clamp, which is gp_functions.predict_f (gp_functions.py:484-488).
+ * Either output may be NULL. */
+int gpb_predict(gpb_handle_t h, const double* Xc, long long M, int add_data_variance, double* mean, double* var);
+
+/* argmax with lowest-index tie-break, like np.argmax in aquisition_functions.py:68. v: (M). */
+int gpb_argmax(gpb_handle_t h, const double* v, long long M, long long* idx, double* val);
+
+/* Dense kernel matrix and derivative tensor -- python_kernels.RBF (python_kernels.py:8-57) and the Matern-5/2
+ * twin.  K: (na, nb); dK: (na, nb, n_ell + 2) or NULL. */
+int gpb_kernel_matrix(gpb_handle_t h, int kind, const double* Xa, long long na, const double* Xb, long long nb, int d,
+                      const double* ell, int n_ell, double sigma_f, double sigma_n, double* K, double* dK);
+
+/* L = cholesky(A) (lower, upper zeroed) -- np.linalg.cholesky at gp_functions.py:143,341. A: (n, n). */
+int gpb_cholesky(gpb_handle_t h, const double* A, long long n, double* L);
+
+/* K^-1 from its Cholesky factor -- gp_functions.invert_cholesky (gp_functions.py:304-322). */
+int gpb_invert_cholesky(gpb_handle_t h, const double* L, long long n, double* Kinv);
+
+/* x = L^T \ (L \ b), b: (n, nrhs) -- gp_functions.solve_cholesky (gp_functions.py:72-100). nrhs <= 128. */
+int gpb_solve_cholesky(gpb_handle_t h, const double* L, long long n, const double* b, int nrhs, double* x);
+
+/* Device milliseconds of each stage of the last gpb_nll / gpb_factorize / gpb_predict call (CUDA events on the
+ * handle's stream).  out has GPB_NUM_STAGES entries. */
+int gpb_stage_ms(gpb_handle_t h, double* out);
+
+/* Number of kernels launched by this handle since creation (the host layer reports it as gpu_launches). */
+long long gpb_launch_count(gpb_handle_t h);
+
+/* Test/benchmark hook: C(MxN) = A(MxK) * B(NxK)^T with the tile-GEMM kernel, device pointers, all dimensions
+ * multiples of 128.  cfg selects the tile configuration.  Returns the average ms over reps in *ms. */
+int gpb_debug_gemm(gpb_handle_t h, const double* A, const double* B, double* C, long long M, long long N, long long K,
+                   int cfg, int reps, double* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPB_H_ */

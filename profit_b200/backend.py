@@ -1,0 +1,178 @@
+"""Device-resident GP state: one `GPBackend` = one gpb handle = one GPU + one stream.
+
+Thin, allocation-free wrapper over the C ABI; all numerics run in libgpb's CUDA kernels.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+KIND_RBF = 0
+KIND_MATERN52 = 1
+
+
+class GPBackend:
+    def __init__(self, device=None):
+        lib = _lib.load()
+        if device is None:
+            device = _default_device()
+        self.device = int(device)
+        self._h = ctypes.c_void_p()
+        st = lib.gpb_create(self.device, ctypes.byref(self._h))
+        if st != 0:
+            raise RuntimeError(
+                f"gpb_create(device={self.device}) failed with status {st}: a CUDA device is required "
+                "(profit_b200 has no CPU fallback)"
+            )
+        self._lib = lib
+        self.n = 0
+        self.d = 0
+        self.n_out = 0
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.gpb_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- training set ---------------------------------------------------------------------------------
+    def set_train(self, X, y):
+        X = _lib.as_f64(X)
+        y = _lib.as_f64(y)
+        if X.ndim != 2:
+            raise ValueError(f"X should have shape (n, d) but has shape {tuple(X.shape)}")
+        n, d = int(X.shape[0]), int(X.shape[1])
+        if y.ndim == 1:
+            n_out = 1
+        elif y.ndim == 2:
+            n_out = int(y.shape[1])
+        else:
+            raise ValueError(f"y should have shape (n,) or (n, D) but has shape {tuple(y.shape)}")
+        if int(y.shape[0]) != n:
+            raise ValueError(f"mismatched number of data points for X and y: {n} != {int(y.shape[0])}")
+        _lib.check(self._lib.gpb_set_train(self._h, _lib.ptr(X), _lib.ptr(y), n, d, n_out), self._h, "set_train")
+        self.n, self.d, self.n_out = n, d, n_out
+
+    # -- likelihood -----------------------------------------------------------------------------------
+    def nll(self, kind, theta, want_grad=False):
+        """theta = [length_scale..., sigma_f, sigma_n] on the linear scale -> nll [, grad (P,)]."""
+        theta = np.ascontiguousarray(theta, dtype=np.float64).ravel()
+        n_ell = theta.size - 2
+        out = ctypes.c_double()
+        grad = np.empty(theta.size) if want_grad else None
+        st = self._lib.gpb_nll(self._h, int(kind), _lib.ptr(theta), n_ell, int(bool(want_grad)), ctypes.byref(out),
+                               _lib.ptr(grad))
+        _lib.check(st, self._h, "nll")
+        return (out.value, grad) if want_grad else out.value
+
+    def factorize(self, kind, theta):
+        theta = np.ascontiguousarray(theta, dtype=np.float64).ravel()
+        _lib.check(self._lib.gpb_factorize(self._h, int(kind), _lib.ptr(theta), theta.size - 2), self._h, "factorize")
+
+    def predict(self, Xc, add_data_variance=True, out_mean=None, out_var=None, want_mean=True, want_var=True):
+        Xc = _lib.as_f64(Xc)
+        M = int(Xc.shape[0])
+        if want_mean and out_mean is None:
+            out_mean = np.empty((M, self.n_out))
+        if want_var and out_var is None:
+            out_var = np.empty(M)
+        st = self._lib.gpb_predict(self._h, _lib.ptr(Xc), M, int(add_data_variance),
+                                   _lib.ptr(out_mean) if want_mean else None, _lib.ptr(out_var) if want_var else None)
+        _lib.check(st, self._h, "predict")
+        return out_mean, out_var
+
+    def argmax(self, v):
+        v = _lib.as_f64(v)
+        idx = ctypes.c_longlong()
+        val = ctypes.c_double()
+        _lib.check(self._lib.gpb_argmax(self._h, _lib.ptr(v), int(v.shape[0]), ctypes.byref(idx), ctypes.byref(val)),
+                   self._h, "argmax")
+        return int(idx.value), float(val.value)
+
+    # -- dense twins ----------------------------------------------------------------------------------
+    def kernel_matrix(self, kind, Xa, Xb, ell, sigma_f, sigma_n, eval_gradient=False):
+        Xa = _lib.as_f64(Xa)
+        Xb = _lib.as_f64(Xb)
+        ell = np.ascontiguousarray(ell, dtype=np.float64).ravel()
+        na, nb, d = int(Xa.shape[0]), int(Xb.shape[0]), int(Xa.shape[1])
+        K = np.empty((na, nb))
+        dK = np.empty((na, nb, ell.size + 2)) if eval_gradient else None
+        st = self._lib.gpb_kernel_matrix(self._h, int(kind), _lib.ptr(Xa), na, _lib.ptr(Xb), nb, d, _lib.ptr(ell),
+                                         ell.size, float(sigma_f), float(sigma_n), _lib.ptr(K), _lib.ptr(dK))
+        _lib.check(st, self._h, "kernel_matrix")
+        return (K, dK) if eval_gradient else K
+
+    def cholesky(self, A):
+        A = _lib.as_f64(A)
+        L = np.empty_like(A)
+        _lib.check(self._lib.gpb_cholesky(self._h, _lib.ptr(A), int(A.shape[0]), _lib.ptr(L)), self._h, "cholesky")
+        return L
+
+    def invert_cholesky(self, L):
+        L = _lib.as_f64(L)
+        out = np.empty_like(L)
+        _lib.check(self._lib.gpb_invert_cholesky(self._h, _lib.ptr(L), int(L.shape[0]), _lib.ptr(out)), self._h,
+                   "invert_cholesky")
+        return out
+
+    def solve_cholesky(self, L, b):
+        L = _lib.as_f64(L)
+        b = _lib.as_f64(b)
+        nrhs = 1 if b.ndim == 1 else int(b.shape[1])
+        x = np.empty_like(b)
+        _lib.check(self._lib.gpb_solve_cholesky(self._h, _lib.ptr(L), int(L.shape[0]), _lib.ptr(b), nrhs, _lib.ptr(x)),
+                   self._h, "solve_cholesky")
+        return x
+
+    # -- introspection --------------------------------------------------------------------------------
+    def stage_ms(self):
+        out = np.zeros(_lib.NUM_STAGES)
+        self._lib.gpb_stage_ms(self._h, _lib.ptr(out))
+        return dict(zip(_lib.STAGE_NAMES, out.tolist()))
+
+    def launch_count(self):
+        return int(self._lib.gpb_launch_count(self._h))
+
+    def debug_gemm(self, A, B, C, cfg=1, reps=5):
+        M, K = int(A.shape[0]), int(A.shape[1])
+        N = int(B.shape[0])
+        ms = ctypes.c_double()
+        _lib.check(self._lib.gpb_debug_gemm(self._h, _lib.ptr(A), _lib.ptr(B), _lib.ptr(C), M, N, K, int(cfg), int(reps),
+                                            ctypes.byref(ms)), self._h, "debug_gemm")
+        return ms.value
+
+
+def _default_device():
+    """LOCAL_RANK under torchrun (one process per GPU), else the current torch device, else 0."""
+    import os
+
+    if "LOCAL_RANK" in os.environ:
+        return int(os.environ["LOCAL_RANK"])
+    try:
+        import torch
+
+        if torch.cuda.is_available():
+            return torch.cuda.current_device()
+    except Exception:
+        pass
+    return 0
+
+
+_shared = {}
+
+
+def shared_backend(device=None):
+    """Process-wide backend per device, used by the function-level API (kernels.py, gp_functions.py)."""
+    if device is None:
+        device = _default_device()
+    be = _shared.get(device)
+    if be is None:
+        be = GPBackend(device)
+        _shared[device] = be
+    return be

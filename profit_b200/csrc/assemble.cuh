@@ -1,0 +1,349 @@
+// Covariance-kernel evaluation kernels (HBM-bound): K(X,X) assembly into the factorisation buffer, the
+// rectangular K(Xa,Xb) [+ dK/dtheta planes] behind the `kernel(X, Y, ...)` plug-in API, the cross-kernel
+// K(X*,X) with the predictive mean fused in, and the gradient contraction sum_ij A_ij dK_ij/dtheta_p
+// that never materialises dK.
+//
+// Per-element arithmetic follows the reference: inputs are first divided by the length scale
+// (python_kernels.py:35-36), differences are taken per dimension (:37-39), K = sf^2 exp(-d2/2) + sn^2 I
+// (:41), dK/dl_d = (dx_d^2 / l_d) K_pure (:49-53), dK/dsf = 2/sf K_pure (:54), dK/dsn = 2 sn I (:55).
+// Matern-5/2 has no reference implementation on this path; formulas in oracle/gp_oracle.py::matern52.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+namespace gpb {
+
+enum { KIND_RBF = 0, KIND_MATERN52 = 1 };
+constexpr int MAX_D = 32;
+
+struct KernelHyp {
+  int kind;
+  int D;            // input dimension
+  int n_ell;        // 1 (isotropic) or D (ARD)
+  double ell[MAX_D];
+  double sf, sn;
+};
+
+__device__ __forceinline__ double ell_of(const KernelHyp& h, int d) { return h.n_ell == 1 ? h.ell[0] : h.ell[d]; }
+
+// k_pure and the radial derivative factor g with dK/dl_d = g * dx_d^2 / l_d  (dx scaled by 1/l).
+template <int KIND>
+__device__ __forceinline__ void kern_eval(double d2, double sf2, double& kp, double& gfac) {
+  if (KIND == KIND_RBF) {
+    kp = sf2 * exp(-0.5 * d2);
+    gfac = kp;
+  } else {
+    const double s5 = 2.23606797749978969640917366873128;
+    const double r = sqrt(d2);
+    const double e = exp(-s5 * r);
+    kp = sf2 * (1.0 + s5 * r + (5.0 / 3.0) * d2) * e;
+    gfac = sf2 * (5.0 / 3.0) * (1.0 + s5 * r) * e;
+  }
+}
+
+// Xs[i][d] = X[i][d] / l_d (row-major, DP columns, zero padded) and XsT[d][i] (DP x ldt).
+__global__ void prescale_kernel(const double* __restrict__ X, int n, KernelHyp h, int DP, double* __restrict__ Xs,
+                                double* __restrict__ XsT, long long ldt, int n_pad) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long long)n_pad * DP) return;
+  const int i = (int)(e / DP), d = (int)(e % DP);
+  double v = 0.0;
+  if (i < n && d < h.D) v = X[(long long)i * h.D + d] / ell_of(h, d);
+  if (Xs) Xs[(long long)i * DP + d] = v;
+  if (XsT) XsT[(long long)d * ldt + i] = v;
+}
+
+constexpr int AS_TM = 64, AS_TN = 128, AS_THREADS = 256;
+
+// Lower-triangular tiles of K(X,X) + sn^2 I into L (row-major, ldl).  Rows/cols >= n are padding: identity.
+template <int KIND, int DP>
+__global__ void __launch_bounds__(AS_THREADS)
+assemble_sym_kernel(const double* __restrict__ Xs, const double* __restrict__ XsT, long long ldt, int n, int n_pad,
+                    double sf2, double sn2, double* __restrict__ L, long long ldl) {
+  const int row0 = blockIdx.y * AS_TM, col0 = blockIdx.x * AS_TN;
+  if (col0 > row0 + AS_TM - 1) return;  // tile strictly above the diagonal
+  __shared__ double xi[AS_TM][DP];
+  for (int e = threadIdx.x; e < AS_TM * DP; e += AS_THREADS)
+    xi[e / DP][e % DP] = Xs[(long long)(row0 + e / DP) * DP + e % DP];
+  const int cp = threadIdx.x & 63, rg = threadIdx.x >> 6;
+  const int c = col0 + 2 * cp;
+  double xj0[DP], xj1[DP];
+#pragma unroll
+  for (int d = 0; d < DP; ++d) {
+    const double2 v = *reinterpret_cast<const double2*>(XsT + (long long)d * ldt + c);
+    xj0[d] = v.x;
+    xj1[d] = v.y;
+  }
+  __syncthreads();
+  for (int rr = rg; rr < AS_TM; rr += 4) {
+    const int r = row0 + rr;
+    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+    for (int d = 0; d < DP; ++d) {
+      const double x = xi[rr][d];
+      const double u0 = x - xj0[d], u1 = x - xj1[d];
+      a0 = fma(u0, u0, a0);
+      a1 = fma(u1, u1, a1);
+    }
+    double k0, k1, gdummy;
+    kern_eval<KIND>(a0, sf2, k0, gdummy);
+    kern_eval<KIND>(a1, sf2, k1, gdummy);
+    if (r == c) k0 += sn2;
+    if (r == c + 1) k1 += sn2;
+    if (r >= n || c >= n) k0 = (r == c) ? 1.0 : 0.0;
+    if (r >= n || c + 1 >= n) k1 = (r == c + 1) ? 1.0 : 0.0;
+    *reinterpret_cast<double2*>(L + (long long)r * ldl + c) = make_double2(k0, k1);
+  }
+}
+
+// Rows [n_pad, n_pad+128) of the factorisation buffer carry y^T (one output per row) so that the panel solves
+// of the Cholesky also perform the forward substitution z = L^{-1} y.
+__global__ void fill_aug_kernel(const double* __restrict__ y, int n, int m, int n_pad, double* __restrict__ L,
+                                long long ldl) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long long)128 * n_pad) return;
+  const int r = (int)(e / n_pad), j = (int)(e % n_pad);
+  double v = 0.0;
+  if (r < m && j < n) v = y[(long long)j * m + r];
+  L[(long long)(n_pad + r) * ldl + j] = v;
+}
+
+// Rectangular K(Xa, Xb) (+ sn^2 on the main diagonal, as np.eye(n, m) does) and optionally the
+// (na, nb, P) derivative tensor, P ordered [l..., sf, sn] like python_kernels.py:42-56.
+// Thread owns one (row, column-pair); dK is staged through shared memory so global stores are coalesced.
+template <int KIND>
+__global__ void __launch_bounds__(256)
+kernel_matrix_kernel(const double* __restrict__ Xa, int na, const double* __restrict__ Xb, int nb, KernelHyp h,
+                     double* __restrict__ K, double* __restrict__ dK) {
+  extern __shared__ double stage[];  // [rows_per_cta=4][64 cols][P] when dK requested
+  const int P = h.n_ell + 2;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  const int j = blockIdx.x * 64 + tx;
+  const int i = blockIdx.y * 4 + ty;
+  const double sf2 = h.sf * h.sf, sn2 = h.sn * h.sn;
+  const bool valid = (i < na && j < nb);
+  double d2 = 0.0, kp = 0.0, gf = 0.0;
+  double u2[MAX_D];
+  if (valid) {
+#pragma unroll 4
+    for (int d = 0; d < h.D; ++d) {
+      const double l = ell_of(h, d);
+      const double u = Xa[(long long)i * h.D + d] / l - Xb[(long long)j * h.D + d] / l;
+      u2[d] = u * u;
+      d2 += u * u;
+    }
+    kern_eval<KIND>(d2, sf2, kp, gf);
+    K[(long long)i * nb + j] = kp + ((i == j) ? sn2 : 0.0);
+  }
+  if (dK == nullptr) return;
+  double* my = stage + ((long long)ty * 64 + tx) * P;
+  if (valid) {
+    if (h.n_ell == 1) {
+      my[0] = d2 / h.ell[0] * gf;
+    } else {
+      for (int d = 0; d < h.D; ++d) my[d] = u2[d] / h.ell[d] * gf;
+    }
+    my[P - 2] = 2.0 / h.sf * kp;
+    my[P - 1] = (i == j) ? 2.0 * h.sn : 0.0;
+  }
+  __syncthreads();
+  // coalesced copy-out: row (blockIdx.y*4+ty) has a contiguous span of ncols*P doubles
+  const int ncols = min(64, nb - blockIdx.x * 64);
+  for (int r = 0; r < 4; ++r) {
+    const int ii = blockIdx.y * 4 + r;
+    if (ii >= na) break;
+    double* dst = dK + ((long long)ii * nb + (long long)blockIdx.x * 64) * P;
+    const double* src = stage + (long long)r * 64 * P;
+    for (int e = threadIdx.x; e < ncols * P; e += 256) dst[e] = src[e];
+  }
+}
+
+// Gradient contraction over the lower triangle (off-diagonal entries weighted twice):
+//   acc_p = sum_ij w_ij * dKfac_ij,p   with  w = n_out * Kinv_ij - sum_r alpha_r[i] alpha_r[j]
+// (gp_functions.py:169-180 with the trace written as an elementwise contraction).  Partial sums per CTA go to
+// part[cta][DP+2] (slots: l_0..l_{DP-1}, sf, sn) and are reduced in a fixed order by reduce_partials_kernel.
+template <int KIND, int DP>
+__global__ void __launch_bounds__(AS_THREADS)
+grad_contract_kernel(const double* __restrict__ Xs, const double* __restrict__ XsT, long long ldt, int n, double sf2,
+                     const double* __restrict__ Kinv, long long ldk, const double* __restrict__ alpha,
+                     long long lda, int n_out, double* __restrict__ part) {
+  const int row0 = blockIdx.y * AS_TM, col0 = blockIdx.x * AS_TN;
+  const int cta = blockIdx.y * gridDim.x + blockIdx.x;
+  double acc[DP + 2];
+#pragma unroll
+  for (int p = 0; p < DP + 2; ++p) acc[p] = 0.0;
+  __shared__ double xi[AS_TM][DP];
+  __shared__ double red[AS_THREADS / 32][DP + 2];
+  const bool active = !(col0 > row0 + AS_TM - 1) && row0 < n && col0 < n;
+  if (active) {
+    for (int e = threadIdx.x; e < AS_TM * DP; e += AS_THREADS)
+      xi[e / DP][e % DP] = Xs[(long long)(row0 + e / DP) * DP + e % DP];
+    const int cp = threadIdx.x & 63, rg = threadIdx.x >> 6;
+    const int c = col0 + 2 * cp;
+    double xj0[DP], xj1[DP];
+#pragma unroll
+    for (int d = 0; d < DP; ++d) {
+      const double2 v = *reinterpret_cast<const double2*>(XsT + (long long)d * ldt + c);
+      xj0[d] = v.x;
+      xj1[d] = v.y;
+    }
+    __syncthreads();
+    for (int rr = rg; rr < AS_TM; rr += 4) {
+      const int r = row0 + rr;
+      if (r >= n || c > r) continue;
+      const double2 kin = *reinterpret_cast<const double2*>(Kinv + (long long)r * ldk + c);
+      double aa0 = 0.0, aa1 = 0.0;
+      for (int o = 0; o < n_out; ++o) {
+        const double ar = alpha[(long long)o * lda + r];
+        aa0 = fma(ar, alpha[(long long)o * lda + c], aa0);
+        aa1 = fma(ar, alpha[(long long)o * lda + c + 1], aa1);
+      }
+      double w0 = n_out * kin.x - aa0, w1 = n_out * kin.y - aa1;
+      w0 = (c == r) ? w0 : 2.0 * w0;
+      w1 = (c + 1 == r) ? w1 : 2.0 * w1;
+      if (c >= n) w0 = 0.0;
+      if (c + 1 > r || c + 1 >= n) w1 = 0.0;
+      double u0[DP], u1[DP];
+      double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+      for (int d = 0; d < DP; ++d) {
+        const double x = xi[rr][d];
+        const double v0 = x - xj0[d], v1 = x - xj1[d];
+        u0[d] = v0 * v0;
+        u1[d] = v1 * v1;
+        a0 += u0[d];
+        a1 += u1[d];
+      }
+      double k0, g0, k1, g1;
+      kern_eval<KIND>(a0, sf2, k0, g0);
+      kern_eval<KIND>(a1, sf2, k1, g1);
+      const double wg0 = w0 * g0, wg1 = w1 * g1;
+#pragma unroll
+      for (int d = 0; d < DP; ++d) acc[d] = fma(wg0, u0[d], fma(wg1, u1[d], acc[d]));
+      acc[DP] = fma(w0, k0, fma(w1, k1, acc[DP]));
+      if (c == r) acc[DP + 1] += w0;
+      if (c + 1 == r) acc[DP + 1] += w1;
+    }
+  }
+  // fixed-order block reduction
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int p = 0; p < DP + 2; ++p) {
+    double v = acc[p];
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if (lane == 0) red[warp][p] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < DP + 2) {
+    double s = 0.0;
+    for (int w = 0; w < AS_THREADS / 32; ++w) s += red[w][threadIdx.x];
+    part[(long long)cta * (DP + 2) + threadIdx.x] = s;
+  }
+}
+
+// out[p] = sum_c part[c][p] in a fixed (tree) order: deterministic across runs and launches.
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __restrict__ part, int ncta, int width,
+                                                             double* __restrict__ out) {
+  __shared__ double sh[256];
+  const int p = blockIdx.x;
+  double s = 0.0;
+  for (int c = threadIdx.x; c < ncta; c += 256) s += part[(long long)c * width + p];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) {
+    if (threadIdx.x < off) sh[threadIdx.x] += sh[threadIdx.x + off];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[p] = sh[0];
+}
+
+// Cross kernel for prediction: KsT[c][i] = k(x*_c, x_i) (no noise; zero in padded columns) for a chunk of
+// candidates, with the predictive mean fused:  mean[c][o] = sum_i KsT[c][i] * alpha_o[i]
+// (custom_surrogate.py:109,113).  One CTA owns CR candidate rows and sweeps all training points.
+constexpr int CR_ROWS = 32;
+template <int KIND, int DP>
+__global__ void __launch_bounds__(AS_THREADS)
+cross_mean_kernel(const double* __restrict__ Xc, int mc, int D, KernelHyp h, const double* __restrict__ XsT,
+                  long long ldt, int n, int n_pad, const double* __restrict__ alpha, long long lda, int n_out,
+                  double* __restrict__ KsT, long long ldk, double* __restrict__ mean) {
+  __shared__ double xc[CR_ROWS][DP];
+  __shared__ double red[AS_THREADS / 32][CR_ROWS / 4];
+  const int c0 = blockIdx.x * CR_ROWS;
+  for (int e = threadIdx.x; e < CR_ROWS * DP; e += AS_THREADS) {
+    const int r = e / DP, d = e % DP;
+    double v = 0.0;
+    if (c0 + r < mc && d < D) v = Xc[(long long)(c0 + r) * D + d] / ell_of(h, d);
+    xc[r][d] = v;
+  }
+  __syncthreads();
+  const int cp = threadIdx.x & 63, rg = threadIdx.x >> 6;
+  const double sf2 = h.sf * h.sf;
+  for (int o = 0; o < max(n_out, 1); ++o) {
+    double msum[CR_ROWS / 4];
+#pragma unroll
+    for (int q = 0; q < CR_ROWS / 4; ++q) msum[q] = 0.0;
+    for (int col0 = 0; col0 < n_pad; col0 += AS_TN) {
+      const int c = col0 + 2 * cp;
+      double xj0[DP], xj1[DP];
+#pragma unroll
+      for (int d = 0; d < DP; ++d) {
+        const double2 v = *reinterpret_cast<const double2*>(XsT + (long long)d * ldt + c);
+        xj0[d] = v.x;
+        xj1[d] = v.y;
+      }
+      const double al0 = (c < n) ? alpha[(long long)o * lda + c] : 0.0;
+      const double al1 = (c + 1 < n) ? alpha[(long long)o * lda + c + 1] : 0.0;
+#pragma unroll
+      for (int q = 0; q < CR_ROWS / 4; ++q) {
+        const int rr = rg + 4 * q;
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+        for (int d = 0; d < DP; ++d) {
+          const double x = xc[rr][d];
+          const double u0 = x - xj0[d], u1 = x - xj1[d];
+          a0 = fma(u0, u0, a0);
+          a1 = fma(u1, u1, a1);
+        }
+        double k0, k1, gd;
+        kern_eval<KIND>(a0, sf2, k0, gd);
+        kern_eval<KIND>(a1, sf2, k1, gd);
+        if (c >= n) k0 = 0.0;
+        if (c + 1 >= n) k1 = 0.0;
+        if (o == 0 && KsT != nullptr)
+          *reinterpret_cast<double2*>(KsT + (long long)(c0 + rr) * ldk + c) = make_double2(k0, k1);
+        msum[q] = fma(k0, al0, fma(k1, al1, msum[q]));
+      }
+    }
+    // reduce msum over the 64 column-pair threads of each row group (2 warps per rg), fixed order
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int q = 0; q < CR_ROWS / 4; ++q) {
+      double v = msum[q];
+      for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+      if (lane == 0) red[warp][q] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < CR_ROWS) {
+      const int rr = threadIdx.x, rgi = rr & 3, q = rr >> 2;
+      const double s = red[2 * rgi][q] + red[2 * rgi + 1][q];
+      if (c0 + rr < mc && n_out > 0) mean[(long long)(c0 + rr) * n_out + o] = s;
+    }
+    __syncthreads();
+  }
+}
+
+// var[c] = max(sf^2 - sum_t part[t][c], 1e-10) (+ sn^2)   (custom_surrogate.py:110-119)
+// add_first: the noise term joins before the clamp, as gp_functions.predict_f does (gp_functions.py:484-488).
+__global__ void finish_variance_kernel(const double* __restrict__ part, long long ldp, int ntile, int mc, double sf2,
+                                       double add, bool add_first, double* __restrict__ var) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= mc) return;
+  double q = 0.0;
+  for (int t = 0; t < ntile; ++t) q += part[(long long)t * ldp + c];
+  double v = sf2 - q;
+  if (add_first) v = fmax(v + add, 1e-10);
+  else v = fmax(v, 1e-10) + add;
+  var[c] = v;
+}
+
+}  // namespace gpb

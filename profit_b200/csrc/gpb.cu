@@ -1,0 +1,1207 @@
+// libgpb: host orchestration and C ABI (include/gpb.h) of the B200-native GP backend.
+//
+// Data layout in HBM (all row-major fp64, leading dimensions padded to the 128 block size):
+//   Lbuf (Np+128) x Np : K -> L (lower).  Rows [Np, Np+128) carry y^T so the panel solves also produce
+//                        z = L^-1 y.  The strict upper triangle is scratch (T of the triangular inverse); the
+//                        lower triangle is finally overwritten by K^-1 when a gradient is requested.
+//   Ubuf Np x Np       : U = L^-T (upper)            Wbuf Np x Np : W = L^-1 = U^T (lower)
+//   Dinv Np x 128      : inverses of the 128x128 diagonal blocks of L
+// Padding rows/cols (index >= N) hold the identity, which every stage maps to the identity.
+//
+// Algorithms (all dense O(N^3) work is tile tasks for dgemm_tasks_kernel, see dgemm_tasks.cuh):
+//   potrf : two-level right-looking blocked Cholesky; panel solve L_ik = A_ik W_kk^T uses the inverted diagonal
+//           block, so it is a GEMM too.                                   (np.linalg.cholesky, gp_functions.py:143)
+//   trtri : recursive  U12 = -U11 L21^T U22  evaluated level by level as two batched NT GEMMs.
+//   syrk  : K^-1 = U U^T (lower).                                          (invert_cholesky, gp_functions.py:304-322)
+//   predict variance : ||W k*||^2 as a tile GEMM with a column sum-of-squares epilogue.
+#include "../../include/gpb.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "assemble.cuh"
+#include "dgemm_tasks.cuh"
+#include "potrf_diag.cuh"
+
+using namespace gpb;
+
+namespace {
+
+enum MatId { M_L = 0, M_U, M_W, M_DINV, M_KST, M_PART, M_DBG_A, M_DBG_B, M_DBG_C, M_NONE };
+enum GemmCfg { CFG_128x128 = 0, CFG_128x64 = 1, CFG_64x128 = 2, NUM_CFG };
+
+struct Launch {
+  int type;  // 0 = diag block, 1 = tile GEMM
+  int k;     // diag: block index
+  int cfg, matA, matB, matC, matCt;
+  double alpha, beta;
+  size_t task_off;
+  int ntasks;
+  int epi;
+};
+
+struct Plan {
+  std::vector<Launch> launches;
+  std::vector<GemmTask> tasks;
+  GemmTask* d_tasks = nullptr;
+  void clear() {
+    launches.clear();
+    tasks.clear();
+    if (d_tasks) cudaFree(d_tasks);
+    d_tasks = nullptr;
+  }
+};
+
+struct MatDesc {
+  double* ptr = nullptr;
+  long long rows = 0, cols = 0, ld = 0;
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct Workspace {
+  long long N = 0, Np = 0, Nb = 0;
+  MatDesc mat[M_NONE];
+  double *Lbuf = nullptr, *Ubuf = nullptr, *Wbuf = nullptr, *Dinv = nullptr;
+  double *logdet = nullptr, *alpha = nullptr;
+  Plan potrf, trtri, syrk;
+  std::map<std::pair<int, int>, CUtensorMap> maps;
+};
+
+}  // namespace
+
+struct gpb_handle_s {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  EncodeTiledFn encode = nullptr;
+  long long launches = 0;
+
+  // training problem
+  Workspace ws;       // bound to the training set
+  Workspace tmp;      // scratch problem for the function-level twins (cholesky / invert / solve)
+  int D = 0, DP = 0, n_out = 0;
+  double *dX = nullptr, *dy = nullptr, *dXs = nullptr, *dXsT = nullptr;
+  double* dscal = nullptr;   // device scalars: [0]=nll, [1..] gradient sums
+  double* dpart = nullptr;   // gradient partials
+  size_t dpart_cap = 0;
+  int* dinfo = nullptr;
+  KernelHyp hyp{};
+  bool factor_ready = false;
+
+  // predict chunk state
+  long long Mc = 0;
+  double *dXc = nullptr, *dKsT = nullptr, *dVpart = nullptr, *dmean = nullptr, *dvar = nullptr;
+  Plan pred;
+  long long pred_Nb = 0, pred_Mc = 0;
+
+  // generic staging
+  double* dstage = nullptr;
+  size_t dstage_cap = 0;
+  double* dstage2 = nullptr;
+  size_t dstage2_cap = 0;
+
+  cudaEvent_t ev0[GPB_NUM_STAGES], ev1[GPB_NUM_STAGES];
+  bool ev_used[GPB_NUM_STAGES];
+  double stage_ms[GPB_NUM_STAGES];
+};
+
+namespace {
+
+typedef gpb_handle_s H;
+
+int fail(H* h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  return code;
+}
+
+#define CK(call)                                                                                  \
+  do {                                                                                            \
+    cudaError_t e__ = (call);                                                                     \
+    if (e__ != cudaSuccess)                                                                       \
+      return fail(h, -2, std::string(#call) + ": " + cudaGetErrorString(e__) + " @" + std::to_string(__LINE__)); \
+  } while (0)
+
+long long round_up(long long x, long long m) { return (x + m - 1) / m * m; }
+
+int pick_dp(int D) {
+  const int opts[] = {4, 8, 12, 16, 24, 32};
+  for (int o : opts)
+    if (D <= o) return o;
+  return -1;
+}
+
+int ensure_cap(H* h, double** p, size_t* cap, size_t need) {
+  if (*cap >= need) return 0;
+  if (*p) CK(cudaFree(*p));
+  *p = nullptr;
+  *cap = 0;
+  CK(cudaMalloc(p, need * sizeof(double)));
+  *cap = need;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ tensor maps
+int get_map(H* h, Workspace& w, int mat, int box_rows, CUtensorMap* out) {
+  auto key = std::make_pair(mat, box_rows);
+  auto it = w.maps.find(key);
+  if (it != w.maps.end()) {
+    *out = it->second;
+    return 0;
+  }
+  const MatDesc& m = w.mat[mat];
+  if (!m.ptr) return fail(h, -3, "tensor map requested for an unallocated matrix");
+  CUtensorMap tm;
+  cuuint64_t gdim[2] = {(cuuint64_t)m.cols, (cuuint64_t)m.rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)m.ld * sizeof(double)};
+  cuuint32_t box[2] = {16, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = h->encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, m.ptr, gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(h, -2, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+  w.maps[key] = tm;
+  *out = tm;
+  return 0;
+}
+
+void set_mat(Workspace& w, int id, double* p, long long rows, long long cols, long long ld) {
+  w.mat[id].ptr = p;
+  w.mat[id].rows = rows;
+  w.mat[id].cols = cols;
+  w.mat[id].ld = ld;
+  for (auto it = w.maps.begin(); it != w.maps.end();)
+    it = (it->first.first == id) ? w.maps.erase(it) : std::next(it);
+}
+
+// ------------------------------------------------------------------------------------------------ GEMM launch
+template <int BM, int BN, int WM, int WN, int ST, int EPI, int MINB>
+int launch_cfg(H* h, const CUtensorMap& tA, const CUtensorMap& tB, const GemmTask* tasks, int ntasks,
+               const GemmEpilogue& ep) {
+  auto kern = dgemm_tasks_kernel<BM, BN, WM, WN, ST, EPI, MINB>;
+  constexpr int smem = GemmSmem<BM, BN, ST>::BYTES;
+  static bool configured = false;
+  if (!configured) {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  constexpr int threads = (BM / WM) * (BN / WN) * 32 + 32;
+  kern<<<ntasks, threads, smem, h->stream>>>(tA, tB, tasks, ep);
+  h->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+void cfg_tile(int cfg, int* bm, int* bn) {
+  switch (cfg) {
+    case CFG_128x128: *bm = 128; *bn = 128; break;
+    case CFG_128x64: *bm = 128; *bn = 64; break;
+    default: *bm = 64; *bn = 128; break;
+  }
+}
+
+int launch_gemm(H* h, Workspace& w, int cfg, int epi, int matA, int matB, const GemmTask* d_tasks, int ntasks,
+                const GemmEpilogue& ep) {
+  if (ntasks <= 0) return 0;
+  int bm, bn;
+  cfg_tile(cfg, &bm, &bn);
+  CUtensorMap tA, tB;
+  int rc;
+  if ((rc = get_map(h, w, matA, bm, &tA))) return rc;
+  if ((rc = get_map(h, w, matB, bn, &tB))) return rc;
+  if (epi == EPI_STORE) {
+    switch (cfg) {
+      case CFG_128x128: return launch_cfg<128, 128, 64, 32, 4, EPI_STORE, 1>(h, tA, tB, d_tasks, ntasks, ep);
+      case CFG_128x64: return launch_cfg<128, 64, 32, 32, 4, EPI_STORE, 2>(h, tA, tB, d_tasks, ntasks, ep);
+      default: return launch_cfg<64, 128, 32, 32, 4, EPI_STORE, 2>(h, tA, tB, d_tasks, ntasks, ep);
+    }
+  } else {
+    switch (cfg) {
+      case CFG_128x128: return launch_cfg<128, 128, 64, 32, 4, EPI_COLSQ, 1>(h, tA, tB, d_tasks, ntasks, ep);
+      case CFG_128x64: return launch_cfg<128, 64, 32, 32, 4, EPI_COLSQ, 2>(h, tA, tB, d_tasks, ntasks, ep);
+      default: return fail(h, -1, "no column-norm epilogue for this tile configuration");
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ plans
+int g_cfg_update = CFG_128x64;  // trailing updates / trtri / syrk / predict   (env GPB_CFG_UPDATE)
+int g_outer_blocks = 4;         // outer panel width of the Cholesky in 128-blocks (env GPB_OUTER_BLOCKS)
+
+struct TaskSink {
+  Plan& p;
+  size_t begin;
+  explicit TaskSink(Plan& pl) : p(pl), begin(pl.tasks.size()) {}
+  // emit the tile(s) covering the 128x128 block (c_row, c_col) for the given config
+  void block(int cfg, int a_row, int a_k, int b_row, int b_k, int nk, int c_row, int c_col, int aux = 0) {
+    if (cfg == CFG_128x128) {
+      p.tasks.push_back({a_row, a_k, b_row, b_k, nk, c_row, c_col, aux});
+    } else if (cfg == CFG_128x64) {
+      for (int hlf = 0; hlf < 2; ++hlf)
+        p.tasks.push_back({a_row, a_k, b_row + 64 * hlf, b_k, nk, c_row, c_col + 64 * hlf, aux});
+    } else {
+      for (int hlf = 0; hlf < 2; ++hlf)
+        p.tasks.push_back({a_row + 64 * hlf, a_k, b_row, b_k, nk, c_row + 64 * hlf, c_col, aux});
+    }
+  }
+  void finish(int cfg, int epi, int matA, int matB, int matC, int matCt, double alpha, double beta, bool sort_heavy) {
+    const int n = (int)(p.tasks.size() - begin);
+    if (n == 0) return;
+    if (sort_heavy)
+      std::stable_sort(p.tasks.begin() + begin, p.tasks.end(),
+                       [](const GemmTask& a, const GemmTask& b) { return a.nk > b.nk; });
+    p.launches.push_back({1, 0, cfg, matA, matB, matC, matCt, alpha, beta, begin, n, epi});
+  }
+};
+
+void build_potrf_plan(Workspace& w) {
+  Plan& p = w.potrf;
+  p.clear();
+  const int Nb = (int)w.Nb, OB = g_outer_blocks, cfg = g_cfg_update;
+  const int aug = Nb;  // block-row index of the y^T rows
+  for (int J = 0; J < Nb; J += OB) {
+    const int Je = std::min(J + OB, Nb);
+    for (int k = J; k < Je; ++k) {
+      p.launches.push_back({0, k, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0});
+      {  // panel solve: L_ik = A_ik W_kk^T, in place (64-row tiles own all the columns they read)
+        TaskSink s(p);
+        for (int i = k + 1; i <= aug; ++i) s.block(CFG_64x128, i * 128, k * 128, k * 128, 0, 8, i * 128, k * 128);
+        s.finish(CFG_64x128, EPI_STORE, M_L, M_DINV, M_L, M_NONE, 1.0, 0.0, false);
+      }
+      {  // update the remaining columns of the current outer panel with block column k
+        TaskSink s(p);
+        for (int j = k + 1; j < Je; ++j)
+          for (int i = j; i <= aug; ++i) s.block(cfg, i * 128, k * 128, j * 128, k * 128, 8, i * 128, j * 128);
+        s.finish(cfg, EPI_STORE, M_L, M_L, M_L, M_NONE, -1.0, 1.0, false);
+      }
+    }
+    {  // trailing update with the whole outer panel (K = 128 * panel width)
+      TaskSink s(p);
+      for (int j = Je; j < Nb; ++j)
+        for (int i = j; i <= aug; ++i)
+          s.block(cfg, i * 128, J * 128, j * 128, J * 128, 8 * (Je - J), i * 128, j * 128);
+      s.finish(cfg, EPI_STORE, M_L, M_L, M_L, M_NONE, -1.0, 1.0, false);
+    }
+  }
+}
+
+struct Node {
+  int a, mid, b, height;
+};
+
+int build_nodes(int a, int b, std::vector<Node>& out) {
+  if (b - a <= 1) return 0;
+  const int mid = a + (b - a + 1) / 2;
+  const int hl = build_nodes(a, mid, out), hr = build_nodes(mid, b, out);
+  const int hgt = 1 + std::max(hl, hr);
+  out.push_back({a, mid, b, hgt});
+  return hgt;
+}
+
+void build_trtri_plan(Workspace& w) {
+  Plan& p = w.trtri;
+  p.clear();
+  const int Nb = (int)w.Nb, cfg = g_cfg_update;
+  std::vector<Node> nodes;
+  const int top = build_nodes(0, Nb, nodes);
+  for (int hgt = 1; hgt <= top; ++hgt) {
+    {  // T = U11 L21^T  -> scratch in the strict upper triangle of Lbuf
+      TaskSink s(p);
+      for (const Node& nd : nodes)
+        if (nd.height == hgt)
+          for (int m = nd.a; m < nd.mid; ++m)
+            for (int n = nd.mid; n < nd.b; ++n)
+              s.block(cfg, m * 128, m * 128, n * 128, m * 128, 8 * (nd.mid - m), m * 128, n * 128);
+      s.finish(cfg, EPI_STORE, M_U, M_L, M_L, M_NONE, 1.0, 0.0, true);
+    }
+    {  // U12 = -T W22^T, mirrored into W21
+      TaskSink s(p);
+      for (const Node& nd : nodes)
+        if (nd.height == hgt)
+          for (int m = nd.a; m < nd.mid; ++m)
+            for (int n = nd.mid; n < nd.b; ++n)
+              s.block(cfg, m * 128, nd.mid * 128, n * 128, nd.mid * 128, 8 * (n - nd.mid + 1), m * 128, n * 128);
+      s.finish(cfg, EPI_STORE, M_L, M_W, M_U, M_W, -1.0, 0.0, true);
+    }
+  }
+}
+
+void build_syrk_plan(Workspace& w) {
+  Plan& p = w.syrk;
+  p.clear();
+  const int Nb = (int)w.Nb, cfg = g_cfg_update;
+  TaskSink s(p);
+  for (int i = 0; i < Nb; ++i)
+    for (int j = 0; j <= i; ++j) s.block(cfg, i * 128, i * 128, j * 128, i * 128, 8 * (Nb - i), i * 128, j * 128);
+  s.finish(cfg, EPI_STORE, M_U, M_U, M_L, M_NONE, 1.0, 0.0, true);
+}
+
+int upload_plan(H* h, Plan& p) {
+  if (p.d_tasks) {
+    cudaFree(p.d_tasks);
+    p.d_tasks = nullptr;
+  }
+  if (p.tasks.empty()) return 0;
+  CK(cudaMalloc(&p.d_tasks, p.tasks.size() * sizeof(GemmTask)));
+  CK(cudaMemcpyAsync(p.d_tasks, p.tasks.data(), p.tasks.size() * sizeof(GemmTask), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int run_plan(H* h, Workspace& w, Plan& p, bool factor_diag) {
+  for (const Launch& L : p.launches) {
+    if (L.type == 0) {
+      potrf_diag_kernel<<<1, DIAG_THREADS, DIAG_SMEM, h->stream>>>(w.Lbuf, w.Np, L.k * 128,
+                                                                   w.Dinv + (long long)L.k * 128 * 128, w.logdet + L.k,
+                                                                   h->dinfo, (int)w.N, factor_diag);
+      h->launches++;
+      CK(cudaGetLastError());
+    } else {
+      GemmEpilogue ep;
+      ep.C = w.mat[L.matC].ptr;
+      ep.ldc = w.mat[L.matC].ld;
+      ep.Ct = (L.matCt == M_NONE) ? nullptr : w.mat[L.matCt].ptr;
+      ep.ldct = (L.matCt == M_NONE) ? 0 : w.mat[L.matCt].ld;
+      ep.alpha = L.alpha;
+      ep.beta = L.beta;
+      int rc = launch_gemm(h, w, L.cfg, L.epi, L.matA, L.matB, p.d_tasks + L.task_off, L.ntasks, ep);
+      if (rc) return rc;
+    }
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ workspace
+void free_ws(Workspace& w) {
+  cudaFree(w.Lbuf);
+  cudaFree(w.Ubuf);
+  cudaFree(w.Wbuf);
+  cudaFree(w.Dinv);
+  cudaFree(w.logdet);
+  cudaFree(w.alpha);
+  w.Lbuf = w.Ubuf = w.Wbuf = w.Dinv = w.logdet = w.alpha = nullptr;
+  w.potrf.clear();
+  w.trtri.clear();
+  w.syrk.clear();
+  w.maps.clear();
+  w.N = w.Np = w.Nb = 0;
+}
+
+int resize_ws(H* h, Workspace& w, long long N) {
+  const long long Np = round_up(std::max<long long>(N, 1), 128);
+  w.N = N;
+  if (Np == w.Np) return 0;
+  const long long keepN = N;
+  free_ws(w);
+  w.N = keepN;
+  w.Np = Np;
+  w.Nb = Np / 128;
+  CK(cudaMalloc(&w.Lbuf, (size_t)(Np + 128) * Np * sizeof(double)));
+  CK(cudaMalloc(&w.Dinv, (size_t)Np * 128 * sizeof(double)));
+  CK(cudaMalloc(&w.logdet, (size_t)w.Nb * sizeof(double)));
+  CK(cudaMalloc(&w.alpha, (size_t)128 * Np * sizeof(double)));
+  set_mat(w, M_L, w.Lbuf, Np + 128, Np, Np);
+  set_mat(w, M_DINV, w.Dinv, Np, 128, 128);
+  build_potrf_plan(w);
+  int rc = upload_plan(h, w.potrf);
+  if (rc) return rc;
+  return 0;
+}
+
+int ensure_inverse_buffers(H* h, Workspace& w) {
+  if (w.Ubuf) return 0;
+  const long long Np = w.Np;
+  CK(cudaMalloc(&w.Ubuf, (size_t)Np * Np * sizeof(double)));
+  CK(cudaMalloc(&w.Wbuf, (size_t)Np * Np * sizeof(double)));
+  set_mat(w, M_U, w.Ubuf, Np, Np, Np);
+  set_mat(w, M_W, w.Wbuf, Np, Np, Np);
+  build_trtri_plan(w);
+  build_syrk_plan(w);
+  int rc = upload_plan(h, w.trtri);
+  if (rc) return rc;
+  return upload_plan(h, w.syrk);
+}
+
+// ------------------------------------------------------------------------------------------------ small kernels
+// Seed the diagonal tiles of U (= W_kk^T, upper) and W (= W_kk, lower) from the inverted diagonal blocks.
+__global__ void seed_diag_kernel(const double* __restrict__ Dinv, double* __restrict__ U, double* __restrict__ W,
+                                 long long ld) {
+  const int k = blockIdx.x;
+  const double* src = Dinv + (long long)k * 128 * 128;
+  for (int e = threadIdx.x; e < 128 * 128; e += blockDim.x) {
+    const int i = e >> 7, j = e & 127;
+    const long long off = ((long long)k * 128 + i) * ld + (long long)k * 128 + j;
+    W[off] = src[i * 128 + j];
+    U[off] = src[j * 128 + i];
+  }
+}
+
+// out[o*ldo + i] = sum_{k>=i} U[i][k] * z[o*ldz + k]        (alpha = U z, U upper triangular)
+// or, lower == true:  sum_{k<=i} W[i][k] * z[k*sz_k + o*sz_o]
+__global__ void __launch_bounds__(256) trigemv_kernel(const double* __restrict__ T, long long ld, long long n,
+                                                      bool lower, const double* __restrict__ z, long long sz_k,
+                                                      long long sz_o, int n_out, double* __restrict__ out,
+                                                      long long so_i, long long so_o) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long i = (long long)blockIdx.x * 8 + warp;
+  if (i >= n) return;
+  const long long k0 = lower ? 0 : i, k1 = lower ? i + 1 : n;
+  for (int o = 0; o < n_out; ++o) {
+    double s = 0.0;
+    for (long long k = k0 + lane; k < k1; k += 32) s = fma(T[i * ld + k], z[k * sz_k + o * sz_o], s);
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) out[i * so_i + o * so_o] = s;
+  }
+}
+
+// nll = 0.5 * sum_o ||z_o||^2 + n_out * sum_k logdet[k] + 0.5 * n * n_out * log(2 pi)   (gp_functions.py:147-164)
+__global__ void __launch_bounds__(1024) nll_kernel(const double* __restrict__ z, long long ldz, int n_out, long long n,
+                                                   const double* __restrict__ logdet, int nb, double* __restrict__ out) {
+  __shared__ double sh[1024];
+  double s = 0.0;
+  for (int o = 0; o < n_out; ++o)
+    for (long long k = threadIdx.x; k < n; k += 1024) {
+      const double v = z[o * ldz + k];
+      s = fma(v, v, s);
+    }
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int off = 512; off > 0; off >>= 1) {
+    if ((int)threadIdx.x < off) sh[threadIdx.x] += sh[threadIdx.x + off];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    double ld = 0.0;
+    for (int k = 0; k < nb; ++k) ld += logdet[k];
+    out[0] = 0.5 * sh[0] + n_out * ld + 0.5 * (double)n * n_out * 1.8378770664093454835606594728112;
+  }
+}
+
+// dst (rows x cols, ldd) <- padded copy of src (n x n, lds): identity outside, optionally lower only.
+__global__ void pad_copy_kernel(const double* __restrict__ src, long long n, long long lds, double* __restrict__ dst,
+                                long long np, long long ldd) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= np * np) return;
+  const long long i = e / np, j = e % np;
+  double v = (i == j) ? 1.0 : 0.0;
+  if (i < n && j < n) v = src[i * lds + j];
+  dst[i * ldd + j] = v;
+}
+
+// mode 0: out = lower(src) with zero upper (Cholesky factor); mode 1: out = symmetric from lower (K^-1)
+__global__ void unpack_kernel(const double* __restrict__ src, long long lds, long long n, int mode,
+                              double* __restrict__ out) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n * n) return;
+  const long long i = e / n, j = e % n;
+  double v;
+  if (mode == 0) v = (j <= i) ? src[i * lds + j] : 0.0;
+  else v = (j <= i) ? src[i * lds + j] : src[j * lds + i];
+  out[e] = v;
+}
+
+__global__ void zero_aug_kernel(double* __restrict__ L, long long np) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < 128 * np) L[np * np + e] = 0.0;
+}
+
+// argmax with lowest-index tie break (np.argmax semantics, NaN-free input assumed)
+__global__ void __launch_bounds__(1024) argmax_kernel(const double* __restrict__ v, long long n, double* __restrict__ oval,
+                                                      long long* __restrict__ oidx) {
+  __shared__ double sv[1024];
+  __shared__ long long si[1024];
+  double bv = -INFINITY;
+  long long bi = 0x7fffffffffffffffLL;
+  for (long long k = threadIdx.x; k < n; k += 1024) {
+    const double x = v[k];
+    if (x > bv || (x == bv && k < bi)) {
+      bv = x;
+      bi = k;
+    }
+  }
+  sv[threadIdx.x] = bv;
+  si[threadIdx.x] = bi;
+  __syncthreads();
+  for (int off = 512; off > 0; off >>= 1) {
+    if ((int)threadIdx.x < off) {
+      const double x = sv[threadIdx.x + off];
+      const long long k = si[threadIdx.x + off];
+      if (x > sv[threadIdx.x] || (x == sv[threadIdx.x] && k < si[threadIdx.x])) {
+        sv[threadIdx.x] = x;
+        si[threadIdx.x] = k;
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    oval[0] = sv[0];
+    oidx[0] = si[0];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ helpers
+void stage_begin(H* h, int s) {
+  cudaEventRecord(h->ev0[s], h->stream);
+  h->ev_used[s] = true;
+}
+void stage_end(H* h, int s) { cudaEventRecord(h->ev1[s], h->stream); }
+void stages_reset(H* h) {
+  for (int s = 0; s < GPB_NUM_STAGES; ++s) {
+    h->ev_used[s] = false;
+    h->stage_ms[s] = 0.0;
+  }
+}
+void stages_collect(H* h) {
+  for (int s = 0; s < GPB_NUM_STAGES; ++s)
+    if (h->ev_used[s]) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, h->ev0[s], h->ev1[s]) == cudaSuccess) h->stage_ms[s] = ms;
+    }
+}
+
+int set_hyp(H* h, int kind, const double* theta, int n_ell) {
+  if (kind != GPB_KERNEL_RBF && kind != GPB_KERNEL_MATERN52) return fail(h, -1, "unknown kernel kind");
+  if (!(n_ell == 1 || n_ell == h->D)) return fail(h, -1, "n_ell must be 1 or the input dimension");
+  h->hyp.kind = kind;
+  h->hyp.D = h->D;
+  h->hyp.n_ell = n_ell;
+  for (int d = 0; d < n_ell; ++d) h->hyp.ell[d] = theta[d];
+  h->hyp.sf = theta[n_ell];
+  h->hyp.sn = theta[n_ell + 1];
+  return 0;
+}
+
+template <int KIND>
+int assemble_dispatch(H* h, Workspace& w) {
+  const double sf2 = h->hyp.sf * h->hyp.sf, sn2 = h->hyp.sn * h->hyp.sn;
+  dim3 grid((unsigned)(w.Np / AS_TN), (unsigned)(w.Np / AS_TM));
+#define GPB_AS(DPV)                                                                                              \
+  case DPV:                                                                                                      \
+    assemble_sym_kernel<KIND, DPV><<<grid, AS_THREADS, 0, h->stream>>>(h->dXs, h->dXsT, w.Np, (int)w.N, (int)w.Np, \
+                                                                      sf2, sn2, w.Lbuf, w.Np);                  \
+    break;
+  switch (h->DP) {
+    GPB_AS(4) GPB_AS(8) GPB_AS(12) GPB_AS(16) GPB_AS(24) GPB_AS(32)
+    default: return fail(h, -1, "unsupported input dimension");
+  }
+#undef GPB_AS
+  h->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+template <int KIND>
+int contract_dispatch(H* h, Workspace& w, dim3 grid) {
+  const double sf2 = h->hyp.sf * h->hyp.sf;
+#define GPB_GC(DPV)                                                                                               \
+  case DPV:                                                                                                       \
+    grad_contract_kernel<KIND, DPV><<<grid, AS_THREADS, 0, h->stream>>>(h->dXs, h->dXsT, w.Np, (int)w.N, sf2, w.Lbuf, \
+                                                                       w.Np, w.alpha, w.Np, h->n_out, h->dpart); \
+    break;
+  switch (h->DP) {
+    GPB_GC(4) GPB_GC(8) GPB_GC(12) GPB_GC(16) GPB_GC(24) GPB_GC(32)
+    default: return fail(h, -1, "unsupported input dimension");
+  }
+#undef GPB_GC
+  h->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+template <int KIND>
+int cross_dispatch(H* h, Workspace& w, const double* dXc, long long mc, double* KsT, long long ldk, double* mean) {
+  const unsigned grid = (unsigned)((mc + CR_ROWS - 1) / CR_ROWS);
+#define GPB_CM(DPV)                                                                                                  \
+  case DPV:                                                                                                          \
+    cross_mean_kernel<KIND, DPV><<<grid, AS_THREADS, 0, h->stream>>>(dXc, (int)mc, h->D, h->hyp, h->dXsT, w.Np, (int)w.N, \
+                                                                    (int)w.Np, w.alpha, w.Np, h->n_out, KsT, ldk, mean); \
+    break;
+  switch (h->DP) {
+    GPB_CM(4) GPB_CM(8) GPB_CM(12) GPB_CM(16) GPB_CM(24) GPB_CM(32)
+    default: return fail(h, -1, "unsupported input dimension");
+  }
+#undef GPB_CM
+  h->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// Stages shared by gpb_nll and gpb_factorize: K(theta) -> L, z, logdet.
+int assemble_and_factor(H* h) {
+  Workspace& w = h->ws;
+  stage_begin(h, GPB_STAGE_ASSEMBLE);
+  CK(cudaMemsetAsync(h->dinfo, 0, sizeof(int), h->stream));
+  {
+    const long long tot = w.Np * h->DP;
+    prescale_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(h->dX, (int)w.N, h->hyp, h->DP, h->dXs,
+                                                                        h->dXsT, w.Np, (int)w.Np);
+    h->launches++;
+  }
+  int rc = (h->hyp.kind == KIND_RBF) ? assemble_dispatch<KIND_RBF>(h, w) : assemble_dispatch<KIND_MATERN52>(h, w);
+  if (rc) return rc;
+  {
+    const long long tot = 128 * w.Np;
+    fill_aug_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(h->dy, (int)w.N, h->n_out, (int)w.Np, w.Lbuf,
+                                                                        w.Np);
+    h->launches++;
+  }
+  CK(cudaGetLastError());
+  stage_end(h, GPB_STAGE_ASSEMBLE);
+  stage_begin(h, GPB_STAGE_POTRF);
+  rc = run_plan(h, w, w.potrf, true);
+  if (rc) return rc;
+  stage_end(h, GPB_STAGE_POTRF);
+  return 0;
+}
+
+// U = L^-T, W = L^-1 from L and the inverted diagonal blocks.
+int triangular_inverse(H* h, Workspace& w) {
+  int rc = ensure_inverse_buffers(h, w);
+  if (rc) return rc;
+  seed_diag_kernel<<<(unsigned)w.Nb, 256, 0, h->stream>>>(w.Dinv, w.Ubuf, w.Wbuf, w.Np);
+  h->launches++;
+  CK(cudaGetLastError());
+  return run_plan(h, w, w.trtri, false);
+}
+
+int compute_alpha(H* h, Workspace& w, int n_out) {
+  // alpha_o = U z_o with z_o = row o of the y^T block of Lbuf
+  trigemv_kernel<<<(unsigned)((w.Np + 7) / 8), 256, 0, h->stream>>>(w.Ubuf, w.Np, w.Np, false, w.Lbuf + w.Np * w.Np, 1,
+                                                                    w.Np, n_out, w.alpha, 1, w.Np);
+  h->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int check_info(H* h) {
+  int info = 0;
+  CK(cudaMemcpyAsync(&info, h->dinfo, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (info > 0) {
+    h->err = "matrix is not positive definite: non-positive pivot at row " + std::to_string(info);
+    return info;
+  }
+  return 0;
+}
+
+int need_train(H* h) {
+  if (!h) return -1;
+  if (h->ws.N <= 0 || !h->dX) return fail(h, -3, "gpb_set_train has not been called");
+  return 0;
+}
+
+int load_matrix_into_L(H* h, Workspace& w, const double* A, long long n) {
+  // stage A on the device if it is a host pointer, then pad-copy into Lbuf
+  int rc = ensure_cap(h, &h->dstage, &h->dstage_cap, (size_t)n * n);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(h->dstage, A, (size_t)n * n * sizeof(double), cudaMemcpyDefault, h->stream));
+  const long long tot = w.Np * w.Np;
+  pad_copy_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(h->dstage, n, n, w.Lbuf, w.Np, w.Np);
+  zero_aug_kernel<<<(unsigned)((128 * w.Np + 255) / 256), 256, 0, h->stream>>>(w.Lbuf, w.Np);
+  h->launches += 2;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int invert_diag_blocks(H* h, Workspace& w) {
+  potrf_diag_kernel<<<(unsigned)w.Nb, DIAG_THREADS, DIAG_SMEM, h->stream>>>(w.Lbuf, w.Np, 0, w.Dinv, w.logdet, h->dinfo,
+                                                                           (int)w.N, false);
+  h->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+// ================================================================================================ C ABI
+extern "C" {
+
+int gpb_version(void) { return 100; }
+
+int gpb_create(int device, gpb_handle_t* out) {
+  if (!out) return -1;
+  *out = nullptr;
+  H* h = new H();
+  h->device = device;
+  if (cudaSetDevice(device) != cudaSuccess) {
+    delete h;
+    return -2;
+  }
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete h;
+    return -2;
+  }
+  cudaDriverEntryPointQueryResult qres;
+  void* fn = nullptr;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+    delete h;
+    return -2;
+  }
+  h->encode = reinterpret_cast<EncodeTiledFn>(fn);
+  if (cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM) != cudaSuccess) {
+    delete h;
+    return -2;
+  }
+  for (int s = 0; s < GPB_NUM_STAGES; ++s) {
+    cudaEventCreate(&h->ev0[s]);
+    cudaEventCreate(&h->ev1[s]);
+  }
+  stages_reset(h);
+  cudaMalloc(&h->dscal, 64 * sizeof(double));
+  cudaMalloc(&h->dinfo, sizeof(int));
+  if (const char* e = getenv("GPB_CFG_UPDATE")) g_cfg_update = std::max(0, std::min(1, atoi(e)));
+  if (const char* e = getenv("GPB_OUTER_BLOCKS")) g_outer_blocks = std::max(1, std::min(16, atoi(e)));
+  *out = h;
+  return 0;
+}
+
+int gpb_destroy(gpb_handle_t h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  free_ws(h->ws);
+  free_ws(h->tmp);
+  h->pred.clear();
+  cudaFree(h->dX);
+  cudaFree(h->dy);
+  cudaFree(h->dXs);
+  cudaFree(h->dXsT);
+  cudaFree(h->dscal);
+  cudaFree(h->dpart);
+  cudaFree(h->dinfo);
+  cudaFree(h->dXc);
+  cudaFree(h->dKsT);
+  cudaFree(h->dVpart);
+  cudaFree(h->dmean);
+  cudaFree(h->dvar);
+  cudaFree(h->dstage);
+  cudaFree(h->dstage2);
+  for (int s = 0; s < GPB_NUM_STAGES; ++s) {
+    cudaEventDestroy(h->ev0[s]);
+    cudaEventDestroy(h->ev1[s]);
+  }
+  cudaStreamDestroy(h->stream);
+  delete h;
+  return 0;
+}
+
+const char* gpb_error_string(gpb_handle_t h) { return h ? h->err.c_str() : "null handle"; }
+
+long long gpb_launch_count(gpb_handle_t h) { return h ? h->launches : 0; }
+
+int gpb_stage_ms(gpb_handle_t h, double* out) {
+  if (!h || !out) return -1;
+  for (int s = 0; s < GPB_NUM_STAGES; ++s) out[s] = h->stage_ms[s];
+  return 0;
+}
+
+int gpb_set_train(gpb_handle_t h, const double* X, const double* y, long long n, int d, int n_out) {
+  if (!h || !X || !y || n < 1 || d < 1 || n_out < 1) return fail(h, -1, "gpb_set_train: bad argument");
+  if (d > MAX_D) return fail(h, -1, "gpb_set_train: input dimension above 32 is not supported");
+  if (n_out > 128) return fail(h, -1, "gpb_set_train: more than 128 outputs are not supported");
+  CK(cudaSetDevice(h->device));
+  const long long oldNp = h->ws.Np;
+  const int oldDP = h->DP;
+  int rc = resize_ws(h, h->ws, n);
+  if (rc) return rc;
+  h->D = d;
+  h->DP = pick_dp(d);
+  h->n_out = n_out;
+  const long long Np = h->ws.Np;
+  if (Np != oldNp || h->DP != oldDP || !h->dX) {
+    cudaFree(h->dX);
+    cudaFree(h->dy);
+    cudaFree(h->dXs);
+    cudaFree(h->dXsT);
+    h->dX = h->dy = h->dXs = h->dXsT = nullptr;
+    CK(cudaMalloc(&h->dX, (size_t)Np * MAX_D * sizeof(double)));
+    CK(cudaMalloc(&h->dy, (size_t)Np * 128 * sizeof(double)));
+    CK(cudaMalloc(&h->dXs, (size_t)Np * h->DP * sizeof(double)));
+    CK(cudaMalloc(&h->dXsT, (size_t)Np * h->DP * sizeof(double)));
+  }
+  CK(cudaMemcpyAsync(h->dX, X, (size_t)n * d * sizeof(double), cudaMemcpyDefault, h->stream));
+  CK(cudaMemcpyAsync(h->dy, y, (size_t)n * n_out * sizeof(double), cudaMemcpyDefault, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->factor_ready = false;
+  return 0;
+}
+
+int gpb_nll(gpb_handle_t h, int kind, const double* theta, int n_ell, int want_grad, double* nll, double* grad) {
+  int rc = need_train(h);
+  if (rc) return rc;
+  if (!theta || !nll || (want_grad && !grad)) return fail(h, -1, "gpb_nll: null argument");
+  CK(cudaSetDevice(h->device));
+  if ((rc = set_hyp(h, kind, theta, n_ell))) return rc;
+  Workspace& w = h->ws;
+  h->factor_ready = false;
+  stages_reset(h);
+  stage_begin(h, GPB_STAGE_TOTAL);
+  if ((rc = assemble_and_factor(h))) return rc;
+  nll_kernel<<<1, 1024, 0, h->stream>>>(w.Lbuf + w.Np * w.Np, w.Np, h->n_out, w.Np, w.logdet, (int)w.Nb, h->dscal);
+  h->launches++;
+  const int P = n_ell + 2, width = h->DP + 2;
+  if (want_grad) {
+    stage_begin(h, GPB_STAGE_TRTRI);
+    if ((rc = triangular_inverse(h, w))) return rc;
+    stage_end(h, GPB_STAGE_TRTRI);
+    stage_begin(h, GPB_STAGE_GRAD);
+    if ((rc = compute_alpha(h, w, h->n_out))) return rc;
+    stage_end(h, GPB_STAGE_GRAD);
+    stage_begin(h, GPB_STAGE_SYRK);
+    if ((rc = run_plan(h, w, w.syrk, false))) return rc;
+    stage_end(h, GPB_STAGE_SYRK);
+    cudaEvent_t g0, g1;  // the GRAD stage has two pieces; time the second with its own pair and add
+    cudaEventCreate(&g0);
+    cudaEventCreate(&g1);
+    cudaEventRecord(g0, h->stream);
+    dim3 grid((unsigned)(w.Np / AS_TN), (unsigned)(w.Np / AS_TM));
+    const size_t ncta = (size_t)grid.x * grid.y;
+    if ((rc = ensure_cap(h, &h->dpart, &h->dpart_cap, ncta * width))) return rc;
+    rc = (kind == KIND_RBF) ? contract_dispatch<KIND_RBF>(h, w, grid) : contract_dispatch<KIND_MATERN52>(h, w, grid);
+    if (rc) return rc;
+    reduce_partials_kernel<<<width, 256, 0, h->stream>>>(h->dpart, (int)ncta, width, h->dscal + 1);
+    h->launches++;
+    cudaEventRecord(g1, h->stream);
+    stage_end(h, GPB_STAGE_TOTAL);
+    double host[64];
+    CK(cudaMemcpyAsync(host, h->dscal, (1 + width) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if ((rc = check_info(h))) {
+      cudaEventDestroy(g0);
+      cudaEventDestroy(g1);
+      return rc;
+    }
+    stages_collect(h);
+    float gms = 0.f;
+    cudaEventElapsedTime(&gms, g0, g1);
+    h->stage_ms[GPB_STAGE_GRAD] += gms;
+    cudaEventDestroy(g0);
+    cudaEventDestroy(g1);
+    *nll = host[0];
+    // dnll_p = 0.5 * sum_ij A_ij dK_ij,p   (gp_functions.py:180) with the per-parameter factors of
+    // python_kernels.py:49-55 pulled out of the sums.
+    const double* acc = host + 1;
+    if (n_ell == 1) {
+      double s = 0.0;
+      for (int d = 0; d < h->D; ++d) s += acc[d];
+      grad[0] = 0.5 * s / h->hyp.ell[0];
+    } else {
+      for (int d = 0; d < h->D; ++d) grad[d] = 0.5 * acc[d] / h->hyp.ell[d];
+    }
+    grad[P - 2] = 0.5 * (2.0 / h->hyp.sf) * acc[h->DP];
+    grad[P - 1] = 0.5 * (2.0 * h->hyp.sn) * acc[h->DP + 1];
+    h->factor_ready = true;  // W and alpha are valid for this theta
+    return 0;
+  }
+  stage_end(h, GPB_STAGE_TOTAL);
+  double host0 = 0.0;
+  CK(cudaMemcpyAsync(&host0, h->dscal, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if ((rc = check_info(h))) return rc;
+  stages_collect(h);
+  *nll = host0;
+  return 0;
+}
+
+int gpb_factorize(gpb_handle_t h, int kind, const double* theta, int n_ell) {
+  int rc = need_train(h);
+  if (rc) return rc;
+  if (!theta) return fail(h, -1, "gpb_factorize: null argument");
+  CK(cudaSetDevice(h->device));
+  if ((rc = set_hyp(h, kind, theta, n_ell))) return rc;
+  Workspace& w = h->ws;
+  h->factor_ready = false;
+  stages_reset(h);
+  stage_begin(h, GPB_STAGE_TOTAL);
+  if ((rc = assemble_and_factor(h))) return rc;
+  stage_begin(h, GPB_STAGE_TRTRI);
+  if ((rc = triangular_inverse(h, w))) return rc;
+  stage_end(h, GPB_STAGE_TRTRI);
+  stage_begin(h, GPB_STAGE_GRAD);
+  if ((rc = compute_alpha(h, w, h->n_out))) return rc;
+  stage_end(h, GPB_STAGE_GRAD);
+  stage_end(h, GPB_STAGE_TOTAL);
+  if ((rc = check_info(h))) return rc;
+  stages_collect(h);
+  h->factor_ready = true;
+  return 0;
+}
+
+int gpb_predict(gpb_handle_t h, const double* Xc, long long M, int add_data_variance, double* mean, double* var) {
+  int rc = need_train(h);
+  if (rc) return rc;
+  if (!h->factor_ready) return fail(h, -3, "gpb_predict: call gpb_factorize (or gpb_nll with gradient) first");
+  if (!Xc || M < 0) return fail(h, -1, "gpb_predict: bad argument");
+  if (M == 0) return 0;
+  CK(cudaSetDevice(h->device));
+  Workspace& w = h->ws;
+  const int cfg = g_cfg_update;
+  int bm, bn;
+  cfg_tile(cfg, &bm, &bn);
+  // chunk of candidates: K*^T chunk (Mc x Np doubles) bounded to ~2 GiB
+  long long Mc = ((1LL << 28) / w.Np) / 128 * 128;
+  Mc = std::max<long long>(128, std::min<long long>(Mc, 65536));
+  Mc = std::min(Mc, round_up(M, 128));
+  if (Mc != h->pred_Mc || w.Nb != h->pred_Nb) {
+    cudaFree(h->dXc);
+    cudaFree(h->dKsT);
+    cudaFree(h->dVpart);
+    cudaFree(h->dmean);
+    cudaFree(h->dvar);
+    h->dXc = h->dKsT = h->dVpart = h->dmean = h->dvar = nullptr;
+    h->pred_Mc = h->pred_Nb = 0;
+    CK(cudaMalloc(&h->dXc, (size_t)Mc * h->D * sizeof(double)));
+    CK(cudaMalloc(&h->dKsT, (size_t)Mc * w.Np * sizeof(double)));
+    CK(cudaMalloc(&h->dVpart, (size_t)w.Nb * Mc * sizeof(double)));
+    CK(cudaMalloc(&h->dmean, (size_t)Mc * 128 * sizeof(double)));
+    CK(cudaMalloc(&h->dvar, (size_t)Mc * sizeof(double)));
+    // candidate rows beyond the last real one are never written by cross_mean_kernel: keep them finite
+    CK(cudaMemsetAsync(h->dKsT, 0, (size_t)Mc * w.Np * sizeof(double), h->stream));
+    h->pred.clear();
+    TaskSink s(h->pred);
+    for (int mt = (int)w.Nb - 1; mt >= 0; --mt)
+      for (long long ct = 0; ct < Mc / 128; ++ct) s.block(cfg, mt * 128, 0, (int)ct * 128, 0, 8 * (mt + 1), 0, (int)ct * 128, mt);
+    s.finish(cfg, EPI_COLSQ, M_W, M_KST, M_PART, M_NONE, 1.0, 0.0, false);
+    if ((rc = upload_plan(h, h->pred))) return rc;
+    h->pred_Mc = Mc;
+    h->pred_Nb = w.Nb;
+  }
+  set_mat(w, M_KST, h->dKsT, Mc, w.Np, w.Np);
+  set_mat(w, M_PART, h->dVpart, w.Nb, Mc, Mc);
+  const double sf2 = h->hyp.sf * h->hyp.sf;
+  const double add = add_data_variance ? h->hyp.sn * h->hyp.sn : 0.0;
+  stages_reset(h);
+  stage_begin(h, GPB_STAGE_TOTAL);
+  double cross_ms = 0.0, var_ms = 0.0;
+  cudaEvent_t e0, e1, e2;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  cudaEventCreate(&e2);
+  for (long long c0 = 0; c0 < M; c0 += Mc) {
+    const long long mc = std::min(Mc, M - c0);
+    CK(cudaMemcpyAsync(h->dXc, Xc + c0 * h->D, (size_t)mc * h->D * sizeof(double), cudaMemcpyDefault, h->stream));
+    cudaEventRecord(e0, h->stream);
+    rc = (h->hyp.kind == KIND_RBF)
+             ? cross_dispatch<KIND_RBF>(h, w, h->dXc, mc, var ? h->dKsT : nullptr, w.Np, mean ? h->dmean : nullptr)
+             : cross_dispatch<KIND_MATERN52>(h, w, h->dXc, mc, var ? h->dKsT : nullptr, w.Np, mean ? h->dmean : nullptr);
+    if (rc) return rc;
+    cudaEventRecord(e1, h->stream);
+    if (var) {
+      // only the candidate tiles that hold real rows
+      const long long ctiles = (mc + 127) / 128;
+      const Launch& L = h->pred.launches[0];
+      const int per_block = (cfg == CFG_128x128) ? 1 : 2;
+      GemmEpilogue ep;
+      ep.C = h->dVpart;
+      ep.ldc = Mc;
+      ep.Ct = nullptr;
+      ep.ldct = 0;
+      ep.alpha = 1.0;
+      ep.beta = 0.0;
+      if (ctiles == Mc / 128) {
+        if ((rc = launch_gemm(h, w, cfg, EPI_COLSQ, M_W, M_KST, h->pred.d_tasks + L.task_off, L.ntasks, ep))) return rc;
+      } else {
+        // ragged last chunk: tasks are ordered (mt desc, ct asc); launch the first ctiles of every mt row
+        for (int r = 0; r < (int)w.Nb; ++r) {
+          const GemmTask* base = h->pred.d_tasks + L.task_off + (size_t)r * (Mc / 128) * per_block;
+          if ((rc = launch_gemm(h, w, cfg, EPI_COLSQ, M_W, M_KST, base, (int)ctiles * per_block, ep))) return rc;
+        }
+      }
+      finish_variance_kernel<<<(unsigned)((mc + 255) / 256), 256, 0, h->stream>>>(h->dVpart, Mc, (int)w.Nb, (int)mc, sf2,
+                                                                                add, add_data_variance == 2, h->dvar);
+      h->launches++;
+      CK(cudaGetLastError());
+    }
+    cudaEventRecord(e2, h->stream);
+    if (mean)
+      CK(cudaMemcpyAsync(mean + c0 * h->n_out, h->dmean, (size_t)mc * h->n_out * sizeof(double), cudaMemcpyDefault,
+                         h->stream));
+    if (var) CK(cudaMemcpyAsync(var + c0, h->dvar, (size_t)mc * sizeof(double), cudaMemcpyDefault, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    float a = 0.f, b = 0.f;
+    cudaEventElapsedTime(&a, e0, e1);
+    cudaEventElapsedTime(&b, e1, e2);
+    cross_ms += a;
+    var_ms += b;
+  }
+  stage_end(h, GPB_STAGE_TOTAL);
+  CK(cudaStreamSynchronize(h->stream));
+  stages_collect(h);
+  h->stage_ms[GPB_STAGE_CROSS] = cross_ms;
+  h->stage_ms[GPB_STAGE_VAR] = var_ms;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaEventDestroy(e2);
+  return 0;
+}
+
+int gpb_argmax(gpb_handle_t h, const double* v, long long M, long long* idx, double* val) {
+  if (!h || !v || M < 1 || !idx) return fail(h, -1, "gpb_argmax: bad argument");
+  CK(cudaSetDevice(h->device));
+  int rc = ensure_cap(h, &h->dstage, &h->dstage_cap, (size_t)M + 2);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(h->dstage + 2, v, (size_t)M * sizeof(double), cudaMemcpyDefault, h->stream));
+  argmax_kernel<<<1, 1024, 0, h->stream>>>(h->dstage + 2, M, h->dstage, reinterpret_cast<long long*>(h->dstage + 1));
+  h->launches++;
+  CK(cudaGetLastError());
+  double hv[2];
+  CK(cudaMemcpyAsync(hv, h->dstage, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (val) *val = hv[0];
+  memcpy(idx, &hv[1], sizeof(long long));
+  return 0;
+}
+
+int gpb_kernel_matrix(gpb_handle_t h, int kind, const double* Xa, long long na, const double* Xb, long long nb, int d,
+                      const double* ell, int n_ell, double sigma_f, double sigma_n, double* K, double* dK) {
+  if (!h || !Xa || !Xb || !ell || !K || na < 1 || nb < 1 || d < 1 || d > MAX_D)
+    return fail(h, -1, "gpb_kernel_matrix: bad argument");
+  if (!(n_ell == 1 || n_ell == d)) return fail(h, -1, "gpb_kernel_matrix: n_ell must be 1 or d");
+  if (kind != GPB_KERNEL_RBF && kind != GPB_KERNEL_MATERN52) return fail(h, -1, "unknown kernel kind");
+  CK(cudaSetDevice(h->device));
+  KernelHyp hy{};
+  hy.kind = kind;
+  hy.D = d;
+  hy.n_ell = n_ell;
+  for (int i = 0; i < n_ell; ++i) hy.ell[i] = ell[i];
+  hy.sf = sigma_f;
+  hy.sn = sigma_n;
+  const int P = n_ell + 2;
+  const size_t nin = (size_t)(na + nb) * d;
+  const size_t nK = (size_t)na * nb, ndK = dK ? nK * P : 0;
+  int rc = ensure_cap(h, &h->dstage, &h->dstage_cap, nin);
+  if (rc) return rc;
+  if ((rc = ensure_cap(h, &h->dstage2, &h->dstage2_cap, nK + ndK))) return rc;
+  double* dXa = h->dstage;
+  double* dXb = h->dstage + (size_t)na * d;
+  CK(cudaMemcpyAsync(dXa, Xa, (size_t)na * d * sizeof(double), cudaMemcpyDefault, h->stream));
+  CK(cudaMemcpyAsync(dXb, Xb, (size_t)nb * d * sizeof(double), cudaMemcpyDefault, h->stream));
+  double* dKo = h->dstage2;
+  double* ddK = dK ? h->dstage2 + nK : nullptr;
+  dim3 grid((unsigned)((nb + 63) / 64), (unsigned)((na + 3) / 4));
+  const size_t smem = dK ? (size_t)4 * 64 * P * sizeof(double) : 0;
+  if (kind == KIND_RBF)
+    kernel_matrix_kernel<KIND_RBF><<<grid, 256, smem, h->stream>>>(dXa, (int)na, dXb, (int)nb, hy, dKo, ddK);
+  else
+    kernel_matrix_kernel<KIND_MATERN52><<<grid, 256, smem, h->stream>>>(dXa, (int)na, dXb, (int)nb, hy, dKo, ddK);
+  h->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(K, dKo, nK * sizeof(double), cudaMemcpyDefault, h->stream));
+  if (dK) CK(cudaMemcpyAsync(dK, ddK, ndK * sizeof(double), cudaMemcpyDefault, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int gpb_cholesky(gpb_handle_t h, const double* A, long long n, double* L) {
+  if (!h || !A || !L || n < 1) return fail(h, -1, "gpb_cholesky: bad argument");
+  CK(cudaSetDevice(h->device));
+  Workspace& w = h->tmp;
+  int rc = resize_ws(h, w, n);
+  if (rc) return rc;
+  CK(cudaMemsetAsync(h->dinfo, 0, sizeof(int), h->stream));
+  if ((rc = load_matrix_into_L(h, w, A, n))) return rc;
+  if ((rc = run_plan(h, w, w.potrf, true))) return rc;
+  if ((rc = check_info(h))) return rc;
+  if ((rc = ensure_cap(h, &h->dstage2, &h->dstage2_cap, (size_t)n * n))) return rc;
+  unpack_kernel<<<(unsigned)((n * n + 255) / 256), 256, 0, h->stream>>>(w.Lbuf, w.Np, n, 0, h->dstage2);
+  h->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(L, h->dstage2, (size_t)n * n * sizeof(double), cudaMemcpyDefault, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int gpb_invert_cholesky(gpb_handle_t h, const double* L, long long n, double* Kinv) {
+  if (!h || !L || !Kinv || n < 1) return fail(h, -1, "gpb_invert_cholesky: bad argument");
+  CK(cudaSetDevice(h->device));
+  Workspace& w = h->tmp;
+  int rc = resize_ws(h, w, n);
+  if (rc) return rc;
+  CK(cudaMemsetAsync(h->dinfo, 0, sizeof(int), h->stream));
+  if ((rc = load_matrix_into_L(h, w, L, n))) return rc;
+  if ((rc = invert_diag_blocks(h, w))) return rc;
+  if ((rc = triangular_inverse(h, w))) return rc;
+  if ((rc = run_plan(h, w, w.syrk, false))) return rc;
+  if ((rc = ensure_cap(h, &h->dstage2, &h->dstage2_cap, (size_t)n * n))) return rc;
+  unpack_kernel<<<(unsigned)((n * n + 255) / 256), 256, 0, h->stream>>>(w.Lbuf, w.Np, n, 1, h->dstage2);
+  h->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(Kinv, h->dstage2, (size_t)n * n * sizeof(double), cudaMemcpyDefault, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int gpb_solve_cholesky(gpb_handle_t h, const double* L, long long n, const double* b, int nrhs, double* x) {
+  if (!h || !L || !b || !x || n < 1 || nrhs < 1 || nrhs > 128) return fail(h, -1, "gpb_solve_cholesky: bad argument");
+  CK(cudaSetDevice(h->device));
+  Workspace& w = h->tmp;
+  int rc = resize_ws(h, w, n);
+  if (rc) return rc;
+  CK(cudaMemsetAsync(h->dinfo, 0, sizeof(int), h->stream));
+  if ((rc = load_matrix_into_L(h, w, L, n))) return rc;
+  if ((rc = invert_diag_blocks(h, w))) return rc;
+  if ((rc = triangular_inverse(h, w))) return rc;
+  // z = W b ; x = U z.  b and x are (n, nrhs) row-major; z lives in w.alpha as (nrhs, Np).
+  if ((rc = ensure_cap(h, &h->dstage2, &h->dstage2_cap, (size_t)2 * n * nrhs))) return rc;
+  double* db = h->dstage2;
+  double* dx = h->dstage2 + (size_t)n * nrhs;
+  CK(cudaMemcpyAsync(db, b, (size_t)n * nrhs * sizeof(double), cudaMemcpyDefault, h->stream));
+  trigemv_kernel<<<(unsigned)((n + 7) / 8), 256, 0, h->stream>>>(w.Wbuf, w.Np, n, true, db, nrhs, 1, nrhs, w.alpha, 1,
+                                                                 w.Np);
+  trigemv_kernel<<<(unsigned)((n + 7) / 8), 256, 0, h->stream>>>(w.Ubuf, w.Np, n, false, w.alpha, 1, w.Np, nrhs, dx, nrhs,
+                                                                 1);
+  h->launches += 2;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(x, dx, (size_t)n * nrhs * sizeof(double), cudaMemcpyDefault, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int gpb_debug_gemm(gpb_handle_t h, const double* A, const double* B, double* C, long long M, long long N, long long K,
+                   int cfg, int reps, double* ms) {
+  if (!h || !A || !B || !C || M % 128 || N % 128 || K % 128 || cfg < 0 || cfg >= NUM_CFG || reps < 1)
+    return fail(h, -1, "gpb_debug_gemm: bad argument");
+  CK(cudaSetDevice(h->device));
+  Workspace& w = h->tmp;
+  set_mat(w, M_DBG_A, const_cast<double*>(A), M, K, K);
+  set_mat(w, M_DBG_B, const_cast<double*>(B), N, K, K);
+  Plan p;
+  TaskSink s(p);
+  for (long long i = 0; i < M / 128; ++i)
+    for (long long j = 0; j < N / 128; ++j)
+      s.block(cfg, (int)i * 128, 0, (int)j * 128, 0, (int)(K / 16), (int)i * 128, (int)j * 128);
+  s.finish(cfg, EPI_STORE, M_DBG_A, M_DBG_B, M_DBG_C, M_NONE, 1.0, 0.0, false);
+  int rc = upload_plan(h, p);
+  if (rc) return rc;
+  GemmEpilogue ep;
+  ep.C = C;
+  ep.ldc = N;
+  ep.Ct = nullptr;
+  ep.ldct = 0;
+  ep.alpha = 1.0;
+  ep.beta = 0.0;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  if ((rc = launch_gemm(h, w, cfg, EPI_STORE, M_DBG_A, M_DBG_B, p.d_tasks, (int)p.tasks.size(), ep))) return rc;
+  cudaEventRecord(e0, h->stream);
+  for (int r = 0; r < reps; ++r)
+    if ((rc = launch_gemm(h, w, cfg, EPI_STORE, M_DBG_A, M_DBG_B, p.d_tasks, (int)p.tasks.size(), ep))) return rc;
+  cudaEventRecord(e1, h->stream);
+  CK(cudaStreamSynchronize(h->stream));
+  float t = 0.f;
+  cudaEventElapsedTime(&t, e0, e1);
+  if (ms) *ms = t / reps;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  p.clear();
+  return 0;
+}
+
+}  // extern "C"

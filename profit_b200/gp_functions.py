@@ -1,0 +1,145 @@
+"""Function-level twins of profit/sur/gp/backend/gp_functions.py, backed by libgpb (CUDA, sm_100a).
+
+Same names, argument meaning and error behaviour as the reference:
+
+* ``optimize``                          gp_functions.py:8-69    (SciPy BFGS on the host, objective on the GPU)
+* ``solve_cholesky``                    gp_functions.py:72-100
+* ``negative_log_likelihood_cholesky``  gp_functions.py:103-187
+* ``negative_log_likelihood``           gp_functions.py:190-301 (Cholesky branch; see note)
+* ``invert_cholesky`` / ``invert``      gp_functions.py:304-373
+* ``predict_f``                         gp_functions.py:457-491
+
+Note on ``negative_log_likelihood``: the reference first runs eigsh warm-up passes and only falls back to a
+truncated eigen-decomposition when the Cholesky factorisation fails (:254-301).  Whenever the Cholesky branch
+is reached its value is bit-identical to ``negative_log_likelihood_cholesky``.
+This backend implements the Cholesky branch only: a non-SPD matrix raises ``np.linalg.LinAlgError``.
+"""
+import numpy as np
+
+from .backend import shared_backend
+from .kernels import kernel_kind
+
+
+def _train_arrays(X, y):
+    X = np.asarray(X, dtype=np.float64)
+    if X.ndim == 1:
+        X = X.reshape(-1, 1)
+    y = np.asarray(y, dtype=np.float64)
+    return np.ascontiguousarray(X), np.ascontiguousarray(y)
+
+
+def solve_cholesky(L, b):
+    r"""alpha = L^T \ (L \ b)  (gp_functions.py:72-100)."""
+    return shared_backend().solve_cholesky(np.asarray(L, dtype=np.float64), np.asarray(b, dtype=np.float64))
+
+
+def invert_cholesky(L):
+    r"""(L L^T)^{-1} from the lower Cholesky factor (gp_functions.py:304-322)."""
+    return shared_backend().invert_cholesky(np.asarray(L, dtype=np.float64))
+
+
+def invert(K, neig=0, tol=1e-10, eps=1e-6, max_iter=1000):
+    """Inverse of an SPD matrix via Cholesky (gp_functions.py:325-349).
+
+    Like the reference, a failed factorisation is retried once with ``eps`` added to the diagonal (:343-346).
+    The eigen-decomposition branch (``neig > 0``, :350-373) is not part of the accelerated path.
+    """
+    if neig and 0 < neig <= 0.05 * len(K):
+        raise NotImplementedError("the truncated eigen-decomposition branch is not implemented on the GPU path")
+    be = shared_backend()
+    K = np.asarray(K, dtype=np.float64)
+    try:
+        L = be.cholesky(K)
+    except np.linalg.LinAlgError:
+        L = be.cholesky(K + eps * np.eye(K.shape[0], K.shape[1]))
+    return be.invert_cholesky(L)
+
+
+def negative_log_likelihood_cholesky(hyp, X, y, kernel, eval_gradient=False, log_scale_hyp=False,
+                                     fixed_sigma_n=False, backend=None):
+    """NLL (and gradient) through the Cholesky factorisation (gp_functions.py:103-187).
+
+    ``hyp`` is on the linear scale, ``[length_scale..., sigma_f, sigma_n]``.  Returns ``float`` or
+    ``(float, ndarray)``; raises ``np.linalg.LinAlgError`` if the covariance matrix is not SPD.
+    ``backend`` (optional) is a GPBackend that already holds (X, y); otherwise they are uploaded now.
+    """
+    hyp = np.asarray(hyp, dtype=np.float64)
+    kind = kernel_kind(kernel)
+    if backend is None:
+        backend = shared_backend()
+        Xc, yc = _train_arrays(X, y)
+        backend.set_train(Xc, yc)
+    if not eval_gradient:
+        return backend.nll(kind, hyp, want_grad=False)
+    nll, dnll = backend.nll(kind, hyp, want_grad=True)
+    if fixed_sigma_n:                      # :181-183
+        dnll = dnll[:-1]
+        hyp = hyp[:-1]
+    if log_scale_hyp:                      # :184-186, chain rule
+        dnll = dnll * (hyp * np.log(10))
+    return nll, dnll
+
+
+def negative_log_likelihood(hyp, X, y, kernel, eval_gradient=False, log_scale_hyp=False,
+                            fixed_sigma_n_value=None, neig=0, max_iter=1000, backend=None):
+    """Objective handed to the optimiser (gp_functions.py:190-270): ``hyp`` on the log10 scale if
+    ``log_scale_hyp``; a fixed sigma_n is appended before evaluation."""
+    hyp = np.asarray(hyp, dtype=np.float64)
+    if log_scale_hyp:
+        hyp = 10**hyp                      # :239-240
+    fixed_sigma_n = fixed_sigma_n_value is not None
+    if fixed_sigma_n:
+        hyp = np.append(hyp, fixed_sigma_n_value)   # :241-243
+    return negative_log_likelihood_cholesky(hyp, X, y, kernel, eval_gradient=eval_gradient,
+                                            log_scale_hyp=log_scale_hyp, fixed_sigma_n=fixed_sigma_n,
+                                            backend=backend)
+
+
+def optimize(xtrain, ytrain, a0, kernel, fixed_sigma_n=False, eval_gradient=False, return_hess_inv=False,
+             backend=None):
+    """Hyper-parameter optimisation, gp_functions.py:8-69: log10 transform, SciPy ``minimize(method="bfgs")``
+    with the same arguments; the training set is uploaded once and stays resident across evaluations."""
+    from scipy.optimize import minimize
+
+    a0 = np.asarray(a0, dtype=np.float64)
+    if fixed_sigma_n:
+        sigma_n = a0[-1]
+        a0 = a0[:-1]
+    else:
+        sigma_n = None
+    a0 = np.log10(a0)
+
+    if backend is None:
+        backend = shared_backend()
+    Xc, yc = _train_arrays(xtrain, ytrain)
+    backend.set_train(Xc, yc)
+
+    def objective(h):
+        return negative_log_likelihood(h, Xc, yc, kernel, eval_gradient, True, sigma_n, backend=backend)
+
+    opt_result = minimize(objective, a0, method="bfgs", bounds=None, jac=eval_gradient)
+    if return_hess_inv:
+        return 10**opt_result.x, opt_result.hess_inv
+    return 10**opt_result.x
+
+
+def predict_f(hyp, x, y, xtest, kernel, return_full_cov=False, neig=0):
+    """Posterior mean and variance from a flat hyper-parameter array (gp_functions.py:457-491).
+
+    The diagonal of K** carries sigma_n^2 (:484) and the clamp is applied after it (:488).  Only the diagonal
+    is available on the accelerated path.
+    """
+    if return_full_cov:
+        raise NotImplementedError("full predictive covariance is not part of the accelerated path")
+    hyp = np.asarray(hyp, dtype=np.float64)
+    be = shared_backend()
+    Xc, yc = _train_arrays(x, y)
+    be.set_train(Xc, yc)
+    be.factorize(kernel_kind(kernel), hyp)
+    xt = np.asarray(xtest, dtype=np.float64)
+    if xt.ndim == 1:
+        xt = xt.reshape(-1, 1)
+    mean, vstar = be.predict(np.ascontiguousarray(xt), add_data_variance=2)   # sn^2 joins before the clamp
+    if yc.ndim == 1:
+        mean = mean.reshape(-1)
+    return mean, vstar

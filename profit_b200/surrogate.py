@@ -1,0 +1,333 @@
+"""``B200GPSurrogate`` -- drop-in for proFit's ``GPSurrogate`` ("Custom", profit/sur/gp/custom_surrogate.py:7-282).
+
+Same method set, argument meaning, attribute names and error behaviour; the numerics run in libgpb on the GPU.
+When ``profit`` is importable the class subclasses ``profit.sur.gp.GaussianProcess`` and registers itself as
+``Surrogate["B200"]`` (config: ``fit: {surrogate: B200}`` + ``include: <path to this file>``); call
+``register_as_custom()`` to also take over the hard-coded ``Surrogate["Custom"]`` of McmcAL (mcmc_al.py:101-102).
+Without ``profit`` (e.g. on a bare GPU box) a minimal stand-in base class restates the checks of
+``Surrogate.pre_train`` / ``pre_predict`` (sur.py:136-164,187-221) and ``GaussianProcess.pre_train``
+(gaussian_process.py:74-136) so the class works stand-alone.
+"""
+import numpy as np
+
+from . import gp_functions as _gpf
+from .backend import GPBackend
+from .kernels import kernel_kind, select_kernel
+
+try:  # pragma: no cover - depends on the environment
+    from profit.sur import Surrogate as _Surrogate
+    from profit.sur.gp import GaussianProcess as _GPBase
+    from profit.defaults import fit_gaussian_process as _gp_defaults, fit as _base_defaults
+
+    HAVE_PROFIT = True
+except Exception:  # profit not installed: stand-alone base with the same contract
+    HAVE_PROFIT = False
+    _Surrogate = None
+    _gp_defaults = {"surrogate": "GPyTorch", "kernel": "RBF",
+                    "hyperparameters": {"length_scale": None, "sigma_f": None, "sigma_n": None}}
+    _base_defaults = {"fixed_sigma_n": False}
+
+    class _GPBase:  # restatement of Surrogate + GaussianProcess plumbing (no numerics)
+        labels = {}
+
+        def __init__(self):
+            self.trained = False
+            self.fixed_sigma_n = False
+            self.Xtrain = None
+            self.ytrain = None
+            self.ndim = None
+            self.output_ndim = 1
+            self.input_encoders = []
+            self.output_encoders = []
+            self.kernel = None
+            self.hyperparameters = {}
+
+        def _check_training_data(self, X, y):            # sur.py:136-164
+            X, y = np.asarray(X), np.asarray(y)
+            if X.ndim == 1:
+                X = X.reshape(-1, 1)
+            elif X.ndim != 2:
+                raise ValueError(f"X should have shape (n,) or (n, d) but has shape {X.shape}")
+            if y.ndim == 1:
+                y = y.reshape(-1, 1)
+            elif y.ndim != 2:
+                raise ValueError(f"y should have shape (n,) or (n, D) but has shape {y.shape}")
+            if X.shape[0] != y.shape[0]:
+                raise ValueError(f"mismatched number of data points for X and y: {X.shape[0]} != {y.shape[0]}")
+            self.Xtrain, self.ytrain = X, y
+            self.ndim = self.Xtrain.shape[-1]
+
+        def pre_train(self, X, y, kernel=_gp_defaults["kernel"], hyperparameters=_gp_defaults["hyperparameters"],
+                      fixed_sigma_n=_base_defaults["fixed_sigma_n"]):     # gaussian_process.py:74-114
+            self._check_training_data(X, y)
+            self.set_attributes(fixed_sigma_n=fixed_sigma_n, kernel=kernel, hyperparameters=hyperparameters)
+            inferred = None
+            for key, value in self.hyperparameters.items():
+                if value is None:
+                    if inferred is None:
+                        inferred = self.infer_hyperparameters()
+                    value = inferred[key]
+                self.hyperparameters[key] = np.atleast_1d(value)
+            if isinstance(self.kernel, str):
+                self.kernel = self.select_kernel(self.kernel)
+
+        def set_attributes(self, **kwargs):              # gaussian_process.py:116-122
+            for key, value in kwargs.items():
+                if not getattr(self, key):
+                    new_value = _gp_defaults.get(key, value) if not value else value
+                    if isinstance(new_value, dict):
+                        new_value = new_value.copy()
+                    setattr(self, key, new_value)
+
+        def pre_predict(self, Xpred):                    # sur.py:187-221
+            if not self.trained:
+                raise RuntimeError("Need to train() before predict()!")
+            Xpred = np.asarray(Xpred)
+            if Xpred.ndim == 1:
+                Xpred = Xpred.reshape(-1, 1)
+            elif Xpred.ndim != 2:
+                if self.ndim == 1:
+                    raise ValueError(f"Xpred should have shape (n,) or (n, 1) but has shape {Xpred.shape}")
+                raise ValueError(f"Xpred should have shape (n, {self.ndim}) but has shape {Xpred.shape}")
+            if Xpred.shape[1] != self.ndim:
+                raise ValueError(f"Xpred should have shape (n, {self.ndim}) but has shape {Xpred.shape}")
+            return Xpred
+
+        def decode_training_data(self):
+            pass
+
+        def print_hyperparameters(self, prefix):
+            pass
+
+        @classmethod
+        def from_config(cls, config, base_config):       # gaussian_process.py:193-208
+            self = cls()
+            self.kernel = config["kernel"]
+            self.hyperparameters = config["hyperparameters"]
+            return self
+
+
+def _mean_pairwise_distance(X, block=2048):
+    """mean_ij |x_i - x_j| without the reference's (N, N, D) temporary (gaussian_process.py:126-128)."""
+    X = np.asarray(X, dtype=np.float64)
+    n = X.shape[0]
+    sq = np.einsum("ij,ij->i", X, X)
+    total = 0.0
+    for r0 in range(0, n, block):
+        r1 = min(n, r0 + block)
+        d2 = sq[r0:r1, None] + sq[None, :] - 2.0 * (X[r0:r1] @ X.T)
+        np.maximum(d2, 0.0, out=d2)
+        # exact zeros on the diagonal (the subtraction above leaves round-off there)
+        idx = np.arange(r0, r1)
+        d2[idx - r0, idx] = 0.0
+        total += np.sqrt(d2).sum()
+    return total / (float(n) * float(n))
+
+
+class B200GPSurrogate(_GPBase):
+    """Custom GP on the B200: train / optimize / predict / add_training_data / set_ytrain, reference semantics.
+
+    Attributes (as read by proFit's callers and tests): ``trained, fixed_sigma_n, Xtrain, ytrain, ndim,
+    output_ndim, kernel, hyperparameters`` (dict of 1-D float64 arrays), ``hess_inv``.
+    """
+
+    gp_functions = _gpf
+
+    def __init__(self, device=None):
+        super().__init__()
+        self.hess_inv = None
+        self._device = device
+        self._backend = None
+        self._resident = None     # (id(X), id(y), shapes) currently uploaded
+        self._factor_key = None   # (resident key, hyper-parameters) currently factorised
+
+    # -- device plumbing --------------------------------------------------------------------------------
+    @property
+    def backend(self):
+        if self._backend is None:
+            self._backend = GPBackend(self._device)
+        return self._backend
+
+    def _upload(self):
+        X = np.ascontiguousarray(self.Xtrain, dtype=np.float64)
+        y = np.ascontiguousarray(self.ytrain, dtype=np.float64)
+        key = (X.shape, y.shape, hash(X.tobytes()), hash(y.tobytes())) if X.size < (1 << 22) else None
+        if key is None or key != self._resident:
+            self.backend.set_train(X, y)
+            self._resident = key
+            self._factor_key = None
+
+    def _theta(self, with_sigma_n=True):
+        keys = ("length_scale", "sigma_f", "sigma_n")
+        parts = [np.atleast_1d(np.asarray(self.hyperparameters[k], dtype=np.float64)).ravel() for k in keys]
+        return np.concatenate(parts)
+
+    # -- reference API ----------------------------------------------------------------------------------
+    def infer_hyperparameters(self):
+        """gaussian_process.py:124-136, with the pairwise mean evaluated block-wise (same value, O(N) memory)."""
+        std = np.std(self.ytrain, axis=0)
+        spread = np.abs(self.ytrain.max(axis=0) - self.ytrain.min(axis=0))
+        dist = _mean_pairwise_distance(self.Xtrain)
+        std, spread = np.mean(std), np.mean(spread)
+        return {"length_scale": np.array([0.5 * dist]), "sigma_f": np.array([std]),
+                "sigma_n": 1e-2 * np.array([spread])}
+
+    def pre_train(self, X, y, kernel=_gp_defaults["kernel"], hyperparameters=_gp_defaults["hyperparameters"],
+                  fixed_sigma_n=_base_defaults["fixed_sigma_n"]):
+        if HAVE_PROFIT:
+            # Same as GaussianProcess.pre_train (gaussian_process.py:74-114) except that hyper-parameters are
+            # only inferred when one is missing: the reference always builds an (N, N, D) tensor here.
+            _Surrogate.pre_train(self, X, y)
+            self.set_attributes(fixed_sigma_n=fixed_sigma_n, kernel=kernel, hyperparameters=hyperparameters)
+            inferred = None
+            for key, value in self.hyperparameters.items():
+                if value is None:
+                    if inferred is None:
+                        inferred = self.infer_hyperparameters()
+                    value = inferred[key]
+                self.hyperparameters[key] = np.atleast_1d(value)
+            self.print_hyperparameters("Initial")
+            if isinstance(self.kernel, str):
+                self.kernel = self.select_kernel(self.kernel)
+        else:
+            super().pre_train(X, y, kernel, hyperparameters, fixed_sigma_n)
+
+    def train(self, X, y, kernel=_gp_defaults["kernel"], hyperparameters=_gp_defaults["hyperparameters"],
+              fixed_sigma_n=_base_defaults["fixed_sigma_n"], eval_gradient=True, return_hess_inv=False):
+        """custom_surrogate.py:47-90."""
+        self.pre_train(X, y, kernel, hyperparameters, fixed_sigma_n)
+        if self.input_encoders or self.output_encoders:
+            print("For now, encoding is not supported for this surrogate. The model is created without encoding.")
+            self.decode_training_data()
+        self.kernel = self.select_kernel(self.kernel)
+        self.optimize(fixed_sigma_n=self.fixed_sigma_n, eval_gradient=eval_gradient, return_hess_inv=return_hess_inv)
+        self.post_train()
+
+    def post_train(self):
+        self.trained = True
+
+    def predict(self, Xpred, add_data_variance=True):
+        """custom_surrogate.py:95-120: returns (M, n_out) mean and (M, 1) variance."""
+        Xpred = self.pre_predict(Xpred)
+        for enc in self.input_encoders[::-1]:
+            Xpred = enc.decode(Xpred)
+        self._ensure_factor()
+        mean, var = self.backend.predict(np.ascontiguousarray(Xpred, dtype=np.float64),
+                                         add_data_variance=1 if add_data_variance else 0)
+        return mean, var.reshape(-1, 1)
+
+    def _ensure_factor(self):
+        self._upload()
+        theta = self._theta()
+        key = (self._resident, theta.tobytes(), getattr(self.kernel, "__name__", str(self.kernel)))
+        if self._resident is None or key != self._factor_key:
+            self.backend.factorize(kernel_kind(self.kernel), theta)
+            self._factor_key = key
+
+    def add_training_data(self, X, y):
+        """custom_surrogate.py:122-134: append rows; hyper-parameters are not re-optimised here."""
+        self.Xtrain = np.concatenate([self.Xtrain, X], axis=0)
+        self.ytrain = np.concatenate([self.ytrain, y], axis=0)
+        self._resident = None
+
+    def set_ytrain(self, ydata):
+        """custom_surrogate.py:136-142."""
+        self.ytrain = np.atleast_2d(ydata.copy())
+        self._resident = None
+
+    def get_marginal_variance(self, Xpred):
+        raise NotImplementedError(
+            "marginal_variance_BBQ (gp_functions.py:376-454) is outside the accelerated path (SURVEY.md section 8f-2)")
+
+    def select_kernel(self, kernel):
+        """custom_surrogate.py:213-238: name or callable -> kernel callable; unknown names raise RuntimeError."""
+        return select_kernel(kernel)
+
+    def optimize(self, fixed_sigma_n=_base_defaults["fixed_sigma_n"], eval_gradient=False, return_hess_inv=False):
+        """custom_surrogate.py:240-272."""
+        ordered = ("length_scale", "sigma_f", "sigma_n")
+        a0 = np.concatenate([np.atleast_1d(self.hyperparameters[key]) for key in ordered])
+        self.kernel = self.select_kernel(self.kernel)
+        fixed = bool(self.fixed_sigma_n or fixed_sigma_n)
+        opt = _gpf.optimize(self.Xtrain, self.ytrain, a0, self.kernel, fixed_sigma_n=fixed,
+                            eval_gradient=eval_gradient, return_hess_inv=return_hess_inv, backend=self.backend)
+        self._resident = None  # optimize() uploaded through the function-level path
+        if return_hess_inv:
+            self.hess_inv = opt[1]
+            opt = opt[0]
+        self._set_hyperparameters_from_model(opt, fixed)
+        self.print_hyperparameters("Optimized")
+
+    def _set_hyperparameters_from_model(self, model_hyperparameters, fixed=None):
+        # custom_surrogate.py:274-282 (the reference keys on self.fixed_sigma_n only; an optimize(fixed_sigma_n=True)
+        # call on an unfixed surrogate would otherwise mis-slice, so the effective flag is used)
+        fixed = self.fixed_sigma_n if fixed is None else fixed
+        last_idx = -1 if fixed else -2
+        self.hyperparameters["length_scale"] = np.atleast_1d(model_hyperparameters[:last_idx])
+        self.hyperparameters["sigma_f"] = np.atleast_1d(model_hyperparameters[last_idx])
+        if not fixed:
+            self.hyperparameters["sigma_n"] = np.atleast_1d(model_hyperparameters[-1])
+
+    def save_model(self, path):
+        """custom_surrogate.py:165-187: same dictionary of attributes; .npz here (h5py-free), .hdf5 via proFit's
+        FileHandler when it is available."""
+        saved_attrs = ("trained", "fixed_sigma_n", "Xtrain", "ytrain", "ndim", "kernel", "hyperparameters")
+        save_dict = {attr: getattr(self, attr) for attr in saved_attrs}
+        if not isinstance(save_dict["kernel"], str):
+            save_dict["kernel"] = self.kernel.__name__
+        if str(path).endswith(".npz"):
+            flat = {k: v for k, v in save_dict.items() if k != "hyperparameters"}
+            for k, v in save_dict["hyperparameters"].items():
+                flat["hyperparameters." + k] = v
+            np.savez(path, **flat)
+        else:
+            from profit.util.file_handler import FileHandler
+
+            FileHandler.save(path, save_dict)
+
+    @classmethod
+    def load_model(cls, path):
+        """custom_surrogate.py:189-211."""
+        self = cls()
+        if str(path).endswith(".npz"):
+            data = np.load(path, allow_pickle=False)
+            hyp = {}
+            for k in data.files:
+                if k.startswith("hyperparameters."):
+                    hyp[k.split(".", 1)[1]] = data[k]
+                elif k in ("trained", "fixed_sigma_n"):
+                    setattr(self, k, bool(data[k]))
+                elif k == "ndim":
+                    setattr(self, k, int(data[k]))
+                elif k == "kernel":
+                    setattr(self, k, str(data[k]))
+                else:
+                    setattr(self, k, data[k])
+            self.hyperparameters = hyp
+        else:
+            from profit.util.file_handler import FileHandler
+
+            for attr, value in FileHandler.load(path, as_type="dict").items():
+                setattr(self, attr, value)
+        self.kernel = self.select_kernel(self.kernel)
+        self.print_hyperparameters("Loaded")
+        return self
+
+
+def register(label="B200"):
+    """Register the class in proFit's surrogate registry (util/base_class.py:15-26)."""
+    if not HAVE_PROFIT:
+        raise RuntimeError("profit is not importable: nothing to register with")
+    return _Surrogate.register(label)(B200GPSurrogate)
+
+
+def register_as_custom():
+    """Take over the label "Custom" (prints proFit's duplicate-label warning, base_class.py:20-23)."""
+    return register("Custom")
+
+
+if HAVE_PROFIT:  # pragma: no cover
+    try:
+        register("B200")
+    except Exception:
+        pass
