@@ -92,10 +92,11 @@ int gpb_stage_ms(gpb_handle_t h, double* out);
 /* Number of kernels launched by this handle since creation (the host layer reports it as gpu_launches). */
 long long gpb_launch_count(gpb_handle_t h);
 
-/* Test/benchmark hook: C(MxN) = A(MxK) * B(NxK)^T with the tile-GEMM kernel, device pointers, all dimensions
- * multiples of 128.  cfg selects the tile configuration.  Returns the average ms over reps in *ms. */
+/* Test/benchmark hook: C(MxN) = alpha * A(MxK) * B(NxK)^T + beta * C with the tile-GEMM kernel, device pointers,
+ * all dimensions multiples of 128.  cfg selects the tile configuration.  The product is applied `reps` times;
+ * *ms receives the average device time of one application. */
 int gpb_debug_gemm(gpb_handle_t h, const double* A, const double* B, double* C, long long M, long long N, long long K,
-                   int cfg, int reps, double* ms);
+                   int cfg, double alpha, double beta, int reps, double* ms);
 
 #ifdef __cplusplus
 }

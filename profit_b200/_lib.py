@@ -37,7 +37,8 @@ SIGNATURES = {
     "gpb_stage_ms": (ctypes.c_int, [ctypes.c_void_p, _c_double_p]),
     "gpb_launch_count": (_ll, [ctypes.c_void_p]),
     "gpb_debug_gemm": (ctypes.c_int, [ctypes.c_void_p, _c_double_p, _c_double_p, _c_double_p, _ll, _ll, _ll,
-                                      ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]),
+                                      ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_int,
+                                      ctypes.POINTER(ctypes.c_double)]),
 }
 
 NUM_STAGES = 8

@@ -139,12 +139,12 @@ class GPBackend:
     def launch_count(self):
         return int(self._lib.gpb_launch_count(self._h))
 
-    def debug_gemm(self, A, B, C, cfg=1, reps=5):
+    def debug_gemm(self, A, B, C, cfg=1, reps=5, alpha=1.0, beta=0.0):
         M, K = int(A.shape[0]), int(A.shape[1])
         N = int(B.shape[0])
         ms = ctypes.c_double()
-        _lib.check(self._lib.gpb_debug_gemm(self._h, _lib.ptr(A), _lib.ptr(B), _lib.ptr(C), M, N, K, int(cfg), int(reps),
-                                            ctypes.byref(ms)), self._h, "debug_gemm")
+        _lib.check(self._lib.gpb_debug_gemm(self._h, _lib.ptr(A), _lib.ptr(B), _lib.ptr(C), M, N, K, int(cfg), float(alpha), float(beta),
+                                            int(reps), ctypes.byref(ms)), self._h, "debug_gemm")
         return ms.value
 
 

@@ -111,6 +111,14 @@ dgemm_tasks_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int s = kt % STAGES;
     const uint32_t ph = (kt / STAGES) & 1;
     mbar_wait(&full[s], ph);
+    // Deferred release: the slab of the PREVIOUS step is handed back only here, behind the spin loop above.
+    // Its LDS results were consumed by DMMAs that sit before the loop back-edge, so every shared-memory read of
+    // that slab has returned before the producer may overwrite it (an arrive placed right after the loads can
+    // overtake them in the memory pipeline when two CTAs share an SM).
+    if (kt > 0) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[(kt - 1) % STAGES]);
+    }
     const uint32_t st = smem_base + s * SM::STAGE_BYTES;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -129,8 +137,6 @@ dgemm_tasks_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
         for (int ni = 0; ni < NI; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], af[mi].y, bf[ni].y);
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[s]);
   }
 
   // ---------------- epilogue ----------------

@@ -464,7 +464,8 @@ __global__ void __launch_bounds__(256) trigemv_kernel(const double* __restrict__
 
 // nll = 0.5 * sum_o ||z_o||^2 + n_out * sum_k logdet[k] + 0.5 * n * n_out * log(2 pi)   (gp_functions.py:147-164)
 __global__ void __launch_bounds__(1024) nll_kernel(const double* __restrict__ z, long long ldz, int n_out, long long n,
-                                                   const double* __restrict__ logdet, int nb, double* __restrict__ out) {
+                                                   long long n_data, const double* __restrict__ logdet, int nb,
+                                                   double* __restrict__ out) {
   __shared__ double sh[1024];
   double s = 0.0;
   for (int o = 0; o < n_out; ++o)
@@ -481,7 +482,7 @@ __global__ void __launch_bounds__(1024) nll_kernel(const double* __restrict__ z,
   if (threadIdx.x == 0) {
     double ld = 0.0;
     for (int k = 0; k < nb; ++k) ld += logdet[k];
-    out[0] = 0.5 * sh[0] + n_out * ld + 0.5 * (double)n * n_out * 1.8378770664093454835606594728112;
+    out[0] = 0.5 * sh[0] + n_out * ld + 0.5 * (double)n_data * n_out * 1.8378770664093454835606594728112;
   }
 }
 
@@ -735,7 +736,9 @@ int gpb_create(int device, gpb_handle_t* out) {
     delete h;
     return -2;
   }
-  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+  // A blocking stream: implicitly ordered with the legacy default stream, which is what torch uses by default,
+  // so device pointers handed in by the caller are safe to read without an explicit cross-stream event.
+  if (cudaStreamCreate(&h->stream) != cudaSuccess) {
     delete h;
     return -2;
   }
@@ -845,7 +848,7 @@ int gpb_nll(gpb_handle_t h, int kind, const double* theta, int n_ell, int want_g
   stages_reset(h);
   stage_begin(h, GPB_STAGE_TOTAL);
   if ((rc = assemble_and_factor(h))) return rc;
-  nll_kernel<<<1, 1024, 0, h->stream>>>(w.Lbuf + w.Np * w.Np, w.Np, h->n_out, w.Np, w.logdet, (int)w.Nb, h->dscal);
+  nll_kernel<<<1, 1024, 0, h->stream>>>(w.Lbuf + w.Np * w.Np, w.Np, h->n_out, w.Np, w.N, w.logdet, (int)w.Nb, h->dscal);
   h->launches++;
   const int P = n_ell + 2, width = h->DP + 2;
   if (want_grad) {
@@ -1164,7 +1167,7 @@ int gpb_solve_cholesky(gpb_handle_t h, const double* L, long long n, const doubl
 }
 
 int gpb_debug_gemm(gpb_handle_t h, const double* A, const double* B, double* C, long long M, long long N, long long K,
-                   int cfg, int reps, double* ms) {
+                   int cfg, double alpha, double beta, int reps, double* ms) {
   if (!h || !A || !B || !C || M % 128 || N % 128 || K % 128 || cfg < 0 || cfg >= NUM_CFG || reps < 1)
     return fail(h, -1, "gpb_debug_gemm: bad argument");
   CK(cudaSetDevice(h->device));
@@ -1184,12 +1187,11 @@ int gpb_debug_gemm(gpb_handle_t h, const double* A, const double* B, double* C, 
   ep.ldc = N;
   ep.Ct = nullptr;
   ep.ldct = 0;
-  ep.alpha = 1.0;
-  ep.beta = 0.0;
+  ep.alpha = alpha;
+  ep.beta = beta;
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
-  if ((rc = launch_gemm(h, w, cfg, EPI_STORE, M_DBG_A, M_DBG_B, p.d_tasks, (int)p.tasks.size(), ep))) return rc;
   cudaEventRecord(e0, h->stream);
   for (int r = 0; r < reps; ++r)
     if ((rc = launch_gemm(h, w, cfg, EPI_STORE, M_DBG_A, M_DBG_B, p.d_tasks, (int)p.tasks.size(), ep))) return rc;

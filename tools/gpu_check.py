@@ -56,7 +56,7 @@ if stage in ("all", "chol"):
         print("non-SPD ->", e)
 
 if stage in ("all", "nll"):
-    for (N, D) in ((3, 2), (200, 2), (300, 5), (1000, 8), (1500, 10)):
+    for (N, D) in ((3, 2), (200, 2), (300, 5), (1000, 8), (1500, 10), (1100, 16), (700, 20), (520, 32)):
         X, y = oracle.synthetic_problem(N, D)
         Xc = np.random.default_rng(2).random((777, D))
         for n_ell in (D, 1):
@@ -73,6 +73,34 @@ if stage in ("all", "nll"):
                 e_m = np.max(np.abs(mean - rm)) / np.abs(rm).max(); e_v = np.max(np.abs(var - rv.ravel()) / rv.ravel())
                 print(f"N={N} D={D} n_ell={n_ell} kind={kind}: nll {e_n:.1e} (nograd {abs(nll0-rn)/abs(rn):.1e}) grad {e_g:.1e} mean {e_m:.1e} var {e_v:.1e}", flush=True)
                 assert e_n < 1e-9 and e_g < 1e-8 and e_m < 1e-8 and e_v < 1e-8
+
+if stage == "big":
+    for (N, D) in ((4096, 16), (8192, 8), (8192, 16)):
+        X, y = oracle.synthetic_problem(N, D)
+        theta = np.concatenate([np.linspace(0.6, 1.2, D), [1.5, 0.3]])
+        from profit_b200 import kernels
+        K = be.kernel_matrix(KIND_RBF, X, X, theta[:D], 1.5, 0.3)
+        Kt = torch.from_numpy(K).to(dev)
+        Lt = torch.linalg.cholesky(Kt)
+        print(N, D, "torch chol ok, min diag", Lt.diagonal().min().item(), "sym err", (Kt-Kt.T).abs().max().item(), flush=True)
+        try:
+            L = be.cholesky(K)
+            print("  gpb chol err", np.abs(L - Lt.cpu().numpy()).max(), flush=True)
+        except Exception as e:
+            print("  gpb chol FAILED", e, flush=True)
+        be.set_train(X, y)
+        try:
+            print("  nll", be.nll(KIND_RBF, theta), flush=True)
+        except Exception as e:
+            print("  nll FAILED", e, flush=True)
+
+if stage == "time4096":
+    X, y = oracle.synthetic_problem(4096, 8)
+    theta = np.concatenate([np.linspace(0.6, 1.2, 8), [1.5, 0.3]])
+    be.set_train(X, y)
+    be.nll(KIND_RBF, theta, want_grad=True)
+    be.nll(KIND_RBF, theta, want_grad=True)
+    print(be.stage_ms())
 
 if stage in ("all", "time"):
     for (N, D, kind) in ((4096, 8, KIND_RBF), (8192, 16, KIND_RBF), (16384, 10, KIND_MATERN52)):
