@@ -753,6 +753,11 @@ int gpb_create(int device, gpb_handle_t* out) {
     delete h;
     return -2;
   }
+  {
+    const int dk_smem = 4 * 64 * (MAX_D + 2) * (int)sizeof(double);
+    cudaFuncSetAttribute(kernel_matrix_kernel<KIND_RBF>, cudaFuncAttributeMaxDynamicSharedMemorySize, dk_smem);
+    cudaFuncSetAttribute(kernel_matrix_kernel<KIND_MATERN52>, cudaFuncAttributeMaxDynamicSharedMemorySize, dk_smem);
+  }
   for (int s = 0; s < GPB_NUM_STAGES; ++s) {
     cudaEventCreate(&h->ev0[s]);
     cudaEventCreate(&h->ev1[s]);
@@ -959,7 +964,7 @@ int gpb_predict(gpb_handle_t h, const double* Xc, long long M, int add_data_vari
     cudaFree(h->dvar);
     h->dXc = h->dKsT = h->dVpart = h->dmean = h->dvar = nullptr;
     h->pred_Mc = h->pred_Nb = 0;
-    CK(cudaMalloc(&h->dXc, (size_t)Mc * h->D * sizeof(double)));
+    CK(cudaMalloc(&h->dXc, (size_t)Mc * MAX_D * sizeof(double)));  // sized for any D: the chunk buffers outlive set_train
     CK(cudaMalloc(&h->dKsT, (size_t)Mc * w.Np * sizeof(double)));
     CK(cudaMalloc(&h->dVpart, (size_t)w.Nb * Mc * sizeof(double)));
     CK(cudaMalloc(&h->dmean, (size_t)Mc * 128 * sizeof(double)));

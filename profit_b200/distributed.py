@@ -1,0 +1,128 @@
+"""Multi-GPU sharding of the two paths that partition naturally.
+
+One process per GPU (torchrun); ``torch.distributed`` is only used for tiny result gathers:
+
+* candidate prediction -- contiguous shards of ceil(M/G) candidates per rank, X/y/theta replicated, every rank
+  factorises on its own; one all_gather of (best value, global index) = 16 B per rank, then a local arg-max
+  with lowest-index tie-break (np.argmax semantics, aquisition_functions.py:68).
+* multi-start hyper-parameter optimisation -- restart r runs on rank r mod G; one all_gather of
+  (nll, theta[P]) per restart, arg-min with tie-break on the restart index.  The reference has a single start
+  (gp_functions.py:59-66); per restart the optimiser is exactly ``gp_functions.optimize``.
+
+A single NLL+gradient evaluation does not shard ("replicas only").  No data-path collective exists.
+"""
+import numpy as np
+
+
+def _dist():
+    import torch.distributed as dist
+
+    return dist if (dist.is_available() and dist.is_initialized()) else None
+
+
+def world():
+    d = _dist()
+    return (d.get_rank(), d.get_world_size()) if d else (0, 1)
+
+
+def shard_bounds(M, world_size, rank):
+    """Contiguous shard [lo, hi) of ceil(M/G) items for this rank (the last shards may be short or empty)."""
+    per = -(-int(M) // int(world_size))
+    lo = min(int(M), rank * per)
+    hi = min(int(M), lo + per)
+    return lo, hi
+
+
+def _all_gather_rows(row):
+    """all_gather a small float64 vector from every rank -> (G, len) numpy array (same on all ranks)."""
+    d = _dist()
+    row = np.asarray(row, dtype=np.float64)
+    if d is None:
+        return row[None, :]
+    import torch
+
+    dev = torch.device("cuda", torch.cuda.current_device()) if d.get_backend() == "nccl" else torch.device("cpu")
+    mine = torch.from_numpy(row.copy()).to(dev)
+    out = [torch.empty_like(mine) for _ in range(d.get_world_size())]
+    d.all_gather(out, mine)
+    return torch.stack(out).cpu().numpy()
+
+
+def gather_argmax(local_value, local_global_index):
+    """Global (index, value) of the maximum over ranks; ties -> lowest global index; empty shards pass -inf."""
+    rows = _all_gather_rows([local_value, float(local_global_index)])
+    best_val, best_idx = -np.inf, -1
+    for val, idx in rows:
+        idx = int(idx)
+        if idx < 0:
+            continue
+        if val > best_val or (val == best_val and idx < best_idx):
+            best_val, best_idx = val, idx
+    return best_idx, best_val
+
+
+def gather_argmin_rows(local_rows):
+    """local_rows: (k, 2+P) rows [restart_index, nll, theta...]; returns the row with the smallest nll over all
+    ranks (ties -> smallest restart index).  Ranks may hold different numbers of rows."""
+    local_rows = np.atleast_2d(np.asarray(local_rows, dtype=np.float64))
+    d = _dist()
+    width = local_rows.shape[1]
+    counts = _all_gather_rows([float(local_rows.shape[0])])[:, 0].astype(int)
+    kmax = int(counts.max())
+    padded = np.full((kmax, width), np.inf)
+    padded[:, 0] = -1
+    padded[: local_rows.shape[0]] = local_rows
+    allrows = _all_gather_rows(padded.ravel()).reshape(-1, width) if d else padded
+    allrows = allrows[allrows[:, 0] >= 0]
+    order = np.lexsort((allrows[:, 0], allrows[:, 1]))
+    return allrows[order[0]], allrows[np.argsort(allrows[:, 0])]
+
+
+def predict_sharded(backend, Xpred, add_data_variance=True):
+    """Predict this rank's contiguous shard of the candidate set.  Returns (lo, hi, mean, var)."""
+    rank, ws = world()
+    lo, hi = shard_bounds(len(Xpred), ws, rank)
+    if hi > lo:
+        mean, var = backend.predict(np.ascontiguousarray(Xpred[lo:hi], dtype=np.float64),
+                                    add_data_variance=1 if add_data_variance else 0)
+    else:
+        mean, var = np.empty((0, backend.n_out)), np.empty(0)
+    return lo, hi, mean, var
+
+
+def acquisition_argmax(backend, Xpred, add_data_variance=True, mask=None):
+    """argmax_c var(c) * mask(c) over the whole candidate set, sharded over ranks
+    (SimpleExploration: aquisition_functions.py:63-74,107-119).  Returns (global index, value)."""
+    lo, hi, _, var = predict_sharded(backend, Xpred, add_data_variance)
+    if hi > lo:
+        score = var if mask is None else var * np.asarray(mask, dtype=np.float64)[lo:hi]
+        li, lv = backend.argmax(np.ascontiguousarray(score))
+        return gather_argmax(lv, lo + li)
+    return gather_argmax(-np.inf, -1)
+
+
+def multistart_optimize(xtrain, ytrain, starts, kernel, fixed_sigma_n=False, eval_gradient=True, backend=None):
+    """Run ``gp_functions.optimize`` from every start in ``starts`` (R, P), restarts sharded r -> rank r mod G.
+
+    Returns (best_theta, best_nll, table) where table has one row per restart: [restart, nll, theta...].
+    """
+    from . import gp_functions as gpf
+    from .backend import shared_backend
+
+    rank, ws = world()
+    be = backend or shared_backend()
+    starts = np.atleast_2d(np.asarray(starts, dtype=np.float64))
+    rows = []
+    for r in range(rank, starts.shape[0], ws):
+        try:
+            theta = gpf.optimize(xtrain, ytrain, starts[r], kernel, fixed_sigma_n=fixed_sigma_n,
+                                 eval_gradient=eval_gradient, backend=be)
+            full = np.append(theta, starts[r][-1]) if fixed_sigma_n else theta
+            nll = gpf.negative_log_likelihood_cholesky(full, xtrain, ytrain, kernel, backend=be)
+        except np.linalg.LinAlgError:
+            theta, nll = starts[r][:-1] if fixed_sigma_n else starts[r], np.inf
+        rows.append(np.concatenate([[r, nll], theta]))
+    width = 2 + (starts.shape[1] - (1 if fixed_sigma_n else 0))
+    local = np.array(rows) if rows else np.empty((0, width))
+    best, table = gather_argmin_rows(local) if len(local) or ws > 1 else (None, local)
+    return best[2:], float(best[1]), table

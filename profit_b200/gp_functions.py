@@ -83,16 +83,48 @@ def negative_log_likelihood_cholesky(hyp, X, y, kernel, eval_gradient=False, log
 def negative_log_likelihood(hyp, X, y, kernel, eval_gradient=False, log_scale_hyp=False,
                             fixed_sigma_n_value=None, neig=0, max_iter=1000, backend=None):
     """Objective handed to the optimiser (gp_functions.py:190-270): ``hyp`` on the log10 scale if
-    ``log_scale_hyp``; a fixed sigma_n is appended before evaluation."""
+    ``log_scale_hyp``; a fixed sigma_n is appended before evaluation.
+
+    Non-SPD handling.  The reference catches ``LinAlgError`` here and switches to a truncated
+    eigen-decomposition with eigenvalues clipped at 1e-10 (:271-301), which returns a *different* number than
+    the Cholesky NLL.  This backend keeps the optimiser alive the same way but stays on the device: the
+    factorisation is retried with a growing diagonal jitter (equivalently an inflated sigma_n, since
+    K = K_pure + sigma_n^2 I), after printing a warning like the reference does.  If no jitter up to
+    1e-2 sigma_f^2 helps, ``LinAlgError`` propagates.
+    """
     hyp = np.asarray(hyp, dtype=np.float64)
     if log_scale_hyp:
         hyp = 10**hyp                      # :239-240
     fixed_sigma_n = fixed_sigma_n_value is not None
     if fixed_sigma_n:
         hyp = np.append(hyp, fixed_sigma_n_value)   # :241-243
-    return negative_log_likelihood_cholesky(hyp, X, y, kernel, eval_gradient=eval_gradient,
-                                            log_scale_hyp=log_scale_hyp, fixed_sigma_n=fixed_sigma_n,
-                                            backend=backend)
+    try:
+        return negative_log_likelihood_cholesky(hyp, X, y, kernel, eval_gradient=eval_gradient,
+                                                log_scale_hyp=log_scale_hyp, fixed_sigma_n=fixed_sigma_n,
+                                                backend=backend)
+    except np.linalg.LinAlgError:
+        print("Warning! Covariance matrix is not positive definite; retrying with diagonal jitter.")
+    sigma_f, sigma_n = float(hyp[-2]), float(hyp[-1])
+    for jitter in (1e-10, 1e-8, 1e-6, 1e-4, 1e-2):
+        inflated = np.array(hyp, dtype=np.float64)
+        inflated[-1] = np.sqrt(sigma_n**2 + jitter * sigma_f**2)
+        try:
+            out = negative_log_likelihood_cholesky(inflated, X, y, kernel, eval_gradient=eval_gradient,
+                                                   log_scale_hyp=False, fixed_sigma_n=False, backend=backend)
+        except np.linalg.LinAlgError:
+            continue
+        if not eval_gradient:
+            return out
+        nll, dnll = out
+        dnll = np.array(dnll)
+        dnll[-1] *= sigma_n / inflated[-1]          # d sigma_n' / d sigma_n
+        dnll[-2] += out[1][-1] * jitter * sigma_f / inflated[-1]   # d sigma_n' / d sigma_f
+        if fixed_sigma_n:
+            dnll, hyp = dnll[:-1], hyp[:-1]
+        if log_scale_hyp:
+            dnll = dnll * (hyp * np.log(10))
+        return nll, dnll
+    raise np.linalg.LinAlgError("covariance matrix is not positive definite even with diagonal jitter")
 
 
 def optimize(xtrain, ytrain, a0, kernel, fixed_sigma_n=False, eval_gradient=False, return_hess_inv=False,

@@ -1,0 +1,355 @@
+"""Parity of the CUDA path against the oracle and the reference's golden vectors, through the C ABI
+(ctypes -> libgpb.so).  Tolerances are the north-star's: NLL and gradient 1e-9 relative, predictive mean and
+variance 1e-8 relative (fp64)."""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+NLL_RTOL = 1e-9     # NLL and every gradient component
+PRED_RTOL = 1e-8    # predictive mean and variance
+KERN = {"RBF": (0, oracle.rbf), "Matern52": (1, oracle.matern52)}
+
+
+def grad_err(g, ref):
+    g, ref = np.asarray(g), np.asarray(ref)
+    return float(np.max(np.abs(g - ref) / np.maximum(np.abs(ref), 1e-12 * np.abs(ref).max())))
+
+
+# ------------------------------------------------------------------------------------------ golden vectors
+def test_kat1_nll_and_gradient(backend, golden):
+    from profit_b200 import RBF, gp_functions as gpf
+
+    k = golden["kat1"]
+    nll, g = gpf.negative_log_likelihood_cholesky(np.array(k["hyp"]), np.array(k["X"]), np.array(k["y"]), RBF,
+                                                  eval_gradient=True)
+    assert abs(nll - k["nll"]) <= 1e-12 * abs(k["nll"])
+    assert rel_err(g, k["grad"]) <= 1e-12
+    assert isinstance(gpf.negative_log_likelihood_cholesky(np.array(k["hyp"]), np.array(k["X"]), np.array(k["y"]), RBF),
+                      float)
+
+
+def test_kat2_kernel_matrix(backend, golden):
+    from profit_b200 import RBF
+
+    k = golden["kat2"]
+    K, dK = RBF(np.array(k["Xa"]), np.array(k["Xb"]), np.array(k["length_scale"]), 1.0, 0.0, eval_gradient=True)
+    assert K.shape == (3, 2) and dK.shape == (3, 2, 4)
+    assert np.allclose(K, k["K"], rtol=1e-12, atol=0)
+    assert np.allclose(dK, k["dK"], rtol=1e-12, atol=1e-300)
+
+
+def test_kat3_kat4_halton(backend, golden):
+    from profit_b200 import RBF, gp_functions as gpf
+
+    h = golden["halton128"]
+    X, y = np.array(h["X"]), np.array(h["y"])
+    n4, g4 = gpf.negative_log_likelihood_cholesky(np.array(h["kat4"]["hyp"]), X, y, RBF, eval_gradient=True)
+    assert abs(n4 - h["kat4"]["nll"]) <= NLL_RTOL * abs(h["kat4"]["nll"])
+    assert rel_err(g4, h["kat4"]["grad"]) <= 1e-8            # cond(K) ~ 1e6 here
+    n3, g3 = gpf.negative_log_likelihood_cholesky(np.array(h["kat3"]["hyp"]), X, y, RBF, eval_gradient=True)
+    assert abs(n3 - h["kat3"]["nll"]) <= 1e-6 * abs(h["kat3"]["nll"])   # cond(K) = 7.7e9
+    assert rel_err(g3, h["kat3"]["grad"]) <= 1e-4
+
+
+def test_sine10_linear_algebra_twins(backend, golden):
+    """tests/unit_tests/sur/test_gp.py:21-38 with the device-backed functions."""
+    from profit_b200 import RBF, gp_functions as gpf
+
+    s = golden["sine10"]
+    X, y = np.array(s["X"]), np.array(s["y"])
+    Ky = RBF(X, X, 1.0, 1.0)
+    assert np.array_equal(Ky, Ky.T)
+    assert np.allclose(Ky, s["Ky"], rtol=1e-14)
+    L = backend.cholesky(Ky)
+    assert np.allclose(L, s["L"], rtol=1e-9, atol=1e-13) and np.all(np.triu(L, 1) == 0.0)
+    alpha = gpf.solve_cholesky(np.array(s["L"]), y)
+    assert alpha.shape == y.shape
+    assert np.allclose(alpha, np.linalg.solve(Ky, y), rtol=1e-10, atol=1e-10)
+    assert np.allclose(gpf.invert_cholesky(np.array(s["L"])), s["Kinv"], rtol=1e-9, atol=1e-9)
+    assert np.allclose(gpf.invert(Ky), s["Kinv"], rtol=1e-9, atol=1e-9)
+    ypred = RBF(np.array(s["xtest"]), X, 1.0, 1.0).dot(alpha)
+    assert np.allclose(y, ypred[::10], rtol=1e-12, atol=1e-12)
+    assert np.allclose(np.sin(np.array(s["xtest"])), ypred, rtol=1e-2, atol=1e-2)
+
+
+@pytest.mark.parametrize("idx", range(5))
+def test_synthetic_golden_cases(backend, golden, idx):
+    from profit_b200 import gp_functions as gpf, select_kernel
+
+    c = golden["synthetic"][idx]
+    X, y = oracle.synthetic_problem(c["N"], c["D"])
+    theta = np.array(c["theta"])
+    kern = select_kernel(c["kernel"])
+    nll, g = gpf.negative_log_likelihood_cholesky(theta, X, y, kern, eval_gradient=True)
+    assert abs(nll - c["nll"]) <= NLL_RTOL * abs(c["nll"])
+    assert rel_err(g, c["grad"]) <= NLL_RTOL
+    assert abs(gpf.negative_log_likelihood_cholesky(theta, X, y, kern) - c["nll"]) <= NLL_RTOL * abs(c["nll"])
+    nw, gw = gpf.negative_log_likelihood(np.log10(theta), X, y, kern, eval_gradient=True, log_scale_hyp=True)
+    assert abs(nw - c["wrapper_log10"]["nll"]) <= NLL_RTOL * abs(nw) and rel_err(gw, c["wrapper_log10"]["grad"]) <= NLL_RTOL
+    nf, gf = gpf.negative_log_likelihood(np.log10(theta[:-1]), X, y, kern, eval_gradient=True, log_scale_hyp=True,
+                                         fixed_sigma_n_value=theta[-1])
+    assert len(gf) == len(theta) - 1
+    assert abs(nf - c["wrapper_fixed_sn"]["nll"]) <= NLL_RTOL * abs(nf)
+    assert rel_err(gf, c["wrapper_fixed_sn"]["grad"]) <= NLL_RTOL
+    # predict through the surrogate class (the outer drop-in boundary)
+    from profit_b200 import B200GPSurrogate
+
+    s = B200GPSurrogate()
+    s.Xtrain, s.ytrain, s.ndim, s.trained, s.kernel = X, y, c["D"], True, kern
+    s.hyperparameters = {"length_scale": theta[:-2].copy(), "sigma_f": theta[-2:-1].copy(), "sigma_n": theta[-1:].copy()}
+    Xc = np.random.default_rng(c["predict"]["seed"]).random((c["predict"]["M"], c["D"]))
+    m, v = s.predict(Xc)
+    assert m.shape == (96, 1) and v.shape == (96, 1)
+    assert rel_err(m, c["predict"]["mean"]) <= PRED_RTOL
+    assert rel_err(v, c["predict"]["var"]) <= PRED_RTOL
+    _, v0 = s.predict(Xc, add_data_variance=False)
+    assert rel_err(v0, c["predict"]["var_nodata"]) <= PRED_RTOL
+    if "predict_f" in c:
+        f, vf = gpf.predict_f(theta, X, y, Xc, kern)
+        assert rel_err(f, c["predict_f"]["mean"]) <= PRED_RTOL and rel_err(vf, c["predict_f"]["var"]) <= PRED_RTOL
+
+
+def test_multi_output_nll(backend, golden):
+    from profit_b200 import RBF, gp_functions as gpf
+
+    c = golden["multi_output"]
+    X, _ = oracle.synthetic_problem(c["N"], c["D"])
+    nll, g = gpf.negative_log_likelihood_cholesky(np.array(c["theta"]), X, np.array(c["Y"]), RBF, eval_gradient=True)
+    assert abs(nll - c["nll"]) <= NLL_RTOL * abs(c["nll"])
+    assert rel_err(g, c["grad"]) <= NLL_RTOL
+
+
+def test_matern_against_sklearn_vectors(backend, golden):
+    from profit_b200 import Matern52
+
+    c = golden["matern_sklearn"]
+    X = np.random.default_rng(c["seed"]).random((c["n"], c["D"]))
+    ell = np.array(c["length_scale"])
+    K, dK = Matern52(X, X, ell, 1.0, 0.0, eval_gradient=True)
+    assert np.abs(K - np.array(c["K"])).max() <= 1e-14
+    assert np.abs(dK[..., :-2] * ell - np.array(c["dK_dlogl"])).max() <= 1e-14
+
+
+def test_surrogate_train_matches_reference_fit(backend, golden):
+    """BASELINE configs[0]: GPSurrogate.train on 200 Halton points, then predict."""
+    from profit_b200 import B200GPSurrogate
+
+    c = golden["c0_train"]
+    X, y = np.array(c["X"]), np.array(c["y"])
+    s = B200GPSurrogate()
+    s.train(X, y)
+    hyp = np.concatenate([s.hyperparameters[k] for k in ("length_scale", "sigma_f", "sigma_n")])
+    assert np.allclose(hyp, c["hyp_opt"], rtol=1e-4)
+    assert abs(oracle.nll_cholesky(hyp, X, y, oracle.rbf) - c["nll_opt"]) <= 1e-8 * abs(c["nll_opt"])
+    m, v = s.predict(np.array(c["predict"]["X"]))
+    assert np.allclose(m, c["predict"]["mean"], rtol=1e-4, atol=1e-6)
+    assert np.allclose(v, c["predict"]["var"], rtol=1e-3)
+    # active-learning style update: append a point, re-optimise with finite-difference gradients (simple_al.py:149)
+    s.add_training_data(np.array([[0.5, 0.5]]), np.array([[0.1]]))
+    s.optimize()
+    assert s.Xtrain.shape == (201, 2) and all(np.isfinite(v).all() for v in s.hyperparameters.values())
+    m2, v2 = s.predict(np.array([[0.5, 0.5]]))
+    assert abs(m2[0, 0] - (np.sin(1.0) + np.cos(1.5))) < 0.1 and v2[0, 0] > 0   # one outlier barely moves the fit
+
+
+# ------------------------------------------------------------------------------------------ oracle sweeps
+@pytest.mark.parametrize("kname", ["RBF", "Matern52"])
+@pytest.mark.parametrize("N,D,n_ell", [(1, 1, 1), (2, 3, 3), (127, 2, 2), (128, 4, 1), (129, 4, 4), (700, 10, 10),
+                                         (1000, 16, 16), (1300, 7, 1), (520, 32, 32)])
+def test_nll_grad_predict_vs_oracle(backend, kname, N, D, n_ell):
+    kind, kern = KERN[kname]
+    X, y = oracle.synthetic_problem(N, D)
+    theta = np.concatenate([np.linspace(0.6, 1.2, D) if n_ell == D else [0.8], [1.5, 0.3]])
+    backend.set_train(X, y)
+    nll0 = backend.nll(kind, theta)
+    nll, g = backend.nll(kind, theta, want_grad=True)
+    rn, rg = oracle.nll_cholesky(theta, X, y, kern, eval_gradient=True)
+    assert nll0 == nll
+    assert abs(nll - rn) <= NLL_RTOL * abs(rn)
+    assert grad_err(g, rg) <= NLL_RTOL
+    Xc = np.random.default_rng(2).random((131, D))
+    mean, var = backend.predict(Xc)        # the gradient call left alpha and L^-1 behind
+    ell = theta[:-2] if n_ell > 1 else theta[0]
+    rm, rv = oracle.predict(X, y, Xc, kern, ell, theta[-2], theta[-1])
+    assert np.max(np.abs(mean - rm)) <= PRED_RTOL * np.abs(rm).max()
+    assert rel_err(var, rv.ravel()) <= PRED_RTOL
+    backend.factorize(kind, theta)
+    mean2, var2 = backend.predict(Xc)
+    assert np.array_equal(mean, mean2) and np.array_equal(var, var2)
+
+
+@pytest.mark.parametrize("kname", ["RBF", "Matern52"])
+@pytest.mark.parametrize("na,nb,D,n_ell", [(1, 1, 1, 1), (5, 3, 2, 2), (63, 130, 3, 1), (200, 65, 10, 10), (70, 70, 32, 32)])
+def test_kernel_matrix_vs_oracle(backend, kname, na, nb, D, n_ell):
+    kind, kern = KERN[kname]
+    rng = np.random.default_rng(7)
+    Xa, Xb = rng.random((na, D)), rng.random((nb, D))
+    ell = np.linspace(0.5, 1.5, D) if n_ell == D else np.array([0.9])
+    K, dK = backend.kernel_matrix(kind, Xa, Xb, ell, 1.3, 0.2, eval_gradient=True)
+    rK, rdK = kern(Xa, Xb, ell if n_ell > 1 else ell[0], 1.3, 0.2, eval_gradient=True)
+    assert K.shape == rK.shape and dK.shape == rdK.shape
+    assert np.abs(K - rK).max() <= 1e-14 * np.abs(rK).max()
+    assert np.abs(dK - rdK).max() <= 1e-13 * np.abs(rdK).max()
+    assert np.array_equal(backend.kernel_matrix(kind, Xa, Xb, ell, 1.3, 0.2), K)
+
+
+def test_ragged_candidate_counts_and_chunk_invariance(backend):
+    X, y = oracle.synthetic_problem(300, 4)
+    theta = np.array([0.7, 0.8, 0.9, 1.0, 1.5, 0.3])
+    backend.set_train(X, y)
+    backend.factorize(0, theta)
+    Xc = np.random.default_rng(3).random((1000, 4))
+    m_all, v_all = backend.predict(Xc)
+    for M in (1, 31, 128, 129, 640):
+        m, v = backend.predict(Xc[:M])
+        assert m.shape == (M, 1) and v.shape == (M,)
+        assert np.array_equal(m, m_all[:M]) and np.array_equal(v, v_all[:M])
+    m, v = backend.predict(Xc[:0])
+    assert m.shape == (0, 1) and v.shape == (0,)
+    _, v0 = backend.predict(Xc, add_data_variance=False)
+    assert np.allclose(v0 + 0.09, v_all, rtol=1e-13)
+    assert np.all(v0 >= 1e-10) and np.all(v0 <= 1.5**2 * (1 + 1e-12))
+
+
+def test_variance_clamp_and_interpolation(backend):
+    """Candidates on top of training points with negligible noise: variance hits the 1e-10 clamp
+    (custom_surrogate.py:117) and the mean interpolates."""
+    X = np.random.default_rng(0).random((40, 2))
+    y = np.sin(3 * X[:, 0]) + X[:, 1]
+    backend.set_train(X, y)
+    backend.factorize(0, np.array([0.8, 1.0, 1e-5]))
+    m, v = backend.predict(X, add_data_variance=False)
+    assert np.all(v >= 1e-10) and np.all(v < 1e-6)
+    assert np.allclose(m.ravel(), y, atol=1e-5)
+
+
+def test_not_spd_raises_linalgerror(backend):
+    from profit_b200 import RBF, gp_functions as gpf
+
+    X = np.zeros((5, 2))
+    with pytest.raises(np.linalg.LinAlgError):
+        gpf.negative_log_likelihood_cholesky(np.array([1.0, 1.0, 1.0, 0.0]), X, np.ones(5), RBF)
+    with pytest.raises(np.linalg.LinAlgError):
+        backend.cholesky(-np.eye(3))
+    Kinv = gpf.invert(np.ones((3, 3)) + 1e-13 * np.eye(3))   # retried with eps = 1e-6 like gp_functions.py:343-346
+    assert np.all(np.isfinite(Kinv))
+    backend.set_train(X, np.ones(5))           # new data, nothing factorised yet
+    with pytest.raises(RuntimeError):
+        backend.predict(np.zeros((1, 2)))
+
+
+@pytest.mark.parametrize("n", [1, 64, 200, 513, 1500])
+def test_dense_factor_twins_vs_numpy(backend, n):
+    rng = np.random.default_rng(n)
+    Q = rng.standard_normal((n, n))
+    A = Q @ Q.T / n + np.eye(n)
+    L = backend.cholesky(A)
+    Lr = np.linalg.cholesky(A)
+    assert np.abs(L - Lr).max() <= 1e-12 * np.abs(Lr).max()
+    assert np.abs(backend.invert_cholesky(Lr) - np.linalg.inv(A)).max() <= 1e-11 * np.abs(np.linalg.inv(A)).max()
+    for nrhs in (1, 3):
+        b = rng.standard_normal((n, nrhs))
+        x = backend.solve_cholesky(Lr, b if nrhs > 1 else b[:, 0])
+        xr = oracle.solve_cholesky(Lr, b if nrhs > 1 else b[:, 0])
+        assert x.shape == xr.shape and np.abs(x - xr).max() <= 1e-11 * np.abs(xr).max()
+
+
+def test_argmax_tie_break(backend):
+    v = np.sin(np.arange(5000) * 0.37)
+    v[[4000, 100, 2500]] = 3.0
+    assert backend.argmax(v) == (100, 3.0) and int(np.argmax(v)) == 100
+    assert backend.argmax(np.array([-1.0])) == (0, -1.0)
+
+
+def test_device_pointers_and_host_pointers_agree(backend):
+    import torch
+
+    X, y = oracle.synthetic_problem(400, 6)
+    theta = np.concatenate([np.linspace(0.6, 1.2, 6), [1.5, 0.3]])
+    Xc = np.random.default_rng(2).random((500, 6))
+    backend.set_train(X, y)
+    n_host, g_host = backend.nll(1, theta, want_grad=True)
+    m_host, v_host = backend.predict(Xc)
+    dX, dy, dXc = (torch.from_numpy(a).cuda() for a in (X, y, Xc))
+    backend.set_train(dX, dy)
+    n_dev, g_dev = backend.nll(1, theta, want_grad=True)
+    dm = torch.empty(500, 1, dtype=torch.float64, device="cuda")
+    dv = torch.empty(500, dtype=torch.float64, device="cuda")
+    backend.predict(dXc, out_mean=dm, out_var=dv)
+    torch.cuda.synchronize()
+    assert n_host == n_dev and np.array_equal(g_host, g_dev)
+    assert np.array_equal(dm.cpu().numpy(), m_host) and np.array_equal(dv.cpu().numpy(), v_host)
+
+
+# ------------------------------------------------------------------------------------------ BASELINE sizes
+def _directional_fd(backend, kind, theta, v, h=1e-5):
+    return (backend.nll(kind, theta * (1 + h * v)) - backend.nll(kind, theta * (1 - h * v))) / (2 * h)
+
+
+@pytest.mark.parametrize("N,D,kind", [(4096, 8, 0), (16384, 10, 1)])
+def test_full_size_properties(backend, N, D, kind):
+    """BASELINE.json configs[1] / configs[2] shapes, where the oracle is too slow: size-independent properties --
+    run-to-run bit reproducibility, NLL consistency between the two code paths, a directional finite
+    difference of the NLL against the analytic gradient, and the exact chain-rule identity between NLL(N),
+    NLL(N-1) and the predictive density of the last point."""
+    X, y = oracle.synthetic_problem(N, D)
+    theta = np.concatenate([np.linspace(0.6, 1.2, D), [1.5, 0.3]])
+    backend.set_train(X, y)
+    nll, g = backend.nll(kind, theta, want_grad=True)
+    nll2, g2 = backend.nll(kind, theta, want_grad=True)
+    assert nll == nll2 and np.array_equal(g, g2)
+    assert backend.nll(kind, theta) == nll
+    v = np.random.default_rng(0).standard_normal(theta.size)
+    fd = _directional_fd(backend, kind, theta, v)
+    assert abs(fd - g @ (theta * v)) <= 1e-5 * np.abs(g * theta).max()
+    # Chain rule of the marginal likelihood ties the NLL path to the predict path (and N to N-1, i.e. a
+    # different padding of the last tile):  NLL(N) - NLL(N-1) = -log p(y_N | y_1..N-1)
+    #                                                        = 0.5 log(2 pi s2) + (y_N - mu)^2 / (2 s2).
+    backend.set_train(X[:-1], y[:-1])
+    nll_m1 = backend.nll(kind, theta)
+    backend.factorize(kind, theta)
+    mu, s2 = backend.predict(X[-1:], add_data_variance=True)
+    delta = 0.5 * np.log(2 * np.pi * s2[0]) + (y[-1, 0] - mu[0, 0]) ** 2 / (2 * s2[0])
+    assert abs((nll - nll_m1) - delta) <= 1e-9 * abs(nll)
+
+
+def test_matern_4096_vs_chunked_oracle(backend):
+    """Largest size the oracle's full NLL+gradient finishes in a few seconds on the host."""
+    N, D = 2048, 10
+    X, y = oracle.synthetic_problem(N, D)
+    theta = np.concatenate([np.linspace(0.6, 1.2, D), [1.5, 0.3]])
+    backend.set_train(X, y)
+    nll, g = backend.nll(1, theta, want_grad=True)
+    rn, rg = oracle.nll_cholesky(theta, X, y, oracle.matern52, eval_gradient=True)
+    assert abs(nll - rn) <= NLL_RTOL * abs(rn) and grad_err(g, rg) <= NLL_RTOL
+    Xc = np.random.default_rng(2).random((4096, D))
+    m, v = backend.predict(Xc)
+    rm, rv = oracle.predict(X, y, Xc, oracle.matern52, theta[:-2], theta[-2], theta[-1], chunk=1024)
+    assert np.max(np.abs(m - rm)) <= PRED_RTOL * np.abs(rm).max() and rel_err(v, rv.ravel()) <= PRED_RTOL
+
+
+def test_predict_8192_sharding_invariance(backend):
+    """configs[3] shape (N=8192) on a candidate sample: shards of the candidate set give the same per-candidate
+    numbers as one call, and the arg-max over shards equals the global arg-max."""
+    from profit_b200.distributed import shard_bounds
+
+    N, D, M = 8192, 10, 20000
+    X, y = oracle.synthetic_problem(N, D)
+    theta = np.concatenate([np.linspace(0.6, 1.2, D), [1.5, 0.3]])
+    backend.set_train(X, y)
+    backend.factorize(1, theta)
+    Xc = np.random.default_rng(2).random((M, D))
+    m, v = backend.predict(Xc)
+    best = []
+    for r in range(4):
+        lo, hi = shard_bounds(M, 4, r)
+        ms, vs = backend.predict(Xc[lo:hi])
+        assert np.array_equal(ms, m[lo:hi]) and np.array_equal(vs, v[lo:hi])
+        li, lv = backend.argmax(vs)
+        best.append((lv, -(lo + li)))
+    assert -max(best)[1] == int(np.argmax(v))
+    assert np.all(v > 0.09) and np.all(v < 1.5**2 + 0.09 + 1e-9)

@@ -1,0 +1,178 @@
+"""Host-side logic of the drop-in (no GPU): kernel selection, the log10 / fixed-sigma_n handling around the
+device objective, surrogate plumbing, sharding helpers, and the world_size-2 gloo path."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import rel_err
+from profit_b200 import gp_functions as gpf
+from profit_b200 import kernels
+from profit_b200.distributed import gather_argmax, shard_bounds
+from profit_b200.surrogate import B200GPSurrogate, _mean_pairwise_distance
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class OracleBackedFake:
+    """Stands in for GPBackend so the host logic can be exercised on CPU: same call surface, numbers from the
+    oracle.  (Test infrastructure only -- the product never does this.)"""
+
+    def __init__(self):
+        self.calls = 0
+
+    def set_train(self, X, y):
+        self.X, self.y = np.array(X), np.array(y)
+        self.n_out = 1 if self.y.ndim == 1 else self.y.shape[1]
+
+    def nll(self, kind, theta, want_grad=False):
+        self.calls += 1
+        kern = oracle.rbf if kind == 0 else oracle.matern52
+        return oracle.nll_cholesky(np.asarray(theta), self.X, self.y, kern, eval_gradient=want_grad)
+
+
+def test_select_kernel():
+    assert kernels.select_kernel("RBF") is kernels.RBF
+    assert kernels.select_kernel("Matern52") is kernels.Matern52
+    assert kernels.select_kernel(kernels.RBF) is kernels.RBF
+    assert kernels.select_kernel(oracle.rbf) is kernels.RBF          # any callable named "RBF" (e.g. the reference's)
+    assert kernels.RBF.__name__ == "RBF" and kernels.Matern52.__name__ == "Matern52"
+    with pytest.raises(RuntimeError, match="not implemented"):       # custom_surrogate.py:238
+        kernels.select_kernel("LinearEmbedding")
+
+
+@pytest.mark.parametrize("idx", [0, 3])
+def test_objective_wrappers_match_reference_semantics(golden, idx):
+    c = golden["synthetic"][idx]
+    X, y = oracle.synthetic_problem(c["N"], c["D"])
+    theta = np.array(c["theta"])
+    kern = kernels.select_kernel(c["kernel"])
+    be = OracleBackedFake()
+    be.set_train(X, y)
+    nll = gpf.negative_log_likelihood_cholesky(theta, X, y, kern, backend=be)
+    assert isinstance(nll, float) and abs(nll - c["nll"]) <= 1e-12 * abs(c["nll"])
+    nll, g = gpf.negative_log_likelihood_cholesky(theta, X, y, kern, eval_gradient=True, backend=be)
+    assert rel_err(g, c["grad"]) <= 1e-10
+    nw, gw = gpf.negative_log_likelihood(np.log10(theta), X, y, kern, eval_gradient=True, log_scale_hyp=True, backend=be)
+    assert abs(nw - c["wrapper_log10"]["nll"]) <= 1e-12 * abs(nw) and rel_err(gw, c["wrapper_log10"]["grad"]) <= 1e-10
+    nf, gf = gpf.negative_log_likelihood(np.log10(theta[:-1]), X, y, kern, eval_gradient=True, log_scale_hyp=True,
+                                         fixed_sigma_n_value=theta[-1], backend=be)
+    assert len(gf) == len(theta) - 1
+    assert abs(nf - c["wrapper_fixed_sn"]["nll"]) <= 1e-12 * abs(nf) and rel_err(gf, c["wrapper_fixed_sn"]["grad"]) <= 1e-10
+
+
+def test_optimize_driver_matches_reference_optimum(golden):
+    """gp_functions.optimize: same SciPy BFGS call as the reference -> same optimum on BASELINE configs[0]."""
+    c = golden["c0_train"]
+    X, y = np.array(c["X"]), np.array(c["y"])
+    s = B200GPSurrogate()
+    s._backend = OracleBackedFake()
+    s.train(X, y)
+    assert s.trained and s.kernel is kernels.RBF
+    hyp = np.concatenate([s.hyperparameters[k] for k in ("length_scale", "sigma_f", "sigma_n")])
+    assert all(v.ndim == 1 and v.dtype == np.float64 for v in s.hyperparameters.values())
+    assert np.allclose(hyp, c["hyp_opt"], rtol=1e-4)
+    assert abs(oracle.nll_cholesky(hyp, X, y, oracle.rbf) - c["nll_opt"]) <= 1e-8 * abs(c["nll_opt"])
+    # fixed sigma_n: one parameter fewer is optimised, sigma_n stays put
+    s2 = B200GPSurrogate()
+    s2._backend = OracleBackedFake()
+    s2.train(X, y, hyperparameters={"length_scale": np.array([0.3]), "sigma_f": np.array([1.0]),
+                                    "sigma_n": np.array([0.05])}, fixed_sigma_n=True)
+    assert s2.hyperparameters["sigma_n"][0] == 0.05 and s2.hyperparameters["length_scale"].shape == (1,)
+    s3 = B200GPSurrogate()
+    s3._backend = OracleBackedFake()
+    s3.train(X, y, return_hess_inv=True)
+    assert s3.hess_inv.shape == (3, 3)
+
+
+def test_surrogate_plumbing_and_errors(tmp_path):
+    rng = np.random.default_rng(0)
+    X, y = rng.random((30, 2)), rng.random(30)
+    s = B200GPSurrogate()
+    with pytest.raises(RuntimeError, match="train"):                  # sur.py:197-198
+        s.predict(X)
+    with pytest.raises(ValueError):
+        s.pre_train(rng.random((3, 2, 2)), y)
+    with pytest.raises(ValueError, match="mismatched"):
+        s.pre_train(X, y[:-1])
+    s.pre_train(X, y, kernel="RBF")
+    assert s.Xtrain.shape == (30, 2) and s.ytrain.shape == (30, 1) and s.ndim == 2
+    # inferred defaults, gaussian_process.py:124-136: l = 0.5*mean|x-x'| (scalar), sf = std(y), sn = 0.01*range(y)
+    dist = np.linalg.norm(X[:, None, :] - X[None, :, :], axis=-1)
+    assert np.allclose(s.hyperparameters["length_scale"], [0.5 * dist.mean()], rtol=1e-12)
+    assert np.allclose(s.hyperparameters["sigma_f"], [np.std(y)])
+    assert np.allclose(s.hyperparameters["sigma_n"], [1e-2 * (y.max() - y.min())])
+    assert abs(_mean_pairwise_distance(X, block=7) - dist.mean()) < 1e-13
+    # add_training_data / set_ytrain (test_units.py:28-45)
+    s.add_training_data(np.array([[0.1, 0.2]]), np.array([[0.3]]))
+    assert s.Xtrain.shape == (31, 2) and s.ytrain.shape == (31, 1) and s.ytrain[-1, 0] == 0.3
+    s.set_ytrain(np.arange(31.0).reshape(-1, 1))
+    assert s.ytrain[5, 0] == 5.0
+    s.trained = True
+    with pytest.raises(ValueError):
+        s.pre_predict(rng.random((4, 3)))
+    # save / load round trip keeps the reference's attribute set
+    path = str(tmp_path / "model.npz")
+    s.save_model(path)
+    t = B200GPSurrogate.load_model(path)
+    assert t.trained and t.ndim == 2 and t.kernel is kernels.RBF and t.kernel.__name__ == "RBF"
+    assert np.array_equal(t.Xtrain, s.Xtrain) and np.array_equal(t.ytrain, s.ytrain)
+    for k in ("length_scale", "sigma_f", "sigma_n"):
+        assert np.array_equal(t.hyperparameters[k], s.hyperparameters[k])
+    with pytest.raises(RuntimeError, match="not implemented"):
+        s.select_kernel("Wendland4")
+
+
+def test_shard_bounds_cover_everything_once():
+    for M in (0, 1, 7, 8, 1000, 2**22):
+        for G in (1, 2, 3, 4, 8):
+            spans = [shard_bounds(M, G, r) for r in range(G)]
+            assert spans[0][0] == 0 and spans[-1][1] == M
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(hi - lo for lo, hi in spans) == -(-M // G) if M else True
+    assert gather_argmax(3.5, 17) == (17, 3.5)      # single process: identity
+
+
+_WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import numpy as np, torch.distributed as dist
+from profit_b200.distributed import gather_argmax, gather_argmin_rows, shard_bounds, world
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+rank, ws = world()
+v = np.sin(np.arange(1001) * 0.37); v[[100, 900]] = 2.0           # a tie across the two shards
+lo, hi = shard_bounds(len(v), ws, rank)
+li = int(np.argmax(v[lo:hi]))
+idx, val = gather_argmax(v[lo:hi][li], lo + li)
+assert (idx, val) == (int(np.argmax(v)), 2.0) and idx == 100, (idx, val)
+idx, val = gather_argmax(-np.inf, -1) if rank == 1 else gather_argmax(1.0, 5)   # an empty shard
+assert (idx, val) == (5, 1.0)
+rows = np.array([[r, 10.0 - (r % 3), 0.1 * r, 0.2] for r in range(rank, 5, ws)])   # restarts r -> rank r mod G
+best, table = gather_argmin_rows(rows)
+assert best[0] == 2 and best[1] == 8.0 and table.shape == (5, 4) and list(table[:, 0]) == [0, 1, 2, 3, 4]
+dist.barrier(); dist.destroy_process_group()
+print("worker", rank, "ok")
+'''
+
+
+def test_world_size_2_gloo_gathers(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    port = str(29500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and f"worker {r} ok" in o, o
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/profit"), reason="reference tree not mounted")
+def test_registers_with_profit_when_available():
+    code = ("import profit_b200.surrogate as s; from profit.sur import Surrogate; from profit.sur.gp import GaussianProcess;"
+            "c = Surrogate['B200']; assert c is s.B200GPSurrogate and issubclass(c, GaussianProcess); print('registered')")
+    env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + "/root/reference", PYTHONDONTWRITEBYTECODE="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "registered" in out.stdout, out.stderr

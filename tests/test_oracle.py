@@ -1,0 +1,144 @@
+"""The CPU oracle against the reference's known answers (committed golden vectors) and, when the reference is
+mounted, against the live reference.  No GPU."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import rel_err
+
+KERN = {"RBF": oracle.rbf, "Matern52": oracle.matern52}
+
+
+def test_kat1_grad_nll_fixture(golden):
+    k = golden["kat1"]
+    nll, g = oracle.nll_cholesky(np.array(k["hyp"]), np.array(k["X"]), np.array(k["y"]), oracle.rbf, eval_gradient=True)
+    assert abs(nll - k["nll"]) <= 1e-12 * abs(k["nll"])
+    assert rel_err(g, k["grad"]) <= 1e-12
+    # the survey's frozen values
+    assert abs(k["nll"] - 1.9722432670948513) < 1e-14
+    assert np.allclose(k["grad"], [0.00636503697630928, -0.01083208294680081, 0.4185845267735342, 2.8176562446606948],
+                       rtol=1e-13)
+
+
+def test_kat2_build_K_fixture(golden):
+    k = golden["kat2"]
+    K, dK = oracle.rbf(np.array(k["Xa"]), np.array(k["Xb"]), np.array(k["length_scale"]), 1.0, 0.0, eval_gradient=True)
+    assert np.allclose(K, k["K"], rtol=1e-15, atol=0)
+    assert np.allclose(dK, k["dK"], rtol=1e-14, atol=1e-300)
+    assert np.allclose(k["K"], [[1, 0.9219631718378984], [0.9950124791926823, 0.9358968608271978],
+                                [0.9920195145156273, 0.8789629784396834]], rtol=1e-15)
+
+
+def test_kat3_kat4_halton(golden):
+    h = golden["halton128"]
+    X, y = np.array(h["X"]), np.array(h["y"])
+    n4, g4 = oracle.nll_cholesky(np.array(h["kat4"]["hyp"]), X, y, oracle.rbf, eval_gradient=True)
+    assert abs(n4 - h["kat4"]["nll"]) <= 1e-11 * abs(h["kat4"]["nll"])
+    assert rel_err(g4, h["kat4"]["grad"]) <= 1e-9
+    n3, g3 = oracle.nll_cholesky(np.array(h["kat3"]["hyp"]), X, y, oracle.rbf, eval_gradient=True)
+    assert abs(n3 - h["kat3"]["nll"]) <= 1e-6 * abs(h["kat3"]["nll"])   # cond(K) = 7.7e9
+    assert rel_err(g3, h["kat3"]["grad"]) <= 1e-4
+
+
+def test_sine10_linear_algebra(golden):
+    s = golden["sine10"]
+    X, y = np.array(s["X"]), np.array(s["y"])
+    Ky = oracle.rbf(X, X, 1.0, 1.0)
+    assert np.array_equal(Ky, Ky.T)                           # test_gp.py:24
+    assert np.allclose(Ky, s["Ky"], rtol=1e-15)
+    L = np.linalg.cholesky(Ky)
+    alpha = oracle.solve_cholesky(L, y)
+    assert np.allclose(alpha, s["alpha"], rtol=1e-12)
+    assert np.allclose(alpha, np.linalg.solve(Ky, y), rtol=1e-10, atol=1e-10)   # test_gp.py:31
+    assert np.allclose(oracle.invert_cholesky(L), s["Kinv"], rtol=1e-10)
+    ypred = oracle.rbf(np.array(s["xtest"]), X, 1.0, 1.0).dot(alpha)
+    assert np.allclose(np.array(y), ypred[::10], rtol=1e-14, atol=1e-14)        # test_gp.py:37
+
+
+@pytest.mark.parametrize("idx", range(5))
+def test_synthetic_cases(golden, idx):
+    c = golden["synthetic"][idx]
+    X, y = oracle.synthetic_problem(c["N"], c["D"])
+    theta = np.array(c["theta"])
+    kern = KERN[c["kernel"]]
+    nll, g = oracle.nll_cholesky(theta, X, y, kern, eval_gradient=True, block=100)   # ragged row blocks
+    assert abs(nll - c["nll"]) <= 1e-13 * abs(c["nll"])
+    assert rel_err(g, c["grad"]) <= 1e-11
+    nw, gw = oracle.nll(np.log10(theta), X, y, kern, eval_gradient=True, log_scale_hyp=True)
+    assert abs(nw - c["wrapper_log10"]["nll"]) <= 1e-13 * abs(nw)
+    assert rel_err(gw, c["wrapper_log10"]["grad"]) <= 1e-11
+    nf, gf = oracle.nll(np.log10(theta[:-1]), X, y, kern, eval_gradient=True, log_scale_hyp=True,
+                        fixed_sigma_n_value=theta[-1])
+    assert abs(nf - c["wrapper_fixed_sn"]["nll"]) <= 1e-13 * abs(nf)
+    assert len(gf) == len(theta) - 1 and rel_err(gf, c["wrapper_fixed_sn"]["grad"]) <= 1e-11
+    Xc = np.random.default_rng(c["predict"]["seed"]).random((c["predict"]["M"], c["D"]))
+    ell = theta[:-2] if c["n_ell"] > 1 else theta[0]
+    m, v = oracle.predict(X, y, Xc, kern, ell, theta[-2], theta[-1], chunk=40)      # ragged chunks
+    assert rel_err(m, c["predict"]["mean"]) <= 1e-10
+    assert rel_err(v, c["predict"]["var"]) <= 1e-9
+    _, v0 = oracle.predict(X, y, Xc, kern, ell, theta[-2], theta[-1], add_data_variance=False)
+    assert rel_err(v0, c["predict"]["var_nodata"]) <= 1e-8
+    if "predict_f" in c:
+        f, vf = oracle.predict_f(theta, X, y, Xc, kern)
+        assert rel_err(f, c["predict_f"]["mean"]) <= 1e-10
+        assert rel_err(vf, c["predict_f"]["var"]) <= 1e-9
+
+
+def test_multi_output(golden):
+    c = golden["multi_output"]
+    X, _ = oracle.synthetic_problem(c["N"], c["D"])
+    nll, g = oracle.nll_cholesky(np.array(c["theta"]), X, np.array(c["Y"]), oracle.rbf, eval_gradient=True)
+    assert abs(nll - c["nll"]) <= 1e-13 * abs(c["nll"])
+    assert rel_err(g, c["grad"]) <= 1e-11
+
+
+def test_matern_against_sklearn_vectors(golden):
+    c = golden["matern_sklearn"]
+    X = np.random.default_rng(c["seed"]).random((c["n"], c["D"]))
+    ell = np.array(c["length_scale"])
+    K, dK = oracle.matern52(X, X, ell, 1.0, 0.0, eval_gradient=True)
+    assert np.abs(K - np.array(c["K"])).max() <= 1e-15
+    assert np.abs(dK[..., :-2] * ell - np.array(c["dK_dlogl"])).max() <= 2e-15
+    assert np.all(dK[..., -1] == 0.0)
+
+
+def test_matern_gradient_finite_difference():
+    X, y = oracle.synthetic_problem(60, 3)
+    theta = np.array([0.7, 0.9, 1.1, 1.5, 0.3])
+    _, g = oracle.nll_cholesky(theta, X, y, oracle.matern52, eval_gradient=True)
+    for p in range(len(theta)):
+        e = np.zeros_like(theta)
+        e[p] = 1e-6
+        fd = (oracle.nll_cholesky(theta + e, X, y, oracle.matern52) - oracle.nll_cholesky(theta - e, X, y, oracle.matern52)) / 2e-6
+        assert abs(fd - g[p]) <= 1e-6 * max(1.0, abs(g[p]))
+
+
+def test_not_spd_raises():
+    X = np.zeros((4, 2))   # identical points, no noise -> singular
+    with pytest.raises(np.linalg.LinAlgError):
+        oracle.nll_cholesky(np.array([1.0, 1.0, 1.0, 0.0]), X, np.ones(4), oracle.rbf)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/profit"), reason="reference tree not mounted")
+def test_oracle_against_live_reference():
+    sys.path.insert(0, "/root/reference")
+    sys.dont_write_bytecode = True
+    from profit.sur.gp.backend import gp_functions as G
+    from profit.sur.gp.backend.python_kernels import RBF
+
+    X, y = oracle.synthetic_problem(333, 6)
+    theta = np.concatenate([np.linspace(0.6, 1.2, 6), [1.5, 0.3]])
+    for yy in (y, y.ravel()):
+        a = G.negative_log_likelihood_cholesky(theta, X, yy, RBF, eval_gradient=True)
+        b = oracle.nll_cholesky(theta, X, yy, oracle.rbf, eval_gradient=True, block=128)
+        assert abs(a[0] - b[0]) <= 1e-13 * abs(a[0]) and rel_err(b[1], a[1]) <= 1e-12
+    K1, dK1 = RBF(X[:50], X[:70], theta[:6], 1.5, 0.3, eval_gradient=True)
+    K2, dK2 = oracle.rbf(X[:50], X[:70], theta[:6], 1.5, 0.3, eval_gradient=True)
+    assert np.array_equal(K1, K2) and np.array_equal(dK1, dK2)
+    # the reference's own NLL algebra with the oracle's Matern callable plugged in
+    a = G.negative_log_likelihood_cholesky(theta, X, y, oracle.matern52, eval_gradient=True)
+    b = oracle.nll_cholesky(theta, X, y, oracle.matern52, eval_gradient=True)
+    assert abs(a[0] - b[0]) <= 1e-13 * abs(a[0]) and rel_err(b[1], a[1]) <= 1e-12
