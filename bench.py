@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""Headline benchmark: NLL+gradient evaluations per second of the Matern-5/2 ARD GP, N=16384, D=10, fp64
+(BASELINE.json metric, configs[2]); the active-learning candidate-prediction throughput (configs[3] shape,
+N=8192 training points) rides along in the same JSON line under "al_predict".
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm on the host cores
+
+One "step" = one NLL+gradient evaluation (Cholesky + triangular inverse + K^-1 + gradient contraction).
+N > 1 (torchrun, one rank per GPU): the path does not shard inside one evaluation, so ranks evaluate
+independent multi-start restarts (weak scaling) and NCCL only gathers (nll, theta) for the best-NLL pick;
+candidate prediction shards candidates and gathers the arg-max.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_TRAIN, DIM = 16384, 10                 # BASELINE configs[2]
+N_TRAIN_PRED, M_FULL = 8192, 1 << 22     # BASELINE configs[3]
+METRIC = "NLL+grad evals/s (N=16384, D=10, fp64)"
+UNIT = "evals/s"
+DMMA_CEILING_TFLOPS = 37.05              # profiles/r01_probe_fp64_dmma.txt: register-resident DMMA.8x8x4 issue rate
+
+
+def synthetic_problem(N, D, seed_x=0, seed_y=1, sigma_n=0.3):
+    """Deterministic inputs of SURVEY.md section 8d (same generator as oracle.synthetic_problem; the GPU legs do
+    not import the oracle): X ~ U[0,1)^(N,D), y = sin 3x0 + cos 2x1 + sum_{d>=2} x_d + sigma_n N(0,1)."""
+    X = np.random.default_rng(seed_x).random((N, D))
+    f = np.sin(3 * X[:, 0]) + np.cos(2 * X[:, 1]) + X[:, 2:].sum(axis=1)
+    y = f + sigma_n * np.random.default_rng(seed_y).standard_normal(N)
+    return X, y.reshape(-1, 1)
+
+
+def theta_ref(D):
+    return np.concatenate([np.linspace(0.6, 1.2, D), [1.5, 0.3]])
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, flag in zip(names, r[3:7]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_setup(gpus):
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, local, dist
+
+
+def max_over_ranks(x, dist, local):
+    if dist is None:
+        return x
+    import torch
+
+    t = torch.tensor([x], dtype=torch.float64, device=torch.device("cuda", local))
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier(dist):
+    import torch
+
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+# ------------------------------------------------------------------------------------------------ CPU leg
+def cpu_nll_grad_sample(n_sample, steps=1):
+    """Reference algorithm on the host cores: the oracle port of gp_functions.negative_log_likelihood_cholesky
+    (row-blocked, O(N^2 P) gradient contraction) on a bounded sample.  The sample is scaled to N=16384 phase by
+    phase: Cholesky / solves / inverse with (N/n)^3, assembly and contraction with (N/n)^2."""
+    import oracle
+
+    X, y = oracle.synthetic_problem(n_sample, DIM)
+    th = theta_ref(DIM)
+    best, best_t = float("inf"), None
+    for _ in range(steps):
+        tm = {}
+        t0 = time.perf_counter()
+        oracle.nll_cholesky(th, X, y, oracle.matern52, eval_gradient=True, timings=tm)
+        dt = time.perf_counter() - t0
+        if dt < best:
+            best, best_t = dt, tm
+    r = N_TRAIN / n_sample
+    full = best_t["cubic"] * r**3 + best_t["quadratic"] * r**2
+    cores = len(os.sched_getaffinity(0))
+    return {"value": 1.0 / full, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"one NLL+grad eval of the oracle port at N={n_sample}, D={DIM} Matern-5/2: {best:.2f} s "
+                      f"({best_t['cubic']:.2f} s O(N^3) phases scaled by {r**3:.0f}, {best_t['quadratic']:.2f} s "
+                      f"O(N^2 P) phases scaled by {r**2:.0f}) -> {full:.0f} s per eval at N=16384; the unmodified "
+                      f"reference cannot hold N=16384 (>70 GB of (N,N,D) temporaries)",
+            "sample_seconds": best, "scaled_seconds": full}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    warm = cpu_nll_grad_sample(1024)           # page in numpy/BLAS
+    del warm
+    for _ in range(max(1, args.warmup // 3)):
+        cpu_nll_grad_sample(args.cpu_sample_n)
+    samples = [cpu_nll_grad_sample(args.cpu_sample_n) for _ in range(args.steps)]
+    sec = statistics.mean(s["scaled_seconds"] for s in samples)
+    cores = len(os.sched_getaffinity(0))
+    sample = (f"{args.steps} x " + samples[0]["sample"])
+    line = {"impl": "reference", "metric": METRIC, "value": 1.0 / sec, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(),
+            "cpu_baseline": {"value": 1.0 / sec, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": 1.0 / sec, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config():
+    return {"workload": "Matern-5/2 ARD GP NLL+gradient, N=16384, D=10, P=12 (BASELINE configs[2])",
+            "n_train": N_TRAIN, "dim": DIM, "kernel": "Matern52", "theta": "l=linspace(0.6,1.2,10), sf=1.5, sn=0.3",
+            "l2": "inputs larger than L2: every evaluation streams the 2.1 GB factor (and two more 2.1 GB "
+                  "triangles for the inverse) through HBM, 126 MB L2",
+            "parallelism": "replicas (independent multi-start restarts per GPU; NCCL gathers best NLL only)"}
+
+
+# ------------------------------------------------------------------------------------------------ GPU legs
+def fp64_gemm_peak(local):
+    """cuBLAS DGEMM 8192^3, best of 5 after warm-up -- the measured FP64 tensor roofline denominator
+    (MEASURED_PEAKS.json carries HBM and bf16 only)."""
+    import torch
+
+    dev = torch.device("cuda", local)
+    n = 8192
+    a = torch.randn(n, n, dtype=torch.float64, device=dev)
+    b = torch.randn(n, n, dtype=torch.float64, device=dev)
+    torch.matmul(a, b.T)
+    torch.cuda.synchronize()
+    best = float("inf")
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b.T)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    del a, b
+    torch.cuda.empty_cache()
+    return 2 * n**3 / best * 1e-9
+
+
+def run_gpu(args):
+    import torch
+
+    from profit_b200 import GPBackend, KIND_MATERN52, Matern52, gp_functions as gpf
+    from profit_b200.distributed import gather_argmax, gather_argmin_rows, shard_bounds
+
+    rank, world, local, dist = dist_setup(args.gpus)
+    torch.cuda.set_device(local)
+    be = GPBackend(local)
+    out = {}
+
+    # ---------------- NLL + gradient (headline) ----------------
+    X, y = synthetic_problem(N_TRAIN, DIM)
+    th0 = theta_ref(DIM)
+    # every rank/step gets its own hyper-parameters (multi-start restarts): nothing can be cached across steps
+    def theta_of(step, r=rank):
+        return th0 * 10 ** (0.05 * np.sin(1.0 + 0.7 * (r * 131 + step) + np.arange(th0.size)))
+
+    be.set_train(X, y)
+    for w in range(args.warmup):
+        be.nll(KIND_MATERN52, theta_of(-1 - w), want_grad=True)
+    stages = {k: 0.0 for k in ("assemble", "potrf", "trtri", "syrk", "grad", "total")}
+    results = []
+    barrier(dist)
+    launches0 = be.launch_count()
+    with ClockSampler(local) as clocks:
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            nll, g = be.nll(KIND_MATERN52, theta_of(k), want_grad=True)
+            results.append(np.concatenate([[rank * args.steps + k, nll], theta_of(k)]))
+            st = be.stage_ms()
+            for key in stages:
+                stages[key] += st[key]
+        torch.cuda.synchronize()
+        elapsed = time.perf_counter() - t0
+    launches = be.launch_count() - launches0
+    barrier(dist)
+    elapsed = max_over_ranks(elapsed, dist, local)
+    best_row, _ = gather_argmin_rows(np.array(results))      # the only collective: (nll, theta) per restart
+    value = world * args.steps / elapsed
+    dense_ms = (stages["potrf"] + stages["trtri"] + stages["syrk"]) / args.steps
+
+    # end to end: the reference-facing function with HOST buffers (pinned), H2D of (X, y, theta) and D2H of
+    # (nll, grad) inside every step
+    Xp = torch.from_numpy(X).pin_memory()
+    yp = torch.from_numpy(y).pin_memory()
+    Xh, yh = Xp.numpy(), yp.numpy()
+    gpf.negative_log_likelihood(np.log10(theta_of(-9)), Xh, yh, Matern52, True, True, backend=None)
+    barrier(dist)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        gpf.negative_log_likelihood(np.log10(theta_of(1000 + k)), Xh, yh, Matern52, True, True, backend=None)
+    torch.cuda.synchronize()
+    e2e_elapsed = max_over_ranks(time.perf_counter() - t0, dist, local)
+    barrier(dist)
+    P = th0.size
+    e2e = {"value": world * args.steps / e2e_elapsed, "unit": UNIT,
+           "h2d_bytes_per_step": int(X.nbytes + y.nbytes + P * 8), "d2h_bytes_per_step": int((P + 1) * 8 + 4),
+           "api": "profit_b200.gp_functions.negative_log_likelihood(hyp_log10, X, y, Matern52, eval_gradient=True, "
+                  "log_scale_hyp=True) with pinned host arrays"}
+
+    # ---------------- candidate prediction (configs[3] shape, bounded sample unless --predict-full) -------
+    pred = None
+    if not args.skip_predict:
+        Xt, yt = synthetic_problem(N_TRAIN_PRED, DIM)
+        M_total = M_FULL if args.predict_full else args.predict_candidates * world
+        lo, hi = shard_bounds(M_total, world, rank)
+        Xc = np.random.default_rng(2 + rank).random((hi - lo, DIM))
+        bp = GPBackend(local)
+        bp.set_train(Xt, yt)
+        bp.factorize(KIND_MATERN52, th0)
+        dXc = torch.from_numpy(Xc).cuda()
+        dmean = torch.empty(hi - lo, 1, dtype=torch.float64, device="cuda")
+        dvar = torch.empty(hi - lo, dtype=torch.float64, device="cuda")
+        bp.predict(dXc, out_mean=dmean, out_var=dvar)                       # warm-up (allocates the chunk buffers)
+        psteps = max(1, min(args.steps, 3))
+        barrier(dist)
+        l0 = bp.launch_count()
+        var_ms = 0.0
+        t0 = time.perf_counter()
+        for _ in range(psteps):
+            bp.predict(dXc, out_mean=dmean, out_var=dvar)
+            var_ms += bp.stage_ms()["var"]
+        torch.cuda.synchronize()
+        p_elapsed = max_over_ranks(time.perf_counter() - t0, dist, local)
+        p_launch = bp.launch_count() - l0
+        li, lv = bp.argmax(dvar)
+        gidx, gval = gather_argmax(lv, lo + li)
+        # end to end from pinned host candidates to host mean/var
+        Xcp = torch.from_numpy(Xc).pin_memory().numpy()
+        hm = torch.empty(hi - lo, 1, dtype=torch.float64).pin_memory().numpy()
+        hv = torch.empty(hi - lo, dtype=torch.float64).pin_memory().numpy()
+        barrier(dist)
+        t0 = time.perf_counter()
+        for _ in range(psteps):
+            bp.predict(Xcp, out_mean=hm, out_var=hv)
+        pe_elapsed = max_over_ranks(time.perf_counter() - t0, dist, local)
+        flop_per_cand = float(N_TRAIN_PRED) ** 2                            # triangular L^-1 k*: N^2 flop
+        tf = (hi - lo) * psteps * flop_per_cand / (var_ms * 1e-3) * 1e-12 if var_ms > 0 else None
+        pred = {"metric": "AL candidate predictions/s", "unit": "candidates/s",
+                "value": M_total * psteps / p_elapsed,
+                "e2e": {"value": M_total * psteps / pe_elapsed, "unit": "candidates/s",
+                        "h2d_bytes_per_step": int(Xc.nbytes), "d2h_bytes_per_step": int(hm.nbytes + hv.nbytes)},
+                "n_train": N_TRAIN_PRED, "candidates_per_step": int(M_total), "steps": psteps,
+                "workload": ("2^22 candidates (BASELINE configs[3])" if args.predict_full else
+                             f"{M_total} candidates = bounded sample of the 2^22-candidate set of configs[3]"),
+                "argmax": [int(gidx), float(gval)], "gpu_launches": int(p_launch),
+                "variance_gemm_tflops": tf}
+        bp.close()
+
+    if rank != 0:
+        be.close()
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peak = fp64_gemm_peak(local)
+    achieved = float(N_TRAIN) ** 3 / (dense_ms * 1e-3) * 1e-12
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": None,
+                "kernel": "gpb::dgemm_tasks_kernel (DMMA.8x8x4 tile GEMM behind potrf / trtri / syrk)",
+                "algorithmic_flops_per_eval": float(N_TRAIN) ** 3,
+                "dense_ms_per_eval": dense_ms,
+                "peak_source": "cuBLAS DGEMM fp64 8192^3 measured in this run (MEASURED_PEAKS.json has no fp64 "
+                               f"entry); DMMA.8x8x4 issue ceiling {DMMA_CEILING_TFLOPS} TFLOP/s",
+                "stage_tflops": {s: (float(N_TRAIN) ** 3 / 3) / (stages[s] / args.steps * 1e-3) * 1e-12
+                                 for s in ("potrf", "trtri", "syrk")},
+                "stage_ms": {s: stages[s] / args.steps for s in stages}}
+    if pred is not None and pred["variance_gemm_tflops"]:
+        pred["roofline"] = {"bound": "tensor", "achieved": pred["variance_gemm_tflops"], "peak": peak,
+                            "unit": "TFLOP/s", "frac": pred["variance_gemm_tflops"] / peak, "traffic": None}
+    cpu = cpu_nll_grad_sample(args.cpu_sample_n) if not args.skip_cpu else None
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(), "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks.summary(), "roofline": roofline, "cpu_baseline": cpu,
+            "best_restart": {"index": int(best_row[0]), "nll": float(best_row[1])},
+            "al_predict": pred}
+    print(json.dumps(line), flush=True)
+    be.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-sample-n", type=int, default=4096, help="size of the bounded CPU sample evaluation")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-predict", action="store_true")
+    ap.add_argument("--predict-candidates", type=int, default=1 << 17, help="candidates per GPU in the predict leg")
+    ap.add_argument("--predict-full", action="store_true", help="run all 2^22 candidates of configs[3]")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if not os.path.exists(os.path.join(ROOT, "profit_b200", "libgpb.so")):
+            import __graft_entry__ as entry
+
+            entry.build()
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()
