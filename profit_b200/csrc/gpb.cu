@@ -44,15 +44,20 @@ struct Launch {
   size_t task_off;
   int ntasks;
   int epi;
+  int stream = 0;    // 0 = main stream, 1 = panel (look-ahead) stream
+  int wait_ev = -1;  // event to wait for before the launch (index into the handle's event pool)
+  int rec_ev = -1;   // event recorded after the launch
 };
 
 struct Plan {
   std::vector<Launch> launches;
   std::vector<GemmTask> tasks;
+  int num_events = 0;
   GemmTask* d_tasks = nullptr;
   void clear() {
     launches.clear();
     tasks.clear();
+    num_events = 0;
     if (d_tasks) cudaFree(d_tasks);
     d_tasks = nullptr;
   }
@@ -81,6 +86,8 @@ struct Workspace {
 struct gpb_handle_s {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;   // high-priority panel stream for the Cholesky look-ahead
+  std::vector<cudaEvent_t> events;
   std::string err;
   EncodeTiledFn encode = nullptr;
   long long launches = 0;
@@ -184,8 +191,8 @@ void set_mat(Workspace& w, int id, double* p, long long rows, long long cols, lo
 
 // ------------------------------------------------------------------------------------------------ GEMM launch
 template <int BM, int BN, int WM, int WN, int ST, int EPI, int MINB>
-int launch_cfg(H* h, const CUtensorMap& tA, const CUtensorMap& tB, const GemmTask* tasks, int ntasks,
-               const GemmEpilogue& ep) {
+int launch_cfg(H* h, cudaStream_t stream, const CUtensorMap& tA, const CUtensorMap& tB, const GemmTask* tasks,
+               int ntasks, const GemmEpilogue& ep) {
   auto kern = dgemm_tasks_kernel<BM, BN, WM, WN, ST, EPI, MINB>;
   constexpr int smem = GemmSmem<BM, BN, ST>::BYTES;
   static bool configured = false;
@@ -194,7 +201,7 @@ int launch_cfg(H* h, const CUtensorMap& tA, const CUtensorMap& tB, const GemmTas
     configured = true;
   }
   constexpr int threads = (BM / WM) * (BN / WN) * 32 + 32;
-  kern<<<ntasks, threads, smem, h->stream>>>(tA, tB, tasks, ep);
+  kern<<<ntasks, threads, smem, stream>>>(tA, tB, tasks, ep);
   h->launches++;
   CK(cudaGetLastError());
   return 0;
@@ -209,7 +216,8 @@ void cfg_tile(int cfg, int* bm, int* bn) {
 }
 
 int launch_gemm(H* h, Workspace& w, int cfg, int epi, int matA, int matB, const GemmTask* d_tasks, int ntasks,
-                const GemmEpilogue& ep) {
+                const GemmEpilogue& ep, cudaStream_t stream = nullptr) {
+  if (!stream) stream = h->stream;
   if (ntasks <= 0) return 0;
   int bm, bn;
   cfg_tile(cfg, &bm, &bn);
@@ -219,14 +227,14 @@ int launch_gemm(H* h, Workspace& w, int cfg, int epi, int matA, int matB, const 
   if ((rc = get_map(h, w, matB, bn, &tB))) return rc;
   if (epi == EPI_STORE) {
     switch (cfg) {
-      case CFG_128x128: return launch_cfg<128, 128, 64, 32, 4, EPI_STORE, 1>(h, tA, tB, d_tasks, ntasks, ep);
-      case CFG_128x64: return launch_cfg<128, 64, 32, 32, 4, EPI_STORE, 2>(h, tA, tB, d_tasks, ntasks, ep);
-      default: return launch_cfg<64, 128, 32, 32, 4, EPI_STORE, 2>(h, tA, tB, d_tasks, ntasks, ep);
+      case CFG_128x128: return launch_cfg<128, 128, 64, 32, 4, EPI_STORE, 1>(h, stream, tA, tB, d_tasks, ntasks, ep);
+      case CFG_128x64: return launch_cfg<128, 64, 32, 32, 4, EPI_STORE, 2>(h, stream, tA, tB, d_tasks, ntasks, ep);
+      default: return launch_cfg<64, 128, 32, 32, 4, EPI_STORE, 2>(h, stream, tA, tB, d_tasks, ntasks, ep);
     }
   } else {
     switch (cfg) {
-      case CFG_128x128: return launch_cfg<128, 128, 64, 32, 4, EPI_COLSQ, 1>(h, tA, tB, d_tasks, ntasks, ep);
-      case CFG_128x64: return launch_cfg<128, 64, 32, 32, 4, EPI_COLSQ, 2>(h, tA, tB, d_tasks, ntasks, ep);
+      case CFG_128x128: return launch_cfg<128, 128, 64, 32, 4, EPI_COLSQ, 1>(h, stream, tA, tB, d_tasks, ntasks, ep);
+      case CFG_128x64: return launch_cfg<128, 64, 32, 32, 4, EPI_COLSQ, 2>(h, stream, tA, tB, d_tasks, ntasks, ep);
       default: return fail(h, -1, "no column-norm epilogue for this tile configuration");
     }
   }
@@ -235,6 +243,7 @@ int launch_gemm(H* h, Workspace& w, int cfg, int epi, int matA, int matB, const 
 // ------------------------------------------------------------------------------------------------ plans
 int g_cfg_update = CFG_128x64;  // trailing updates / trtri / syrk / predict   (env GPB_CFG_UPDATE)
 int g_outer_blocks = 4;         // outer panel width of the Cholesky in 128-blocks (env GPB_OUTER_BLOCKS)
+int g_lookahead = 1;            // overlap the next panel factorisation with the trailing update (env GPB_LOOKAHEAD)
 
 struct TaskSink {
   Plan& p;
@@ -259,36 +268,81 @@ struct TaskSink {
       std::stable_sort(p.tasks.begin() + begin, p.tasks.end(),
                        [](const GemmTask& a, const GemmTask& b) { return a.nk > b.nk; });
     p.launches.push_back({1, 0, cfg, matA, matB, matC, matCt, alpha, beta, begin, n, epi});
+    last = (int)p.launches.size() - 1;
   }
+  int last = -1;  // index of the launch emitted by finish(), -1 if the task list was empty
 };
 
+// Two-level right-looking Cholesky with one panel of look-ahead.
+//   P(J)     : factor outer panel J (per 128-column: diagonal block, panel solve, update of the panel's own
+//              remaining columns)                                                        -- panel stream
+//   T1(J)    : update the columns of panel J+1 with panel J                              -- panel stream
+//   T2(J)    : update every column right of panel J+1 with panel J                       -- main stream
+// P(J+1) only depends on T1(J), so it runs concurrently with the large T2(J).  Events: evP[J] after P(J),
+// evM[J] after T2(J);  T1(J) waits evM[J-1] (both touch panel J+1's columns), T2(J) waits evP[J].
+// With g_lookahead == 0 everything is issued on the main stream in dependency order (no events).
 void build_potrf_plan(Workspace& w) {
   Plan& p = w.potrf;
   p.clear();
   const int Nb = (int)w.Nb, OB = g_outer_blocks, cfg = g_cfg_update;
   const int aug = Nb;  // block-row index of the y^T rows
-  for (int J = 0; J < Nb; J += OB) {
-    const int Je = std::min(J + OB, Nb);
-    for (int k = J; k < Je; ++k) {
-      p.launches.push_back({0, k, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0});
+  const int nJ = (Nb + OB - 1) / OB;
+  const bool la = g_lookahead != 0;
+  const int ps = la ? 1 : 0;           // stream of the panel work
+  auto evP = [&](int J) { return J; };
+  auto evM = [&](int J) { return nJ + J; };
+  p.num_events = la ? 2 * nJ : 0;
+
+  auto emit_panel = [&](int J) {
+    const int J0 = J * OB, Je = std::min(J0 + OB, Nb);
+    for (int k = J0; k < Je; ++k) {
+      Launch dg{0, k, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+      dg.stream = ps;
+      p.launches.push_back(dg);
       {  // panel solve: L_ik = A_ik W_kk^T, in place (64-row tiles own all the columns they read)
         TaskSink s(p);
         for (int i = k + 1; i <= aug; ++i) s.block(CFG_64x128, i * 128, k * 128, k * 128, 0, 8, i * 128, k * 128);
         s.finish(CFG_64x128, EPI_STORE, M_L, M_DINV, M_L, M_NONE, 1.0, 0.0, false);
+        if (s.last >= 0) p.launches[s.last].stream = ps;
       }
       {  // update the remaining columns of the current outer panel with block column k
         TaskSink s(p);
         for (int j = k + 1; j < Je; ++j)
           for (int i = j; i <= aug; ++i) s.block(cfg, i * 128, k * 128, j * 128, k * 128, 8, i * 128, j * 128);
         s.finish(cfg, EPI_STORE, M_L, M_L, M_L, M_NONE, -1.0, 1.0, false);
+        if (s.last >= 0) p.launches[s.last].stream = ps;
       }
     }
-    {  // trailing update with the whole outer panel (K = 128 * panel width)
-      TaskSink s(p);
-      for (int j = Je; j < Nb; ++j)
-        for (int i = j; i <= aug; ++i)
-          s.block(cfg, i * 128, J * 128, j * 128, J * 128, 8 * (Je - J), i * 128, j * 128);
-      s.finish(cfg, EPI_STORE, M_L, M_L, M_L, M_NONE, -1.0, 1.0, false);
+    if (la) p.launches.back().rec_ev = evP(J);
+  };
+  // columns [jb0, jb1) (in 128-blocks) updated with panel J
+  auto emit_update = [&](int J, int jb0, int jb1, int stream, int wait_ev, int rec_ev) {
+    const int J0 = J * OB, Je = std::min(J0 + OB, Nb);
+    TaskSink s(p);
+    for (int j = jb0; j < jb1; ++j)
+      for (int i = j; i <= aug; ++i) s.block(cfg, i * 128, J0 * 128, j * 128, J0 * 128, 8 * (Je - J0), i * 128, j * 128);
+    s.finish(cfg, EPI_STORE, M_L, M_L, M_L, M_NONE, -1.0, 1.0, false);
+    if (s.last >= 0) {
+      p.launches[s.last].stream = stream;
+      p.launches[s.last].wait_ev = wait_ev;
+      p.launches[s.last].rec_ev = rec_ev;
+    }
+    return s.last >= 0;
+  };
+
+  emit_panel(0);
+  for (int J = 0; J < nJ; ++J) {
+    const int next0 = std::min((J + 1) * OB, Nb), next1 = std::min((J + 2) * OB, Nb);
+    if (next0 >= Nb) break;
+    if (la) {
+      const bool has_t2 = next1 < Nb;
+      // T2(J) first so that the big launch is queued early on the main stream
+      if (has_t2) emit_update(J, next1, Nb, 0, evP(J), evM(J));
+      emit_update(J, next0, next1, 1, J > 0 ? evM(J - 1) : -1, -1);
+      emit_panel(J + 1);
+    } else {
+      emit_update(J, next0, Nb, 0, -1, -1);
+      emit_panel(J + 1);
     }
   }
 }
@@ -357,11 +411,27 @@ int upload_plan(H* h, Plan& p) {
 }
 
 int run_plan(H* h, Workspace& w, Plan& p, bool factor_diag) {
+  const bool multi = p.num_events > 0;
+  if (multi) {
+    while ((int)h->events.size() < p.num_events + 2) {
+      cudaEvent_t e;
+      CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      h->events.push_back(e);
+    }
+    // the panel stream starts after everything already queued on the main stream
+    CK(cudaEventRecord(h->events[p.num_events], h->stream));
+    CK(cudaStreamWaitEvent(h->stream2, h->events[p.num_events], 0));
+  }
   for (const Launch& L : p.launches) {
+    cudaStream_t st = (multi && L.stream == 1) ? h->stream2 : h->stream;
+    if (multi && L.wait_ev >= 0) CK(cudaStreamWaitEvent(st, h->events[L.wait_ev], 0));
     if (L.type == 0) {
-      potrf_diag_kernel<<<1, DIAG_THREADS, DIAG_SMEM, h->stream>>>(w.Lbuf, w.Np, L.k * 128,
-                                                                   w.Dinv + (long long)L.k * 128 * 128, w.logdet + L.k,
-                                                                   h->dinfo, (int)w.N, factor_diag);
+      if (factor_diag)
+        potrf_diag_kernel<true><<<1, DIAG_THREADS, DIAG_SMEM, st>>>(
+            w.Lbuf, w.Np, L.k * 128, w.Dinv + (long long)L.k * 128 * 128, w.logdet + L.k, h->dinfo, (int)w.N);
+      else
+        potrf_diag_kernel<false><<<1, DIAG_THREADS, DIAG_SMEM, st>>>(
+            w.Lbuf, w.Np, L.k * 128, w.Dinv + (long long)L.k * 128 * 128, w.logdet + L.k, h->dinfo, (int)w.N);
       h->launches++;
       CK(cudaGetLastError());
     } else {
@@ -372,9 +442,15 @@ int run_plan(H* h, Workspace& w, Plan& p, bool factor_diag) {
       ep.ldct = (L.matCt == M_NONE) ? 0 : w.mat[L.matCt].ld;
       ep.alpha = L.alpha;
       ep.beta = L.beta;
-      int rc = launch_gemm(h, w, L.cfg, L.epi, L.matA, L.matB, p.d_tasks + L.task_off, L.ntasks, ep);
+      int rc = launch_gemm(h, w, L.cfg, L.epi, L.matA, L.matB, p.d_tasks + L.task_off, L.ntasks, ep, st);
       if (rc) return rc;
     }
+    if (multi && L.rec_ev >= 0) CK(cudaEventRecord(h->events[L.rec_ev], st));
+  }
+  if (multi) {
+    // join: the main stream continues only after the panel stream has drained
+    CK(cudaEventRecord(h->events[p.num_events + 1], h->stream2));
+    CK(cudaStreamWaitEvent(h->stream, h->events[p.num_events + 1], 0));
   }
   return 0;
 }
@@ -713,8 +789,8 @@ int load_matrix_into_L(H* h, Workspace& w, const double* A, long long n) {
 }
 
 int invert_diag_blocks(H* h, Workspace& w) {
-  potrf_diag_kernel<<<(unsigned)w.Nb, DIAG_THREADS, DIAG_SMEM, h->stream>>>(w.Lbuf, w.Np, 0, w.Dinv, w.logdet, h->dinfo,
-                                                                           (int)w.N, false);
+  potrf_diag_kernel<false><<<(unsigned)w.Nb, DIAG_THREADS, DIAG_SMEM, h->stream>>>(w.Lbuf, w.Np, 0, w.Dinv, w.logdet,
+                                                                                   h->dinfo, (int)w.N);
   h->launches++;
   CK(cudaGetLastError());
   return 0;
@@ -742,6 +818,14 @@ int gpb_create(int device, gpb_handle_t* out) {
     delete h;
     return -2;
   }
+  {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (cudaStreamCreateWithPriority(&h->stream2, cudaStreamDefault, hi) != cudaSuccess) {
+      delete h;
+      return -2;
+    }
+  }
   cudaDriverEntryPointQueryResult qres;
   void* fn = nullptr;
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
@@ -749,7 +833,8 @@ int gpb_create(int device, gpb_handle_t* out) {
     return -2;
   }
   h->encode = reinterpret_cast<EncodeTiledFn>(fn);
-  if (cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM) != cudaSuccess) {
+  if (cudaFuncSetAttribute(potrf_diag_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM) != cudaSuccess ||
+      cudaFuncSetAttribute(potrf_diag_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM) != cudaSuccess) {
     delete h;
     return -2;
   }
@@ -767,6 +852,7 @@ int gpb_create(int device, gpb_handle_t* out) {
   cudaMalloc(&h->dinfo, sizeof(int));
   if (const char* e = getenv("GPB_CFG_UPDATE")) g_cfg_update = std::max(0, std::min(1, atoi(e)));
   if (const char* e = getenv("GPB_OUTER_BLOCKS")) g_outer_blocks = std::max(1, std::min(16, atoi(e)));
+  if (const char* e = getenv("GPB_LOOKAHEAD")) g_lookahead = atoi(e) != 0;
   *out = h;
   return 0;
 }
@@ -796,6 +882,8 @@ int gpb_destroy(gpb_handle_t h) {
     cudaEventDestroy(h->ev0[s]);
     cudaEventDestroy(h->ev1[s]);
   }
+  for (cudaEvent_t e : h->events) cudaEventDestroy(e);
+  cudaStreamDestroy(h->stream2);
   cudaStreamDestroy(h->stream);
   delete h;
   return 0;

@@ -1,7 +1,20 @@
-// Diagonal-block kernels of the blocked Cholesky: one CTA factorises a 128x128 FP64 block in shared
-// memory, inverts the triangular factor, and emits both.  This is the only serial stage of the
-// factorisation (reference: np.linalg.cholesky -> LAPACK dpotrf, gp_functions.py:143); everything
-// else is tile GEMMs on the DMMA pipe (dgemm_tasks.cuh).
+// Diagonal-block kernel of the blocked Cholesky: one CTA factorises a 128x128 FP64 block and inverts the
+// triangular factor in the same sweep.  This is the only serial stage of the factorisation (reference:
+// np.linalg.cholesky -> LAPACK dpotrf, gp_functions.py:143); everything else is tile GEMMs on the DMMA pipe
+// (dgemm_tasks.cuh), including the panel solve, which multiplies by the inverse produced here.
+//
+// Register-resident right-looking elimination.  256 threads; thread (ty = tid/32, tx = tid%32) owns the elements
+// (i = 8a + ty, k = 32b + tx), a = 0..15, b = 0..3, of the lower triangle of A and of R (R starts as I) --
+// 40 + 40 doubles in registers.  Column step j costs one barrier:
+//     owners of column j append c = A[j:, j] (unscaled: c_ij = L_ij sqrt(d_j), c_jj = d_j) to a packed
+//     column store in shared memory, the warp owning row j appends r = R[j, :j+1] to a packed row store,
+//     A[i, k] -= (c_i / d_j) c_k      for i >= k > j          (Cholesky trailing update)
+//     R[i, m] -= (c_i / d_j) r_m      for i > j >= m          (forward substitution of the identity)
+// and at the end  L[i, k] = c_ik / sqrt(d_k),  W[i, m] = r_im / sqrt(d_i)  with W = L^{-1}, read back from the
+// packed stores.  Because a column/row is saved the moment it becomes final, the updates run unmasked over
+// whole 8x32 register sub-blocks (finished entries just collect garbage), and the set of live sub-blocks only
+// depends on j/8 -- the step body is instantiated 16 times and selected by a warp-uniform switch, so it is
+// straight-line DFMA code without per-element predicates.
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
@@ -9,118 +22,141 @@
 namespace gpb {
 
 constexpr int NB = 128;            // block size of the tile algorithms
-constexpr int DIAG_LDS = NB + 1;   // padded leading dimension in shared memory (column walks conflict-free)
-constexpr int DIAG_THREADS = 1024;
-constexpr int DIAG_SMEM = (NB * DIAG_LDS + 2 * NB) * (int)sizeof(double);
+constexpr int DIAG_THREADS = 256;
+constexpr int DIAG_TRI = NB * (NB + 1) / 2;                       // 8256 packed entries
+constexpr int DIAG_SMEM = (2 * DIAG_TRI + 2 * NB) * (int)sizeof(double);
+
+__host__ __device__ constexpr bool diag_owned(int a, int b) { return 32 * b <= 8 * a + 7; }
+__device__ __forceinline__ int diag_colbase(int j) { return NB * j - (j * (j - 1)) / 2; }   // column j, rows j..127
+__device__ __forceinline__ int diag_rowbase(int j) { return (j * (j + 1)) / 2; }            // row j, cols 0..j
+
+template <int JA>
+__device__ __forceinline__ void diag_publish(const double (&av)[16][4], const double (&rv)[16][4], double* ccomp,
+                                             double* rcomp, int j, int ty, int tx) {
+  constexpr int JB = JA / 4;
+  const int jty = j & 7, jtx = j & 31;
+  if (tx == jtx) {
+    double* col = ccomp + diag_colbase(j) - j;
+#pragma unroll
+    for (int a = JA; a < 16; ++a)
+      if (8 * a + ty >= j) col[8 * a + ty] = av[a][JB];
+  }
+  if (ty == jty) {
+    double* row = rcomp + diag_rowbase(j);
+#pragma unroll
+    for (int b = 0; b <= JB; ++b)
+      if (32 * b + tx <= j) row[32 * b + tx] = rv[JA][b];
+  }
+}
+
+template <int JA, bool FACTOR>
+__device__ __forceinline__ void diag_update(double (&av)[16][4], double (&rv)[16][4], const double* ccomp,
+                                            const double* rcomp, int j, int ty, int tx, double invd) {
+  constexpr int JB = JA / 4;
+  const double* col = ccomp + diag_colbase(j) - j;   // col[i] = c_ij for i >= j (reads below j stay in bounds)
+  const double* row = rcomp + diag_rowbase(j);
+  double ck[4], rk[4];
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    ck[b] = (FACTOR && b >= JB) ? col[32 * b + tx] : 0.0;
+    rk[b] = (b < JB) ? row[32 * b + tx] : ((b == JB && 32 * b + tx <= j) ? row[32 * b + tx] : 0.0);
+  }
+#pragma unroll
+  for (int a = JA; a < 16; ++a) {
+    const double ci = col[8 * a + ty] * invd;
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+      if (diag_owned(a, b)) {
+        if (FACTOR && b >= JB) av[a][b] = fma(-ci, ck[b], av[a][b]);
+        if (b <= JB) rv[a][b] = fma(-ci, rk[b], rv[a][b]);
+      }
+  }
+}
 
 // In:  A (row-major, lda) holds the lower triangle of an SPD block at rows/cols [k0, k0+128).
-// Out: A block   <- L (lower, strict upper zeroed),
+// Out: A block   <- L (lower, strict upper zeroed)            [FACTOR]
 //      Winv      <- L^{-1} (128x128 row-major, strict upper zeroed),
-//      logdet[0] <- sum_j log L_jj  (fixed summation order),
+//      logdet[0] <- sum_j log L_jj over rows < n_valid (fixed summation order),
 //      info      <- first non-positive pivot (global 1-based index), LAPACK style; untouched otherwise.
-// With factor == false the block already holds L and only Winv (and logdet) are produced.
+// With FACTOR == false the block already holds L and only Winv (and logdet) are produced.
+// blockIdx.x selects consecutive diagonal blocks (grid > 1 only when they are independent: FACTOR == false).
+template <bool FACTOR>
 __global__ void __launch_bounds__(DIAG_THREADS, 1)
 potrf_diag_kernel(double* __restrict__ A, long long lda, int k0_first, double* __restrict__ Winv_first,
-                  double* __restrict__ logdet_first, int* __restrict__ info, int n_valid, bool factor) {
-  // blockIdx.x selects consecutive diagonal blocks (grid > 1 only when the blocks are independent, i.e. factor == false)
+                  double* __restrict__ logdet_first, int* __restrict__ info, int n_valid) {
   const int k0 = k0_first + blockIdx.x * NB;
   double* Winv = Winv_first + (long long)blockIdx.x * NB * NB;
   double* logdet = logdet_first ? logdet_first + blockIdx.x : nullptr;
-  extern __shared__ double sm[];
-  double* S = sm;                       // [128][129]
-  double* dvec = sm + NB * DIAG_LDS;    // pivots d_j
-  double* rdiag = dvec + NB;            // 1 / L_jj
-  const int tid = threadIdx.x;
+  extern __shared__ double diag_sm[];
+  double* ccomp = diag_sm;               // packed final columns of A (unscaled)
+  double* rcomp = diag_sm + DIAG_TRI;    // packed final rows of R (unscaled)
+  double* dvec = rcomp + DIAG_TRI;       // pivots d_j
+  double* rsv = dvec + NB;               // 1/sqrt(d_j)  (FACTOR)  or  1/L_jj
+  const int tid = threadIdx.x, ty = tid >> 5, tx = tid & 31;
   double* Ablk = A + (long long)k0 * lda + k0;
 
-  for (int e = tid; e < NB * NB; e += DIAG_THREADS) {
-    const int i = e >> 7, j = e & 127;
-    S[i * DIAG_LDS + j] = (j <= i) ? Ablk[(long long)i * lda + j] : 0.0;
-  }
-
-  if (factor) {
-    // Right-looking, square-root free in the loop: column j stays unscaled (c_ij = L_ij * sqrt(d_j)) and the
-    // rank-1 update uses c_i c_k / d_j, so one barrier per column suffices.
-    const int ty = tid >> 5, tx = tid & 31;
-    for (int j = 0; j < NB; ++j) {
-      __syncthreads();
-      const double d = S[j * DIAG_LDS + j];
-      if (tid == 0) {
-        dvec[j] = d;
-        if (!(d > 0.0) && (k0 + j) < n_valid) atomicCAS(info, 0, k0 + j + 1);
-      }
-      const double invd = 1.0 / d;
-      for (int i = j + 1 + ty; i < NB; i += 32) {
-        const double ci = S[i * DIAG_LDS + j] * invd;
-        for (int k = j + 1 + tx; k <= i; k += 32)
-          S[i * DIAG_LDS + k] = fma(-ci, S[k * DIAG_LDS + j], S[i * DIAG_LDS + k]);
+  double av[16][4], rv[16][4];
+#pragma unroll
+  for (int a = 0; a < 16; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      av[a][b] = rv[a][b] = 0.0;
+      if (diag_owned(a, b)) {
+        const int i = 8 * a + ty, k = 32 * b + tx;
+        if (k <= i) av[a][b] = Ablk[(long long)i * lda + k];
+        if (k == i) rv[a][b] = 1.0;
       }
     }
-    __syncthreads();
-    // scale columns: L_ij = c_ij / sqrt(d_j), L_jj = sqrt(d_j)
-    for (int e = tid; e < NB * NB; e += DIAG_THREADS) {
-      const int i = e >> 7, j = e & 127;
-      if (j < i) S[i * DIAG_LDS + j] = S[i * DIAG_LDS + j] / sqrt(dvec[j]);
+
+  for (int j = 0; j < NB; ++j) {
+    const int ja = j >> 3;
+    switch (ja) {
+#define GPB_DIAG_PUB(JA) case JA: diag_publish<JA>(av, rv, ccomp, rcomp, j, ty, tx); break;
+      GPB_DIAG_PUB(0) GPB_DIAG_PUB(1) GPB_DIAG_PUB(2) GPB_DIAG_PUB(3) GPB_DIAG_PUB(4) GPB_DIAG_PUB(5)
+      GPB_DIAG_PUB(6) GPB_DIAG_PUB(7) GPB_DIAG_PUB(8) GPB_DIAG_PUB(9) GPB_DIAG_PUB(10) GPB_DIAG_PUB(11)
+      GPB_DIAG_PUB(12) GPB_DIAG_PUB(13) GPB_DIAG_PUB(14) GPB_DIAG_PUB(15)
+#undef GPB_DIAG_PUB
     }
     __syncthreads();
-    if (tid < NB) S[tid * DIAG_LDS + tid] = sqrt(dvec[tid]);
+    const double d = ccomp[diag_colbase(j)];
+    if (tid == 0) {
+      dvec[j] = d;
+      if (!(d > 0.0) && (k0 + j) < n_valid) atomicCAS(info, 0, k0 + j + 1);
+    }
+    const double invd = 1.0 / d;
+    switch (ja) {
+#define GPB_DIAG_UPD(JA) case JA: diag_update<JA, FACTOR>(av, rv, ccomp, rcomp, j, ty, tx, invd); break;
+      GPB_DIAG_UPD(0) GPB_DIAG_UPD(1) GPB_DIAG_UPD(2) GPB_DIAG_UPD(3) GPB_DIAG_UPD(4) GPB_DIAG_UPD(5)
+      GPB_DIAG_UPD(6) GPB_DIAG_UPD(7) GPB_DIAG_UPD(8) GPB_DIAG_UPD(9) GPB_DIAG_UPD(10) GPB_DIAG_UPD(11)
+      GPB_DIAG_UPD(12) GPB_DIAG_UPD(13) GPB_DIAG_UPD(14) GPB_DIAG_UPD(15)
+#undef GPB_DIAG_UPD
+    }
   }
   __syncthreads();
-  if (tid < NB) rdiag[tid] = 1.0 / S[tid * DIAG_LDS + tid];
-  __syncthreads();
-
-  if (logdet != nullptr && tid < 32) {
+  if (tid < NB) rsv[tid] = FACTOR ? 1.0 / sqrt(dvec[tid]) : 1.0 / dvec[tid];
+  if (logdet != nullptr && tid >= 128 && tid < 160) {
+    const int lane = tid - 128;
     double s = 0.0;
     for (int q = 0; q < 4; ++q) {
-      const int j = tid + 32 * q;
-      s += (k0 + j < n_valid) ? log(S[j * DIAG_LDS + j]) : 0.0;
+      const int j = lane + 32 * q;
+      if (k0 + j < n_valid) s += FACTOR ? 0.5 * log(dvec[j]) : log(dvec[j]);
     }
     for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-    if (tid == 0) logdet[0] = s;
-  }
-
-  // W = L^{-1}, one warp per column j (4 columns per warp), forward substitution with the residual held in
-  // registers (lane owns rows lane+32q).  Column j of W is parked in row j of the (free) strict upper
-  // triangle of S; its diagonal entry is rdiag[j].
-  {
-    const int warp = tid >> 5, lane = tid & 31;
-    for (int j = warp; j < NB; j += 32) {
-      double r[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) r[q] = (lane + 32 * q == j) ? 1.0 : 0.0;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        for (int ii = 0; ii < 32; ++ii) {
-          const int i = 32 * q + ii;
-          if (i < j) continue;  // warp-uniform
-          const double wi = __shfl_sync(0xffffffffu, r[q], ii) * rdiag[i];
-          if (lane == ii) r[q] = wi;
-#pragma unroll
-          for (int q2 = q; q2 < 4; ++q2) {
-            const int k = 32 * q2 + lane;
-            if (k > i) r[q2] = fma(-S[k * DIAG_LDS + i], wi, r[q2]);
-          }
-        }
-      }
-      // r[q] now holds W[32q+lane][j] for rows >= j.  Nobody reads S[j][k>j] as L, so park it there.
-      __syncwarp();
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int k = 32 * q + lane;
-        if (k > j) S[j * DIAG_LDS + k] = r[q];
-      }
-    }
+    if (lane == 0) logdet[0] = s;
   }
   __syncthreads();
 
-  for (int e = tid; e < NB * NB; e += DIAG_THREADS) {
-    const int i = e >> 7, j = e & 127;
-    if (factor) Ablk[(long long)i * lda + j] = (j <= i) ? S[i * DIAG_LDS + j] : 0.0;
-    double w = 0.0;
-    if (j == i) w = rdiag[i];
-    else if (j < i) w = S[j * DIAG_LDS + i];   // W[i][j] parked at S[j][i]
-    Winv[i * NB + j] = w;
-  }
+  for (int a = 0; a < 16; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int i = 8 * a + ty, k = 32 * b + tx;
+      double l = 0.0, w = 0.0;
+      if (k < i) l = ccomp[diag_colbase(k) + i - k] * rsv[k];
+      else if (k == i) l = sqrt(dvec[i]);
+      if (k <= i) w = rcomp[diag_rowbase(i) + k] * rsv[i];
+      if (FACTOR) Ablk[(long long)i * lda + k] = l;
+      Winv[i * NB + k] = w;
+    }
 }
 
 }  // namespace gpb
