@@ -29,6 +29,7 @@ N_TRAIN, DIM = 16384, 10                 # BASELINE configs[2]
 N_TRAIN_PRED, M_FULL = 8192, 1 << 22     # BASELINE configs[3]
 METRIC = "NLL+grad evals/s (N=16384, D=10, fp64)"
 UNIT = "evals/s"
+NCU_DRAM_BYTES_SYRK_LAUNCH = 37.34e9     # profiles/r01_ncu_dgemm_syrk.txt (dram__bytes_read.sum + dram__bytes_write.sum)
 DMMA_CEILING_TFLOPS = 37.05              # profiles/r01_probe_fp64_dmma.txt: register-resident DMMA.8x8x4 issue rate
 
 
@@ -129,20 +130,24 @@ def cpu_nll_grad_sample(n_sample, steps=1):
     (row-blocked, O(N^2 P) gradient contraction) on a bounded sample.  The sample is scaled to N=16384 phase by
     phase: Cholesky / solves / inverse with (N/n)^3, assembly and contraction with (N/n)^2."""
     import oracle
+    from threadpoolctl import threadpool_info, threadpool_limits
 
     X, y = oracle.synthetic_problem(n_sample, DIM)
     th = theta_ref(DIM)
     best, best_t = float("inf"), None
-    for _ in range(steps):
-        tm = {}
-        t0 = time.perf_counter()
-        oracle.nll_cholesky(th, X, y, oracle.matern52, eval_gradient=True, timings=tm)
-        dt = time.perf_counter() - t0
-        if dt < best:
-            best, best_t = dt, tm
+    ncpu = len(os.sched_getaffinity(0))
+    # torchrun exports OMP_NUM_THREADS=1; give BLAS every host core this process may use
+    with threadpool_limits(limits=ncpu):
+        cores = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+        for _ in range(steps):
+            tm = {}
+            t0 = time.perf_counter()
+            oracle.nll_cholesky(th, X, y, oracle.matern52, eval_gradient=True, timings=tm)
+            dt = time.perf_counter() - t0
+            if dt < best:
+                best, best_t = dt, tm
     r = N_TRAIN / n_sample
     full = best_t["cubic"] * r**3 + best_t["quadratic"] * r**2
-    cores = len(os.sched_getaffinity(0))
     return {"value": 1.0 / full, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"one NLL+grad eval of the oracle port at N={n_sample}, D={DIM} Matern-5/2: {best:.2f} s "
                       f"({best_t['cubic']:.2f} s O(N^3) phases scaled by {r**3:.0f}, {best_t['quadratic']:.2f} s "
@@ -161,7 +166,7 @@ def run_reference(args):
         cpu_nll_grad_sample(args.cpu_sample_n)
     samples = [cpu_nll_grad_sample(args.cpu_sample_n) for _ in range(args.steps)]
     sec = statistics.mean(s["scaled_seconds"] for s in samples)
-    cores = len(os.sched_getaffinity(0))
+    cores = samples[0]["cores"]
     sample = (f"{args.steps} x " + samples[0]["sample"])
     line = {"impl": "reference", "metric": METRIC, "value": 1.0 / sec, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
@@ -182,6 +187,16 @@ def workload_config():
 
 
 # ------------------------------------------------------------------------------------------------ GPU legs
+def measured_hbm_peak():
+    """HBM roofline denominator: the driver-measured copy bandwidth, else the profiling guide's fallback."""
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "of measured (MEASURED_PEAKS.json hbm_gbs, STREAM-style copy)"
+    except (OSError, KeyError, ValueError):
+        return 6650.0, "of fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
 def fp64_gemm_peak(local):
     """cuBLAS DGEMM 8192^3, best of 5 after warm-up -- the measured FP64 tensor roofline denominator
     (MEASURED_PEAKS.json carries HBM and bf16 only)."""
@@ -316,6 +331,28 @@ def run_gpu(args):
                 "variance_gemm_tflops": tf}
         bp.close()
 
+    # ---------------- dense K + dK/dtheta assembly (python_kernels.RBF twin), HBM-bound ----------------
+    asm = None
+    if rank == 0 and not args.skip_assembly:
+        P = th0.size
+        Kt = torch.empty(N_TRAIN, N_TRAIN, dtype=torch.float64, device="cuda")
+        dKt = torch.empty(N_TRAIN, N_TRAIN, P, dtype=torch.float64, device="cuda")
+        dX = torch.from_numpy(X).cuda()
+        ms = []
+        for rep in range(args.warmup + 3):
+            be.kernel_matrix(KIND_MATERN52, dX, dX, th0[:-2], th0[-2], th0[-1], eval_gradient=True, out_K=Kt, out_dK=dKt)
+            ms.append(be.stage_ms()["assemble"])
+        ms = statistics.mean(ms[args.warmup:])
+        nbytes = float(N_TRAIN) ** 2 * (1 + P) * 8
+        hbm_peak, hbm_src = measured_hbm_peak()
+        asm = {"workload": f"K and dK/dtheta (N,N,{P}) of the Matern-5/2 ARD kernel, N={N_TRAIN}, D={DIM}, device resident",
+               "ms": ms, "algorithmic_bytes": nbytes,
+               "roofline": {"bound": "hbm", "achieved": nbytes / (ms * 1e-3) * 1e-9, "peak": hbm_peak, "unit": "GB/s",
+                            "frac": nbytes / (ms * 1e-3) * 1e-9 / hbm_peak, "traffic": None, "peak_source": hbm_src,
+                            "kernel": "gpb::kernel_matrix_kernel (bulk-TMA stores of the derivative tiles)"}}
+        del Kt, dKt, dX
+        torch.cuda.empty_cache()
+
     if rank != 0:
         be.close()
         if dist is not None:
@@ -325,7 +362,9 @@ def run_gpu(args):
     peak = fp64_gemm_peak(local)
     achieved = float(N_TRAIN) ** 3 / (dense_ms * 1e-3) * 1e-12
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None,
+                "traffic": NCU_DRAM_BYTES_SYRK_LAUNCH,
+                "traffic_note": "dram__bytes_read+write of the K^-1 = U U^T launch (1.466e12 flop) from "
+                                "profiles/r01_ncu_dgemm_syrk.txt; compute-bound, tile re-reads served by L2/HBM",
                 "kernel": "gpb::dgemm_tasks_kernel (DMMA.8x8x4 tile GEMM behind potrf / trtri / syrk)",
                 "algorithmic_flops_per_eval": float(N_TRAIN) ** 3,
                 "dense_ms_per_eval": dense_ms,
@@ -344,7 +383,7 @@ def run_gpu(args):
             "config": workload_config(), "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks.summary(), "roofline": roofline, "cpu_baseline": cpu,
             "best_restart": {"index": int(best_row[0]), "nll": float(best_row[1])},
-            "al_predict": pred}
+            "al_predict": pred, "assembly": asm}
     print(json.dumps(line), flush=True)
     be.close()
     if dist is not None:
@@ -360,6 +399,7 @@ def main():
     ap.add_argument("--cpu-sample-n", type=int, default=4096, help="size of the bounded CPU sample evaluation")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-predict", action="store_true")
+    ap.add_argument("--skip-assembly", action="store_true")
     ap.add_argument("--predict-candidates", type=int, default=1 << 17, help="candidates per GPU in the predict leg")
     ap.add_argument("--predict-full", action="store_true", help="run all 2^22 candidates of configs[3]")
     args = ap.parse_args()

@@ -96,13 +96,15 @@ class GPBackend:
         return int(idx.value), float(val.value)
 
     # -- dense twins ----------------------------------------------------------------------------------
-    def kernel_matrix(self, kind, Xa, Xb, ell, sigma_f, sigma_n, eval_gradient=False):
+    def kernel_matrix(self, kind, Xa, Xb, ell, sigma_f, sigma_n, eval_gradient=False, out_K=None, out_dK=None):
+        """K (na, nb) [and dK (na, nb, P)].  ``out_K`` / ``out_dK`` may be preallocated numpy arrays or torch CUDA
+        tensors; device outputs are written in place by the kernel (no staging copy)."""
         Xa = _lib.as_f64(Xa)
         Xb = _lib.as_f64(Xb)
         ell = np.ascontiguousarray(ell, dtype=np.float64).ravel()
         na, nb, d = int(Xa.shape[0]), int(Xb.shape[0]), int(Xa.shape[1])
-        K = np.empty((na, nb))
-        dK = np.empty((na, nb, ell.size + 2)) if eval_gradient else None
+        K = np.empty((na, nb)) if out_K is None else out_K
+        dK = (np.empty((na, nb, ell.size + 2)) if out_dK is None else out_dK) if eval_gradient else None
         st = self._lib.gpb_kernel_matrix(self._h, int(kind), _lib.ptr(Xa), na, _lib.ptr(Xb), nb, d, _lib.ptr(ell),
                                          ell.size, float(sigma_f), float(sigma_n), _lib.ptr(K), _lib.ptr(dK))
         _lib.check(st, self._h, "kernel_matrix")

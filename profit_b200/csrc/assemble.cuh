@@ -109,53 +109,120 @@ __global__ void fill_aug_kernel(const double* __restrict__ y, int n, int m, int 
 }
 
 // Rectangular K(Xa, Xb) (+ sn^2 on the main diagonal, as np.eye(n, m) does) and optionally the
-// (na, nb, P) derivative tensor, P ordered [l..., sf, sn] like python_kernels.py:42-56.
-// Thread owns one (row, column-pair); dK is staged through shared memory so global stores are coalesced.
-template <int KIND>
-__global__ void __launch_bounds__(256)
-kernel_matrix_kernel(const double* __restrict__ Xa, int na, const double* __restrict__ Xb, int nb, KernelHyp h,
-                     double* __restrict__ K, double* __restrict__ dK) {
-  extern __shared__ double stage[];  // [rows_per_cta=4][64 cols][P] when dK requested
+// (na, nb, P) derivative tensor, P ordered [l..., sf, sn] like python_kernels.py:42-56.  HBM-bound when the
+// derivative planes are requested: 8 (1 + P) bytes written per element against ~100 FP64 operations.
+//
+// CTA tile: KM_ROWS rows x 64 columns, 256 threads = 64 columns x 4 row lanes.  A thread keeps its column's
+// scaled coordinates in registers; the row coordinates are broadcast from shared memory.  Per pass (4 rows) the
+// P derivative values of every element are written to a shared-memory stage laid out exactly like the global
+// tensor -- a row of the tile is one contiguous span of 64 P doubles -- and shipped with one bulk TMA store per
+// row (cp.async.bulk.global.shared::cta, SASS UBLKCP); two stages alternate so the stores of pass p overlap the
+// arithmetic of pass p+1.  Ragged or 16-byte-misaligned rows fall back to a cooperative coalesced copy.
+constexpr int KM_ROWS = 32, KM_COLS = 64, KM_THREADS = 256;
+
+__device__ __forceinline__ void bulk_store(double* gdst, const double* ssrc, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+               "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+               : "memory");
+}
+
+template <int KIND, int DP>
+__global__ void __launch_bounds__(KM_THREADS, (DP <= 12) ? 3 : 2)
+kernel_matrix_kernel(const double* __restrict__ XsA, int na, const double* __restrict__ XsTB, long long ldt, int nb,
+                     KernelHyp h, double* __restrict__ K, double* __restrict__ dK, int nbuf) {
+  extern __shared__ __align__(16) double km_sm[];
   const int P = h.n_ell + 2;
+  double* xi = km_sm;                                  // [KM_ROWS][DP]
+  double* rl = xi + KM_ROWS * DP;                      // [DP]  1 / l_d  (0 for padding dimensions)
+  double* stage = rl + DP + (DP & 1);                  // [nbuf][4][64 * P], 16-byte aligned
   const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
-  const int j = blockIdx.x * 64 + tx;
-  const int i = blockIdx.y * 4 + ty;
+  const int row0 = blockIdx.y * KM_ROWS, col0 = blockIdx.x * KM_COLS;
+  const int j = col0 + tx;
   const double sf2 = h.sf * h.sf, sn2 = h.sn * h.sn;
-  const bool valid = (i < na && j < nb);
-  double d2 = 0.0, kp = 0.0, gf = 0.0;
-  double u2[MAX_D];
-  if (valid) {
-#pragma unroll 4
-    for (int d = 0; d < h.D; ++d) {
-      const double l = ell_of(h, d);
-      const double u = Xa[(long long)i * h.D + d] / l - Xb[(long long)j * h.D + d] / l;
-      u2[d] = u * u;
-      d2 += u * u;
-    }
-    kern_eval<KIND>(d2, sf2, kp, gf);
-    K[(long long)i * nb + j] = kp + ((i == j) ? sn2 : 0.0);
+  for (int e = threadIdx.x; e < KM_ROWS * DP; e += KM_THREADS) {
+    const int r = row0 + e / DP;
+    xi[e] = (r < na) ? XsA[(long long)r * DP + e % DP] : 0.0;
   }
-  if (dK == nullptr) return;
-  double* my = stage + ((long long)ty * 64 + tx) * P;
-  if (valid) {
-    if (h.n_ell == 1) {
-      my[0] = d2 / h.ell[0] * gf;
-    } else {
-      for (int d = 0; d < h.D; ++d) my[d] = u2[d] / h.ell[d] * gf;
-    }
-    my[P - 2] = 2.0 / h.sf * kp;
-    my[P - 1] = (i == j) ? 2.0 * h.sn : 0.0;
-  }
+  if (threadIdx.x < DP) rl[threadIdx.x] = (threadIdx.x < h.D) ? 1.0 / ell_of(h, threadIdx.x) : 0.0;
+  double xj[DP];
+#pragma unroll
+  for (int d = 0; d < DP; ++d) xj[d] = (j < nb) ? XsTB[(long long)d * ldt + j] : 0.0;
+  const int ncols = min(KM_COLS, nb - col0);
+  // bulk stores need 16-byte aligned global addresses: every row start is (i*nb + col0)*P*8 bytes into dK
+  const bool bulk = (dK != nullptr) && ncols == KM_COLS && ((((long long)nb * P) & 1) == 0) &&
+                    ((reinterpret_cast<unsigned long long>(dK) & 15ull) == 0);
+  const bool ard_even = (h.n_ell > 1) && ((P & 1) == 0);   // 16-byte staged stores are aligned
+  const double two_over_sf = 2.0 / h.sf;
   __syncthreads();
-  // coalesced copy-out: row (blockIdx.y*4+ty) has a contiguous span of ncols*P doubles
-  const int ncols = min(64, nb - blockIdx.x * 64);
-  for (int r = 0; r < 4; ++r) {
-    const int ii = blockIdx.y * 4 + r;
-    if (ii >= na) break;
-    double* dst = dK + ((long long)ii * nb + (long long)blockIdx.x * 64) * P;
-    const double* src = stage + (long long)r * 64 * P;
-    for (int e = threadIdx.x; e < ncols * P; e += 256) dst[e] = src[e];
+
+  for (int pass = 0; pass < KM_ROWS / 4; ++pass) {
+    const int rr = pass * 4 + ty, i = row0 + rr;
+    const bool valid = (i < na && j < nb);
+    double u2[DP];
+    double d2 = 0.0;
+#pragma unroll
+    for (int d = 0; d < DP; ++d) {
+      const double u = xi[rr * DP + d] - xj[d];
+      u2[d] = u * u;
+      d2 += u2[d];
+    }
+    double kp, gf;
+    kern_eval<KIND>(d2, sf2, kp, gf);
+    if (valid) K[(long long)i * nb + j] = kp + ((i == j) ? sn2 : 0.0);
+    if (dK == nullptr) continue;
+
+    double* st = stage + (size_t)(pass % nbuf) * 4 * KM_COLS * P;
+    if (nbuf == 2 && pass >= 2) {  // two stages: wait for the stores issued two passes ago before overwriting
+      if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      __syncthreads();
+    }
+    double* my = st + ((size_t)ty * KM_COLS + tx) * P;
+    const double dsf = two_over_sf * kp, dsn = (i == j) ? 2.0 * h.sn : 0.0;
+    if (h.n_ell == 1) {
+      my[0] = d2 * rl[0] * gf;
+      my[1] = dsf;
+      my[2] = dsn;
+    } else if (ard_even) {
+      // D is even here: pairs (d, d+1) are 16-byte aligned in the stage
+#pragma unroll
+      for (int d = 0; d < DP; d += 2)
+        if (d < h.D) *reinterpret_cast<double2*>(my + d) = make_double2(u2[d] * rl[d] * gf, u2[d + 1] * rl[d + 1] * gf);
+      *reinterpret_cast<double2*>(my + P - 2) = make_double2(dsf, dsn);
+    } else {
+#pragma unroll
+      for (int d = 0; d < DP; ++d)
+        if (d < h.D) my[d] = u2[d] * rl[d] * gf;
+      my[P - 2] = dsf;
+      my[P - 1] = dsn;
+    }
+    if (bulk) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        for (int r = 0; r < 4; ++r) {
+          const int ii = row0 + pass * 4 + r;
+          if (ii < na)
+            bulk_store(dK + ((long long)ii * nb + col0) * P, st + (size_t)r * KM_COLS * P,
+                       (unsigned)(KM_COLS * P * sizeof(double)));
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        // three stages: the stage written in the NEXT pass was shipped two passes ago; waiting here, before this
+        // thread reaches the next barrier, makes one barrier per pass sufficient
+        if (nbuf == 3) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      }
+    } else {
+      __syncthreads();
+      for (int r = 0; r < 4; ++r) {
+        const int ii = row0 + pass * 4 + r;
+        if (ii >= na) break;
+        double* dst = dK + ((long long)ii * nb + col0) * P;
+        const double* src = st + (size_t)r * KM_COLS * P;
+        for (int e = threadIdx.x; e < ncols * P; e += KM_THREADS) dst[e] = src[e];
+      }
+      __syncthreads();
+    }
   }
+  if (bulk && threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // Gradient contraction over the lower triangle (off-diagonal entries weighted twice):

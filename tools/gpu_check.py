@@ -94,6 +94,24 @@ if stage == "big":
         except Exception as e:
             print("  nll FAILED", e, flush=True)
 
+if stage in ("all", "assembly"):
+    for (N, D, kind) in ((8192, 10, KIND_MATERN52), (16384, 10, KIND_MATERN52), (16384, 10, KIND_RBF), (8192, 16, KIND_RBF)):
+        X = np.random.default_rng(0).random((N, D))
+        ell = np.linspace(0.6, 1.2, D); P = D + 2
+        dKt = torch.empty(N, N, P, dtype=torch.float64, device=dev); Kt = torch.empty(N, N, dtype=torch.float64, device=dev)
+        for rep in range(3):
+            be.kernel_matrix(kind, X, X, ell, 1.5, 0.3, eval_gradient=True, out_K=Kt, out_dK=dKt)
+            ms = be.stage_ms()["assemble"]
+        gb = N * N * (1 + P) * 8 / 1e9
+        be.kernel_matrix(kind, X, X, ell, 1.5, 0.3, eval_gradient=False, out_K=Kt)
+        ms0 = be.stage_ms()["assemble"]
+        print(f"assembly N={N} D={D} kind={kind}: K+dK {ms:.3f} ms = {gb/ms*1e3:.0f} GB/s ({gb:.1f} GB);  K only {ms0:.3f} ms = {N*N*8/1e9/ms0*1e3:.0f} GB/s", flush=True)
+        # spot check against the oracle on a corner
+        kern = oracle.rbf if kind == KIND_RBF else oracle.matern52
+        rK, rdK = kern(X[:70], X[N-90:], ell, 1.5, 0.3, eval_gradient=True)
+        print("   err", (Kt[:70, N-90:].cpu().numpy() - rK).__abs__().max(), np.abs(dKt[:70, N-90:].cpu().numpy() - rdK).max(), flush=True)
+        del dKt, Kt
+
 if stage == "time4096":
     X, y = oracle.synthetic_problem(4096, 8)
     theta = np.concatenate([np.linspace(0.6, 1.2, 8), [1.5, 0.3]])
