@@ -353,3 +353,47 @@ def test_predict_8192_sharding_invariance(backend):
         best.append((lv, -(lo + li)))
     assert -max(best)[1] == int(np.argmax(v))
     assert np.all(v > 0.09) and np.all(v < 1.5**2 + 0.09 + 1e-9)
+
+
+# ------------------------------------------------------------------------------------------ sharded paths (1 rank)
+def test_acquisition_argmax_and_multistart_single_rank(backend):
+    """The sharded entry points with world size 1 (the gathers are exercised with gloo in test_host_logic.py)."""
+    from profit_b200 import RBF, gp_functions as gpf
+    from profit_b200.distributed import acquisition_argmax, multistart_optimize
+
+    X, y = oracle.synthetic_problem(300, 3)
+    theta = np.array([0.7, 0.9, 1.1, 1.5, 0.3])
+    backend.set_train(X, y)
+    backend.factorize(0, theta)
+    Xc = np.random.default_rng(4).random((5000, 3))
+    idx, val = acquisition_argmax(backend, Xc)
+    _, rv = oracle.predict(X, y, Xc, oracle.rbf, theta[:3], theta[3], theta[4])
+    assert idx == int(np.argmax(rv)) and abs(val - rv.max()) <= PRED_RTOL * rv.max()
+    mask = np.ones(5000)
+    mask[idx] = 0.0                       # aquisition_functions.py:68 masks already-picked candidates
+    idx2, _ = acquisition_argmax(backend, Xc, mask=mask)
+    assert idx2 != idx and idx2 == int(np.argmax(rv.ravel() * mask))
+    # multi-start: the best of several BFGS runs is at least as good as the single reference start
+    starts = theta * 10 ** (np.array([[0.0], [0.3], [-0.3]]) * np.ones((3, theta.size)))
+    best, best_nll, table = multistart_optimize(X, y, starts, RBF, eval_gradient=True, backend=backend)
+    assert table.shape == (3, 2 + theta.size) and np.isfinite(best_nll)
+    single = gpf.optimize(X, y, theta, RBF, eval_gradient=True, backend=backend)
+    assert best_nll <= oracle.nll_cholesky(single, X, y, oracle.rbf) + 1e-6
+    assert abs(best_nll - oracle.nll_cholesky(best, X, y, oracle.rbf)) <= 1e-8 * abs(best_nll)
+
+
+def test_train_latency_small_problem(backend, golden):
+    """BASELINE configs[0] end to end: the reference needs 0.27 s for this fit on 8 CPU cores."""
+    import time
+
+    from profit_b200 import B200GPSurrogate
+
+    c = golden["c0_train"]
+    s = B200GPSurrogate()
+    s.train(np.array(c["X"]), np.array(c["y"]))       # warm-up
+    t0 = time.perf_counter()
+    s = B200GPSurrogate()
+    s.train(np.array(c["X"]), np.array(c["y"]))
+    dt = time.perf_counter() - t0
+    print(f"train N=200: {dt*1e3:.1f} ms")
+    assert dt < 1.0
