@@ -29,6 +29,9 @@ class GPBackend:
         self.n = 0
         self.d = 0
         self.n_out = 0
+        # bookkeeping for callers that share one backend (set by B200GPSurrogate): what is resident / factorised
+        self.resident_key = None
+        self.factor_key = None
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
@@ -56,6 +59,7 @@ class GPBackend:
             raise ValueError(f"y should have shape (n,) or (n, D) but has shape {tuple(y.shape)}")
         if int(y.shape[0]) != n:
             raise ValueError(f"mismatched number of data points for X and y: {n} != {int(y.shape[0])}")
+        self.resident_key = self.factor_key = None
         _lib.check(self._lib.gpb_set_train(self._h, _lib.ptr(X), _lib.ptr(y), n, d, n_out), self._h, "set_train")
         self.n, self.d, self.n_out = n, d, n_out
 
@@ -64,6 +68,7 @@ class GPBackend:
         """theta = [length_scale..., sigma_f, sigma_n] on the linear scale -> nll [, grad (P,)]."""
         theta = np.ascontiguousarray(theta, dtype=np.float64).ravel()
         n_ell = theta.size - 2
+        self.factor_key = None
         out = ctypes.c_double()
         grad = np.empty(theta.size) if want_grad else None
         st = self._lib.gpb_nll(self._h, int(kind), _lib.ptr(theta), n_ell, int(bool(want_grad)), ctypes.byref(out),
@@ -73,6 +78,7 @@ class GPBackend:
 
     def factorize(self, kind, theta):
         theta = np.ascontiguousarray(theta, dtype=np.float64).ravel()
+        self.factor_key = None
         _lib.check(self._lib.gpb_factorize(self._h, int(kind), _lib.ptr(theta), theta.size - 2), self._h, "factorize")
 
     def predict(self, Xc, add_data_variance=True, out_mean=None, out_var=None, want_mean=True, want_var=True):

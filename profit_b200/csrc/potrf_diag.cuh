@@ -13,8 +13,8 @@
 // and at the end  L[i, k] = c_ik / sqrt(d_k),  W[i, m] = r_im / sqrt(d_i)  with W = L^{-1}, read back from the
 // packed stores.  Because a column/row is saved the moment it becomes final, the updates run unmasked over
 // whole 8x32 register sub-blocks (finished entries just collect garbage), and the set of live sub-blocks only
-// depends on j/8 -- the step body is instantiated 16 times and selected by a warp-uniform switch, so it is
-// straight-line DFMA code without per-element predicates.
+// depends on j/8 -- the step body is instantiated 16 times (eight columns each), so it is straight-line DFMA
+// code without per-element predicates or dispatch.
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
@@ -30,46 +30,60 @@ __host__ __device__ constexpr bool diag_owned(int a, int b) { return 32 * b <= 8
 __device__ __forceinline__ int diag_colbase(int j) { return NB * j - (j * (j - 1)) / 2; }   // column j, rows j..127
 __device__ __forceinline__ int diag_rowbase(int j) { return (j * (j + 1)) / 2; }            // row j, cols 0..j
 
-template <int JA>
-__device__ __forceinline__ void diag_publish(const double (&av)[16][4], const double (&rv)[16][4], double* ccomp,
-                                             double* rcomp, int j, int ty, int tx) {
-  constexpr int JB = JA / 4;
-  const int jty = j & 7, jtx = j & 31;
-  if (tx == jtx) {
-    double* col = ccomp + diag_colbase(j) - j;
-#pragma unroll
-    for (int a = JA; a < 16; ++a)
-      if (8 * a + ty >= j) col[8 * a + ty] = av[a][JB];
-  }
-  if (ty == jty) {
-    double* row = rcomp + diag_rowbase(j);
-#pragma unroll
-    for (int b = 0; b <= JB; ++b)
-      if (32 * b + tx <= j) row[32 * b + tx] = rv[JA][b];
-  }
-}
-
+// Eight consecutive column steps j = 8*JA .. 8*JA+7.  Everything that depends on j/8 (which register sub-blocks are
+// live, which are masked) is a compile-time property of the instantiation, so the step body is straight-line code.
 template <int JA, bool FACTOR>
-__device__ __forceinline__ void diag_update(double (&av)[16][4], double (&rv)[16][4], const double* ccomp,
-                                            const double* rcomp, int j, int ty, int tx, double invd) {
+__device__ __forceinline__ void diag_block8(double (&av)[16][4], double (&rv)[16][4], double* ccomp, double* rcomp,
+                                            double* dvec, int ty, int tx, int tid, int k0, int n_valid, int* info) {
   constexpr int JB = JA / 4;
-  const double* col = ccomp + diag_colbase(j) - j;   // col[i] = c_ij for i >= j (reads below j stay in bounds)
-  const double* row = rcomp + diag_rowbase(j);
-  double ck[4], rk[4];
+#pragma unroll 1
+  for (int jj = 0; jj < 8; ++jj) {
+    const int j = 8 * JA + jj;
+    double* col = ccomp + diag_colbase(j) - j;   // col[i] = c_ij for i >= j (reads below j stay inside the store)
+    double* row = rcomp + diag_rowbase(j);       // row[m] = r_jm for m <= j
+    // ---- publish the now-final column j of A and row j of R
+    if (tx == (j & 31)) {
+      if (ty >= jj) col[8 * JA + ty] = av[JA][JB];
 #pragma unroll
-  for (int b = 0; b < 4; ++b) {
-    ck[b] = (FACTOR && b >= JB) ? col[32 * b + tx] : 0.0;
-    rk[b] = (b < JB) ? row[32 * b + tx] : ((b == JB && 32 * b + tx <= j) ? row[32 * b + tx] : 0.0);
-  }
+      for (int a = JA + 1; a < 16; ++a) col[8 * a + ty] = av[a][JB];
+    }
+    if (ty == jj) {
 #pragma unroll
-  for (int a = JA; a < 16; ++a) {
-    const double ci = col[8 * a + ty] * invd;
+      for (int b = 0; b < JB; ++b) row[32 * b + tx] = rv[JA][b];
+      if (32 * JB + tx <= j) row[32 * JB + tx] = rv[JA][JB];
+    }
+    __syncthreads();
+    const double d = col[j];
+    if (tid == 0) {
+      dvec[j] = d;
+      if (!(d > 0.0) && (k0 + j) < n_valid) atomicCAS(info, 0, k0 + j + 1);
+    }
+    const double invd = __drcp_rn(d);
+    // ---- rank-1 updates, unmasked over the live sub-blocks
+    double ck[4], rk[4];
 #pragma unroll
-    for (int b = 0; b < 4; ++b)
-      if (diag_owned(a, b)) {
-        if (FACTOR && b >= JB) av[a][b] = fma(-ci, ck[b], av[a][b]);
-        if (b <= JB) rv[a][b] = fma(-ci, rk[b], rv[a][b]);
-      }
+    for (int b = 0; b < 4; ++b) {
+      ck[b] = (FACTOR && b >= JB) ? col[32 * b + tx] : 0.0;
+      rk[b] = (b < JB) ? row[32 * b + tx] : 0.0;
+    }
+    rk[JB] = (32 * JB + tx <= j) ? row[32 * JB + tx] : 0.0;
+#pragma unroll
+    for (int a0 = JA; a0 < 16; a0 += 4) {
+      double ci[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (a0 + u < 16) ci[u] = col[8 * (a0 + u) + ty] * invd;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (a0 + u < 16) {
+#pragma unroll
+          for (int b = 0; b < 4; ++b)
+            if (diag_owned(a0 + u, b)) {
+              if (FACTOR && b >= JB) av[a0 + u][b] = fma(-ci[u], ck[b], av[a0 + u][b]);
+              if (b <= JB) rv[a0 + u][b] = fma(-ci[u], rk[b], rv[a0 + u][b]);
+            }
+        }
+    }
   }
 }
 
@@ -108,30 +122,11 @@ potrf_diag_kernel(double* __restrict__ A, long long lda, int k0_first, double* _
       }
     }
 
-  for (int j = 0; j < NB; ++j) {
-    const int ja = j >> 3;
-    switch (ja) {
-#define GPB_DIAG_PUB(JA) case JA: diag_publish<JA>(av, rv, ccomp, rcomp, j, ty, tx); break;
-      GPB_DIAG_PUB(0) GPB_DIAG_PUB(1) GPB_DIAG_PUB(2) GPB_DIAG_PUB(3) GPB_DIAG_PUB(4) GPB_DIAG_PUB(5)
-      GPB_DIAG_PUB(6) GPB_DIAG_PUB(7) GPB_DIAG_PUB(8) GPB_DIAG_PUB(9) GPB_DIAG_PUB(10) GPB_DIAG_PUB(11)
-      GPB_DIAG_PUB(12) GPB_DIAG_PUB(13) GPB_DIAG_PUB(14) GPB_DIAG_PUB(15)
-#undef GPB_DIAG_PUB
-    }
-    __syncthreads();
-    const double d = ccomp[diag_colbase(j)];
-    if (tid == 0) {
-      dvec[j] = d;
-      if (!(d > 0.0) && (k0 + j) < n_valid) atomicCAS(info, 0, k0 + j + 1);
-    }
-    const double invd = 1.0 / d;
-    switch (ja) {
-#define GPB_DIAG_UPD(JA) case JA: diag_update<JA, FACTOR>(av, rv, ccomp, rcomp, j, ty, tx, invd); break;
-      GPB_DIAG_UPD(0) GPB_DIAG_UPD(1) GPB_DIAG_UPD(2) GPB_DIAG_UPD(3) GPB_DIAG_UPD(4) GPB_DIAG_UPD(5)
-      GPB_DIAG_UPD(6) GPB_DIAG_UPD(7) GPB_DIAG_UPD(8) GPB_DIAG_UPD(9) GPB_DIAG_UPD(10) GPB_DIAG_UPD(11)
-      GPB_DIAG_UPD(12) GPB_DIAG_UPD(13) GPB_DIAG_UPD(14) GPB_DIAG_UPD(15)
-#undef GPB_DIAG_UPD
-    }
-  }
+#define GPB_DIAG_BLK(JA) diag_block8<JA, FACTOR>(av, rv, ccomp, rcomp, dvec, ty, tx, tid, k0, n_valid, info);
+  GPB_DIAG_BLK(0) GPB_DIAG_BLK(1) GPB_DIAG_BLK(2) GPB_DIAG_BLK(3) GPB_DIAG_BLK(4) GPB_DIAG_BLK(5) GPB_DIAG_BLK(6)
+  GPB_DIAG_BLK(7) GPB_DIAG_BLK(8) GPB_DIAG_BLK(9) GPB_DIAG_BLK(10) GPB_DIAG_BLK(11) GPB_DIAG_BLK(12)
+  GPB_DIAG_BLK(13) GPB_DIAG_BLK(14) GPB_DIAG_BLK(15)
+#undef GPB_DIAG_BLK
   __syncthreads();
   if (tid < NB) rsv[tid] = FACTOR ? 1.0 / sqrt(dvec[tid]) : 1.0 / dvec[tid];
   if (logdet != nullptr && tid >= 128 && tid < 160) {

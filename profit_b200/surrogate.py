@@ -96,6 +96,18 @@ except Exception:  # profit not installed: stand-alone base with the same contra
         def decode_training_data(self):
             pass
 
+        def encode_training_data(self):
+            pass
+
+        def encode_predict_data(self, x):
+            return x
+
+        def decode_predict_data(self, ym, yv):
+            return ym, yv
+
+        def decode_hyperparameters(self):
+            pass
+
         def print_hyperparameters(self, prefix):
             pass
 
@@ -137,9 +149,7 @@ class B200GPSurrogate(_GPBase):
         super().__init__()
         self.hess_inv = None
         self._device = device
-        self._backend = None
-        self._resident = None     # (id(X), id(y), shapes) currently uploaded
-        self._factor_key = None   # (resident key, hyper-parameters) currently factorised
+        self._backend = None      # may be shared between surrogates (multi-output children): residency is tracked on it
 
     # -- device plumbing --------------------------------------------------------------------------------
     @property
@@ -152,10 +162,10 @@ class B200GPSurrogate(_GPBase):
         X = np.ascontiguousarray(self.Xtrain, dtype=np.float64)
         y = np.ascontiguousarray(self.ytrain, dtype=np.float64)
         key = (X.shape, y.shape, hash(X.tobytes()), hash(y.tobytes())) if X.size < (1 << 22) else None
-        if key is None or key != self._resident:
-            self.backend.set_train(X, y)
-            self._resident = key
-            self._factor_key = None
+        be = self.backend
+        if key is None or key != be.resident_key:
+            be.set_train(X, y)
+            be.resident_key = key
 
     def _theta(self, with_sigma_n=True):
         keys = ("length_scale", "sigma_f", "sigma_n")
@@ -219,21 +229,20 @@ class B200GPSurrogate(_GPBase):
     def _ensure_factor(self):
         self._upload()
         theta = self._theta()
-        key = (self._resident, theta.tobytes(), getattr(self.kernel, "__name__", str(self.kernel)))
-        if self._resident is None or key != self._factor_key:
-            self.backend.factorize(kernel_kind(self.kernel), theta)
-            self._factor_key = key
+        be = self.backend
+        key = (be.resident_key, theta.tobytes(), getattr(self.kernel, "__name__", str(self.kernel)))
+        if be.resident_key is None or key != be.factor_key:
+            be.factorize(kernel_kind(self.kernel), theta)
+            be.factor_key = key
 
     def add_training_data(self, X, y):
         """custom_surrogate.py:122-134: append rows; hyper-parameters are not re-optimised here."""
         self.Xtrain = np.concatenate([self.Xtrain, X], axis=0)
         self.ytrain = np.concatenate([self.ytrain, y], axis=0)
-        self._resident = None
 
     def set_ytrain(self, ydata):
         """custom_surrogate.py:136-142."""
         self.ytrain = np.atleast_2d(ydata.copy())
-        self._resident = None
 
     def get_marginal_variance(self, Xpred):
         raise NotImplementedError(
@@ -251,7 +260,6 @@ class B200GPSurrogate(_GPBase):
         fixed = bool(self.fixed_sigma_n or fixed_sigma_n)
         opt = _gpf.optimize(self.Xtrain, self.ytrain, a0, self.kernel, fixed_sigma_n=fixed,
                             eval_gradient=eval_gradient, return_hess_inv=return_hess_inv, backend=self.backend)
-        self._resident = None  # optimize() uploaded through the function-level path
         if return_hess_inv:
             self.hess_inv = opt[1]
             opt = opt[0]
@@ -314,6 +322,88 @@ class B200GPSurrogate(_GPBase):
         return self
 
 
+class B200MultiOutputGPSurrogate(_GPBase):
+    """Independent GP per output column -- mirror of ``MultiOutputGPSurrogate`` ("CustomMultiOutputGP",
+    custom_surrogate.py:285-451) with ``B200GPSurrogate`` children that share one device backend."""
+
+    def __init__(self, child=B200GPSurrogate, device=None):
+        super().__init__()
+        self.child = child
+        self.models = []
+        self._device = device
+        self._shared_backend = None
+
+    def _new_child(self):
+        m = self.child()
+        if self._shared_backend is None:
+            self._shared_backend = GPBackend(self._device)
+        m._backend = self._shared_backend
+        return m
+
+    def pre_train(self, X, y, *args, **kwargs):
+        if HAVE_PROFIT:
+            _Surrogate.pre_train(self, X, y)
+        else:
+            self._check_training_data(X, y)
+        self.output_ndim = self.ytrain.shape[-1]
+
+    def train(self, X, y, kernel=_gp_defaults["kernel"], hyperparameters=_gp_defaults["hyperparameters"],
+              fixed_sigma_n=_base_defaults["fixed_sigma_n"], return_hess_inv=False):
+        """custom_surrogate.py:292-315.  Like the reference, the children are trained with eval_gradient=False
+        (the positional ``False`` at :309), i.e. SciPy finite-differences the device NLL."""
+        self.pre_train(X, y)
+        self.kernel = kernel if self.kernel is None else self.kernel
+        self.hyperparameters = dict(hyperparameters) if not self.hyperparameters else self.hyperparameters
+        self.fixed_sigma_n = fixed_sigma_n or self.fixed_sigma_n
+        self.models = [self._new_child() for _ in range(self.output_ndim)]
+        for dim, m in enumerate(self.models):
+            m.train(self.Xtrain, self.ytrain[:, [dim]], self.kernel, dict(self.hyperparameters), self.fixed_sigma_n,
+                    False, return_hess_inv)
+        self._set_hyperparameters_from_model()
+        self.trained = True
+
+    def _set_hyperparameters_from_model(self):
+        # custom_surrogate.py:317-328: children concatenated, then reduced to norm / max
+        merged = {k: np.concatenate([np.atleast_1d(m.hyperparameters[k]) for m in self.models])
+                  for k in ("length_scale", "sigma_f", "sigma_n")}
+        self.hyperparameters = {"length_scale": np.atleast_1d(np.linalg.norm(merged["length_scale"])),
+                                "sigma_f": np.atleast_1d(np.max(merged["sigma_f"])),
+                                "sigma_n": np.atleast_1d(np.max(merged["sigma_n"]))}
+
+    def predict(self, Xpred, add_data_variance=True):
+        Xpred = self.pre_predict(Xpred)
+        ypred = np.empty((Xpred.shape[0], self.output_ndim))
+        yvar = np.empty_like(ypred)
+        for dim, m in enumerate(self.models):
+            ypred[:, [dim]], yvar[:, [dim]] = m.predict(Xpred, add_data_variance)
+        return ypred, yvar
+
+    def add_training_data(self, X, y):
+        self.Xtrain = np.concatenate([self.Xtrain, X], axis=0)
+        self.ytrain = np.concatenate([self.ytrain, y], axis=0)
+        for dim, m in enumerate(self.models):
+            m.add_training_data(X, y[:, [dim]])
+
+    def set_ytrain(self, y):
+        for dim, m in enumerate(self.models):
+            m.set_ytrain(y[:, [dim]])
+        self.ytrain = np.atleast_2d(y.copy())
+
+    def optimize(self, **opt_kwargs):
+        for m in self.models:
+            m.optimize(**opt_kwargs)
+
+    def select_kernel(self, kernel):
+        return select_kernel(kernel)
+
+    def save_model(self, path):
+        raise NotImplementedError("use the children's save_model (custom_surrogate.py:356-390 needs proFit's HDF5 handler)")
+
+    @classmethod
+    def load_model(cls, path):
+        raise NotImplementedError("use the children's load_model")
+
+
 def register(label="B200"):
     """Register the class in proFit's surrogate registry (util/base_class.py:15-26)."""
     if not HAVE_PROFIT:
@@ -329,5 +419,6 @@ def register_as_custom():
 if HAVE_PROFIT:  # pragma: no cover
     try:
         register("B200")
+        _Surrogate.register("B200MultiOutputGP")(B200MultiOutputGPSurrogate)
     except Exception:
         pass

@@ -397,3 +397,57 @@ def test_train_latency_small_problem(backend, golden):
     dt = time.perf_counter() - t0
     print(f"train N=200: {dt*1e3:.1f} ms")
     assert dt < 1.0
+
+
+def test_multi_output_surrogate_equals_independent_models(backend):
+    from profit_b200 import B200GPSurrogate, B200MultiOutputGPSurrogate
+
+    X, y = oracle.synthetic_problem(150, 2)
+    Y = np.hstack([y, np.cos(3 * X[:, :1]) + 0.2 * y])
+    hyp = {"length_scale": np.array([0.5]), "sigma_f": np.array([1.0]), "sigma_n": np.array([0.2])}
+    mo = B200MultiOutputGPSurrogate()
+    mo.train(X, Y, kernel="RBF", hyperparameters=hyp)
+    Xc = np.random.default_rng(9).random((40, 2))
+    ym, yv = mo.predict(Xc)
+    assert ym.shape == (40, 2) and yv.shape == (40, 2)
+    for dim in range(2):
+        single = B200GPSurrogate()
+        single.train(X, Y[:, [dim]], kernel="RBF", hyperparameters=dict(hyp), eval_gradient=False)
+        m, v = single.predict(Xc)
+        assert np.allclose(ym[:, [dim]], m, rtol=1e-9, atol=1e-12) and np.allclose(yv[:, [dim]], v, rtol=1e-9)
+
+
+# ------------------------------------------------------------------------------------------ BASELINE shapes vs oracle
+@pytest.fixture(scope="module")
+def baseline_golden():
+    import json
+    import os
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_baseline_shapes.json")
+    with open(path) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("key", ["c1_nll", "c4_nll", "c2_nll"])
+def test_baseline_shapes_nll_grad_vs_oracle(backend, baseline_golden, key):
+    """BASELINE.json configs[1] (N=4096, D=8 RBF), configs[4] (N=8192, D=16 RBF) and the headline configs[2]
+    (N=16384, D=10 Matern-5/2) against oracle values computed on the host (tests/golden/make_golden_large.py)."""
+    c = baseline_golden[key]
+    X, y = oracle.synthetic_problem(c["N"], c["D"])
+    kind = KERN[c["kernel"]][0]
+    backend.set_train(X, y)
+    nll, g = backend.nll(kind, np.array(c["theta"]), want_grad=True)
+    assert abs(nll - c["nll"]) <= NLL_RTOL * abs(c["nll"])
+    assert grad_err(g, c["grad"]) <= NLL_RTOL
+
+
+def test_baseline_shape_predict_vs_oracle(backend, baseline_golden):
+    """BASELINE.json configs[3]: N=8192 training points, 4096 of the candidates."""
+    c = baseline_golden["c3_predict"]
+    X, y = oracle.synthetic_problem(c["N"], c["D"])
+    backend.set_train(X, y)
+    backend.factorize(KERN[c["kernel"]][0], np.array(c["theta"]))
+    Xc = np.random.default_rng(c["seed"]).random((c["M"], c["D"]))
+    m, v = backend.predict(Xc)
+    assert np.max(np.abs(m.ravel() - np.array(c["mean"]))) <= PRED_RTOL * np.abs(c["mean"]).max()
+    assert rel_err(v, c["var"]) <= PRED_RTOL

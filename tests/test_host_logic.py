@@ -23,6 +23,7 @@ class OracleBackedFake:
 
     def __init__(self):
         self.calls = 0
+        self.resident_key = self.factor_key = None
 
     def set_train(self, X, y):
         self.X, self.y = np.array(X), np.array(y)
@@ -124,6 +125,29 @@ def test_surrogate_plumbing_and_errors(tmp_path):
         assert np.array_equal(t.hyperparameters[k], s.hyperparameters[k])
     with pytest.raises(RuntimeError, match="not implemented"):
         s.select_kernel("Wendland4")
+
+
+def test_multi_output_wrapper_trains_one_child_per_column(golden):
+    """custom_surrogate.py:285-328: independent children, merged hyper-parameters (norm / max)."""
+    from profit_b200 import B200MultiOutputGPSurrogate
+
+    c = golden["c0_train"]
+    X, y = np.array(c["X"])[:60], np.array(c["y"])[:60]
+    Y = np.hstack([y, 2.0 * y + 0.1])
+    s = B200MultiOutputGPSurrogate()
+    s._shared_backend = OracleBackedFake()
+    s.train(X, Y)
+    assert s.trained and s.output_ndim == 2 and len(s.models) == 2
+    assert all(m._backend is s._shared_backend for m in s.models)
+    ls = np.concatenate([m.hyperparameters["length_scale"] for m in s.models])
+    assert np.allclose(s.hyperparameters["length_scale"], [np.linalg.norm(ls)])
+    assert np.allclose(s.hyperparameters["sigma_f"], [max(m.hyperparameters["sigma_f"][0] for m in s.models)])
+    # the second output is an affine image of the first: same length scale, doubled signal scale
+    assert np.allclose(s.models[1].hyperparameters["length_scale"], s.models[0].hyperparameters["length_scale"], rtol=5e-2)
+    s.add_training_data(np.array([[0.3, 0.3]]), np.array([[0.5, 1.1]]))
+    assert s.models[1].ytrain.shape == (61, 1) and s.models[1].ytrain[-1, 0] == 1.1
+    s.set_ytrain(np.zeros((61, 2)))
+    assert s.models[0].ytrain.shape == (61, 1)
 
 
 def test_shard_bounds_cover_everything_once():
