@@ -76,6 +76,13 @@ int gpb_argmax(gpb_handle_t h, const double* v, long long M, long long* idx, dou
 int gpb_kernel_matrix(gpb_handle_t h, int kind, const double* Xa, long long na, const double* Xb, long long nb, int d,
                       const double* ell, int n_ell, double sigma_f, double sigma_n, double* K, double* dK);
 
+/* Marginal variance of Osborne (2012) -- gp_functions.marginal_variance_BBQ (gp_functions.py:376-454):
+ * out[c] = dm_c^T Hinv dm_c + pred_var[c] with dm_c = d(mean_c)/d(theta), theta = [length_scale..., sigma_f, sigma_n]
+ * of the factorised model (gpb_factorize).  hess_inv: (P, P) row-major, P = n_ell + 2 (already zero-padded if sigma_n was
+ * fixed); pred_var: (M) or NULL; out: (M).  Single-output models only. */
+int gpb_marginal_variance(gpb_handle_t h, const double* Xc, long long M, const double* hess_inv, const double* pred_var,
+                          double* out);
+
 /* L = cholesky(A) (lower, upper zeroed) -- np.linalg.cholesky at gp_functions.py:143,341. A: (n, n). */
 int gpb_cholesky(gpb_handle_t h, const double* A, long long n, double* L);
 

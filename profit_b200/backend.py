@@ -93,6 +93,17 @@ class GPBackend:
         _lib.check(st, self._h, "predict")
         return out_mean, out_var
 
+    def marginal_variance(self, Xc, hess_inv, predictive_variance=None):
+        """dm^T H^-1 dm + predictive variance per candidate (gp_functions.marginal_variance_BBQ) -> (M,) array."""
+        Xc = _lib.as_f64(Xc)
+        H = np.ascontiguousarray(hess_inv, dtype=np.float64)
+        M = int(Xc.shape[0])
+        pv = None if predictive_variance is None else np.ascontiguousarray(predictive_variance, dtype=np.float64).ravel()
+        out = np.empty(M)
+        st = self._lib.gpb_marginal_variance(self._h, _lib.ptr(Xc), M, _lib.ptr(H), _lib.ptr(pv), _lib.ptr(out))
+        _lib.check(st, self._h, "marginal_variance")
+        return out
+
     def argmax(self, v):
         v = _lib.as_f64(v)
         idx = ctypes.c_longlong()

@@ -115,6 +115,10 @@ struct gpb_handle_s {
   size_t dstage_cap = 0;
   double* dstage2 = nullptr;
   size_t dstage2_cap = 0;
+  double* dkm = nullptr;      // scaled inputs of the dense kernel-matrix kernel
+  size_t dkm_cap = 0;
+  double* dbbq = nullptr;     // marginal-variance scratch
+  size_t dbbq_cap = 0;
 
   cudaEvent_t ev0[GPB_NUM_STAGES], ev1[GPB_NUM_STAGES];
   bool ev_used[GPB_NUM_STAGES];
@@ -805,6 +809,88 @@ int invert_diag_blocks(H* h, Workspace& w) {
   return 0;
 }
 
+// Dense K(Xa, Xb) [+ dK] from device-resident raw inputs into device outputs (kernel_matrix_kernel).
+int dense_kernel_device(H* h, const KernelHyp& hy, const double* dXa, long long na, const double* dXb, long long nb,
+                        double* dKo, double* ddK, bool timed) {
+  const int P = hy.n_ell + 2;
+  const int DP = pick_dp(hy.D);
+  const long long na_pad = round_up(na, KM_ROWS), nb_pad = round_up(nb, KM_COLS);
+  int rc = ensure_cap(h, &h->dkm, &h->dkm_cap, (size_t)na_pad * DP + (size_t)DP * nb_pad);
+  if (rc) return rc;
+  double* dSa = h->dkm;                          // scaled rows of Xa (na_pad x DP)
+  double* dSb = h->dkm + (size_t)na_pad * DP;    // scaled columns of Xb (DP x nb_pad)
+  prescale_kernel<<<(unsigned)((na_pad * DP + 255) / 256), 256, 0, h->stream>>>(dXa, (int)na, hy, DP, dSa, nullptr, 0,
+                                                                              (int)na_pad);
+  prescale_kernel<<<(unsigned)((nb_pad * DP + 255) / 256), 256, 0, h->stream>>>(dXb, (int)nb, hy, DP, nullptr, dSb,
+                                                                              nb_pad, (int)nb_pad);
+  h->launches += 2;
+  if (timed) stage_begin(h, GPB_STAGE_ASSEMBLE);
+  dim3 grid((unsigned)(nb_pad / KM_COLS), (unsigned)(na_pad / KM_ROWS));
+  const size_t stage_doubles = (size_t)4 * KM_COLS * P;
+  // Two stages (2 barriers per pass, 4 CTAs/SM) measured faster than three (1 barrier, 2 CTAs/SM): 6.98 vs 6.01 TB/s.
+  int nbuf = 2;
+  if (const char* e = getenv("GPB_KM_NBUF"))
+    if (atoi(e) == 3 && 3 * stage_doubles * sizeof(double) <= 74 * 1024) nbuf = 3;
+  const size_t smem = ((size_t)KM_ROWS * DP + DP + (DP & 1) + (ddK ? nbuf * stage_doubles : 0)) * sizeof(double);
+#define GPB_KM(KINDV, DPV)                                                                                          \
+  {                                                                                                                 \
+    auto kern = kernel_matrix_kernel<KINDV, DPV>;                                                                   \
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                         \
+    kern<<<grid, KM_THREADS, smem, h->stream>>>(dSa, (int)na, dSb, nb_pad, (int)nb, hy, dKo, ddK, nbuf);            \
+  }
+#define GPB_KM_DP(KINDV)                                                                                            \
+  switch (DP) {                                                                                                     \
+    case 4: GPB_KM(KINDV, 4) break;                                                                                 \
+    case 8: GPB_KM(KINDV, 8) break;                                                                                 \
+    case 12: GPB_KM(KINDV, 12) break;                                                                               \
+    case 16: GPB_KM(KINDV, 16) break;                                                                               \
+    case 24: GPB_KM(KINDV, 24) break;                                                                               \
+    default: GPB_KM(KINDV, 32) break;                                                                               \
+  }
+  if (hy.kind == KIND_RBF) GPB_KM_DP(KIND_RBF) else GPB_KM_DP(KIND_MATERN52)
+#undef GPB_KM_DP
+#undef GPB_KM
+  h->launches++;
+  CK(cudaGetLastError());
+  if (timed) stage_end(h, GPB_STAGE_ASSEMBLE);
+  return 0;
+}
+
+// out[r*so_r + p*so_p] = sum_c T[r][c][p] * a[c]  +  scale * sum_c Kmat[r][c] * B[p*ldb + c]     (B, Kmat optional)
+// One warp per row r; lanes stride over c.  Used by the marginal-variance path (small problems, not a hot kernel).
+__global__ void __launch_bounds__(256) rowwise_contract_kernel(const double* __restrict__ T, const double* __restrict__ Kmat,
+                                                               int R, int C, int P, const double* __restrict__ a,
+                                                               const double* __restrict__ B, long long ldb, double scale,
+                                                               double* __restrict__ out, long long so_r, long long so_p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long r = (long long)blockIdx.x * 8 + warp;
+  if (r >= R) return;
+  const double* Tr = T + r * (long long)C * P;
+  for (int p = 0; p < P; ++p) {
+    double s = 0.0;
+    for (int c = lane; c < C; c += 32) {
+      s = fma(Tr[(long long)c * P + p], a[c], s);
+      if (B != nullptr) s = fma(scale * Kmat[r * (long long)C + c], B[(long long)p * ldb + c], s);
+    }
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) out[r * so_r + p * so_p] = s;
+  }
+}
+
+// out[c] = dm_c^T H dm_c + pv[c]
+__global__ void quadform_kernel(const double* __restrict__ dm, int M, int P, const double* __restrict__ H,
+                                const double* __restrict__ pv, double* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= M) return;
+  double s = 0.0;
+  for (int p = 0; p < P; ++p) {
+    double hq = 0.0;
+    for (int q = 0; q < P; ++q) hq = fma(H[p * P + q], dm[(long long)c * P + q], hq);
+    s = fma(dm[(long long)c * P + p], hq, s);
+  }
+  out[c] = s + pv[c];
+}
+
 }  // namespace
 
 // ================================================================================================ C ABI
@@ -882,6 +968,8 @@ int gpb_destroy(gpb_handle_t h) {
   cudaFree(h->dvar);
   cudaFree(h->dstage);
   cudaFree(h->dstage2);
+  cudaFree(h->dkm);
+  cudaFree(h->dbbq);
   for (int s = 0; s < GPB_NUM_STAGES; ++s) {
     cudaEventDestroy(h->ev0[s]);
     cudaEventDestroy(h->ev1[s]);
@@ -1173,64 +1261,85 @@ int gpb_kernel_matrix(gpb_handle_t h, int kind, const double* Xa, long long na, 
   hy.sf = sigma_f;
   hy.sn = sigma_n;
   const int P = n_ell + 2;
-  const int DP = pick_dp(d);
-  const long long na_pad = round_up(na, KM_ROWS), nb_pad = round_up(nb, KM_COLS);
   const size_t nK = (size_t)na * nb, ndK = dK ? nK * P : 0;
-  // staging: raw inputs | scaled rows of Xa (na_pad x DP) | scaled columns of Xb (DP x nb_pad)
-  const size_t off_xa = 0, off_xb = off_xa + (size_t)na * d, off_sa = off_xb + (size_t)nb * d,
-               off_sb = off_sa + (size_t)na_pad * DP, nin = off_sb + (size_t)DP * nb_pad;
-  int rc = ensure_cap(h, &h->dstage, &h->dstage_cap, nin);
+  int rc = ensure_cap(h, &h->dstage, &h->dstage_cap, (size_t)(na + nb) * d);
   if (rc) return rc;
   const bool k_dev = is_device_ptr(K), dk_dev = dK ? is_device_ptr(dK) : true;
   const size_t need_out = (k_dev ? 0 : nK) + (dk_dev ? 0 : ndK);
   if (need_out && (rc = ensure_cap(h, &h->dstage2, &h->dstage2_cap, need_out))) return rc;
-  double* dXa = h->dstage + off_xa;
-  double* dXb = h->dstage + off_xb;
-  double* dSa = h->dstage + off_sa;
-  double* dSb = h->dstage + off_sb;
+  double* dXa = h->dstage;
+  double* dXb = h->dstage + (size_t)na * d;
   CK(cudaMemcpyAsync(dXa, Xa, (size_t)na * d * sizeof(double), cudaMemcpyDefault, h->stream));
   CK(cudaMemcpyAsync(dXb, Xb, (size_t)nb * d * sizeof(double), cudaMemcpyDefault, h->stream));
-  prescale_kernel<<<(unsigned)((na_pad * DP + 255) / 256), 256, 0, h->stream>>>(dXa, (int)na, hy, DP, dSa, nullptr, 0,
-                                                                              (int)na_pad);
-  prescale_kernel<<<(unsigned)((nb_pad * DP + 255) / 256), 256, 0, h->stream>>>(dXb, (int)nb, hy, DP, nullptr, dSb,
-                                                                              nb_pad, (int)nb_pad);
-  h->launches += 2;
-  stages_reset(h);
-  stage_begin(h, GPB_STAGE_ASSEMBLE);
   double* dKo = k_dev ? K : h->dstage2;
   double* ddK = dK ? (dk_dev ? dK : h->dstage2 + (k_dev ? 0 : nK)) : nullptr;
-  dim3 grid((unsigned)(nb_pad / KM_COLS), (unsigned)(na_pad / KM_ROWS));
-  const size_t stage_doubles = (size_t)4 * KM_COLS * P;
-  // Two stages (2 barriers per pass, 4 CTAs/SM) measured faster than three (1 barrier, 2 CTAs/SM): 6.98 vs 6.01 TB/s.
-  int nbuf = 2;
-  if (const char* e = getenv("GPB_KM_NBUF"))
-    if (atoi(e) == 3 && 3 * stage_doubles * sizeof(double) <= 74 * 1024) nbuf = 3;
-  const size_t smem = ((size_t)KM_ROWS * DP + DP + (DP & 1) + (dK ? nbuf * stage_doubles : 0)) * sizeof(double);
-#define GPB_KM(KINDV, DPV)                                                                                          \
-  {                                                                                                                 \
-    auto kern = kernel_matrix_kernel<KINDV, DPV>;                                                                   \
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                         \
-    kern<<<grid, KM_THREADS, smem, h->stream>>>(dSa, (int)na, dSb, nb_pad, (int)nb, hy, dKo, ddK, nbuf);                  \
-  }
-#define GPB_KM_DP(KINDV)                                                                                            \
-  switch (DP) {                                                                                                     \
-    case 4: GPB_KM(KINDV, 4) break;                                                                                 \
-    case 8: GPB_KM(KINDV, 8) break;                                                                                 \
-    case 12: GPB_KM(KINDV, 12) break;                                                                               \
-    case 16: GPB_KM(KINDV, 16) break;                                                                               \
-    case 24: GPB_KM(KINDV, 24) break;                                                                               \
-    default: GPB_KM(KINDV, 32) break;                                                                               \
-  }
-  if (kind == KIND_RBF) GPB_KM_DP(KIND_RBF) else GPB_KM_DP(KIND_MATERN52)
-#undef GPB_KM_DP
-#undef GPB_KM
-  h->launches++;
-  CK(cudaGetLastError());
-  stage_end(h, GPB_STAGE_ASSEMBLE);
+  stages_reset(h);
+  if ((rc = dense_kernel_device(h, hy, dXa, na, dXb, nb, dKo, ddK, true))) return rc;
   if (!k_dev) CK(cudaMemcpyAsync(K, dKo, nK * sizeof(double), cudaMemcpyDefault, h->stream));
   if (dK && !dk_dev) CK(cudaMemcpyAsync(dK, ddK, ndK * sizeof(double), cudaMemcpyDefault, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   stages_collect(h);
+  return 0;
+}
+
+// Marginal (hyper-parameter-uncertainty) variance after Osborne 2012 -- gp_functions.marginal_variance_BBQ
+// (gp_functions.py:376-454):  out[c] = dm_c^T H^-1 dm_c + pred_var[c],
+//   dm_c[p] = dK*/dtheta_p[c,:] . alpha + K*[c,:] . dalpha/dtheta_p,   dalpha/dtheta_p = -K^-1 (dK/dtheta_p alpha).
+// Needs the factor of the current hyper-parameters (gpb_factorize).  hess_inv is (P, P) row-major, P = n_ell + 2.
+int gpb_marginal_variance(gpb_handle_t h, const double* Xc, long long M, const double* hess_inv, const double* pred_var,
+                          double* out) {
+  int rc = need_train(h);
+  if (rc) return rc;
+  if (!h->factor_ready) return fail(h, -3, "gpb_marginal_variance: call gpb_factorize first");
+  if (!Xc || !hess_inv || !out || M < 1) return fail(h, -1, "gpb_marginal_variance: bad argument");
+  if (h->n_out != 1) return fail(h, -1, "gpb_marginal_variance: single-output models only");
+  CK(cudaSetDevice(h->device));
+  Workspace& w = h->ws;
+  const long long N = w.N, Np = w.Np;
+  const int P = h->hyp.n_ell + 2, D = h->D;
+  // candidate chunk: (Mc x N x (P + 1)) doubles bounded to ~1 GiB
+  long long Mc = std::max<long long>(1, (1LL << 27) / (N * (P + 1)));
+  Mc = std::min<long long>(Mc, M);
+  const size_t n_train_dk = (size_t)N * N * (P + 1), n_cand_dk = (size_t)Mc * N * (P + 1);
+  const size_t vec = (size_t)3 * P * Np + (size_t)P * P + (size_t)Mc * (P + 2 + D);
+  if ((rc = ensure_cap(h, &h->dbbq, &h->dbbq_cap, std::max(n_train_dk, n_cand_dk) + vec))) return rc;
+  double* big = h->dbbq;                       // K | dK of the current block
+  double* v = big + std::max(n_train_dk, n_cand_dk);   // [P][Np]  dK_p alpha
+  double* t = v + (size_t)P * Np;                      // [P][Np]  W v_p
+  double* da = t + (size_t)P * Np;                     // [P][Np]  K^-1 v_p  ( = -dalpha/dtheta_p )
+  double* dH = da + (size_t)P * Np;                    // [P][P]
+  double* dm = dH + (size_t)P * P;                     // [Mc][P]
+  double* dpv = dm + (size_t)Mc * P;                   // [Mc]
+  double* dout = dpv + Mc;                             // [Mc]
+  double* dXc = dout + Mc;                             // [Mc][D]
+  CK(cudaMemcpyAsync(dH, hess_inv, (size_t)P * P * sizeof(double), cudaMemcpyDefault, h->stream));
+  CK(cudaMemsetAsync(v, 0, (size_t)3 * P * Np * sizeof(double), h->stream));
+  // training block: dK(X, X) with the noise plane, then v_p = dK_p alpha
+  if ((rc = dense_kernel_device(h, h->hyp, h->dX, N, h->dX, N, big, big + (size_t)N * N, false))) return rc;
+  rowwise_contract_kernel<<<(unsigned)((N + 7) / 8), 256, 0, h->stream>>>(big + (size_t)N * N, nullptr, (int)N, (int)N, P,
+                                                                          w.alpha, nullptr, Np, 1.0, v, 1, Np);
+  // K^-1 v_p = U (W v_p)
+  trigemv_kernel<<<(unsigned)((Np + 7) / 8), 256, 0, h->stream>>>(w.Wbuf, Np, Np, true, v, 1, Np, P, t, 1, Np);
+  trigemv_kernel<<<(unsigned)((Np + 7) / 8), 256, 0, h->stream>>>(w.Ubuf, Np, Np, false, t, 1, Np, P, da, 1, Np);
+  h->launches += 3;
+  CK(cudaGetLastError());
+  KernelHyp hs = h->hyp;
+  hs.sn = 0.0;   // K* and dK* are evaluated without the noise term (gp_functions.py:427-429)
+  for (long long c0 = 0; c0 < M; c0 += Mc) {
+    const long long mc = std::min(Mc, M - c0);
+    CK(cudaMemcpyAsync(dXc, Xc + c0 * D, (size_t)mc * D * sizeof(double), cudaMemcpyDefault, h->stream));
+    if (pred_var) CK(cudaMemcpyAsync(dpv, pred_var + c0, (size_t)mc * sizeof(double), cudaMemcpyDefault, h->stream));
+    else CK(cudaMemsetAsync(dpv, 0, (size_t)mc * sizeof(double), h->stream));
+    if ((rc = dense_kernel_device(h, hs, dXc, mc, h->dX, N, big, big + (size_t)mc * N, false))) return rc;
+    // dm[c][p] = sum_i dK*[c][i][p] alpha_i - K*[c][i] (K^-1 v_p)_i
+    rowwise_contract_kernel<<<(unsigned)((mc + 7) / 8), 256, 0, h->stream>>>(big + (size_t)mc * N, big, (int)mc, (int)N, P,
+                                                                           w.alpha, da, Np, -1.0, dm, P, 1);
+    quadform_kernel<<<(unsigned)((mc + 255) / 256), 256, 0, h->stream>>>(dm, (int)mc, P, dH, dpv, dout);
+    h->launches += 2;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out + c0, dout, (size_t)mc * sizeof(double), cudaMemcpyDefault, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
   return 0;
 }
 

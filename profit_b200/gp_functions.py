@@ -7,6 +7,7 @@ Same names, argument meaning and error behaviour as the reference:
 * ``negative_log_likelihood_cholesky``  gp_functions.py:103-187
 * ``negative_log_likelihood``           gp_functions.py:190-301 (Cholesky branch; see note)
 * ``invert_cholesky`` / ``invert``      gp_functions.py:304-373
+* ``marginal_variance_BBQ``             gp_functions.py:376-454
 * ``predict_f``                         gp_functions.py:457-491
 
 Note on ``negative_log_likelihood``: the reference first runs eigsh warm-up passes and only falls back to a
@@ -153,6 +154,43 @@ def optimize(xtrain, ytrain, a0, kernel, fixed_sigma_n=False, eval_gradient=Fals
     if return_hess_inv:
         return 10**opt_result.x, opt_result.hess_inv
     return 10**opt_result.x
+
+
+def marginal_variance_BBQ(Xtrain, ytrain, Xpred, kernel, hyperparameters, hess_inv, fixed_sigma_n=False, alpha=None,
+                          predictive_variance=0, backend=None):
+    """Marginal variance for active learning after Osborne (2012), gp_functions.py:376-454:
+    ``dm H^-1 dm^T`` (diagonal) + predictive variance, with ``dm`` the derivative of the predictive mean w.r.t.
+    [length_scale..., sigma_f, sigma_n].  Returns an (M, 1) array.
+
+    ``alpha`` is accepted for signature compatibility and ignored (the device factor supplies it).  With a vector
+    length scale the derivative has one entry per length scale -- the reference indexes ``dKy[..., 0]`` and
+    ``dKy[..., 1]`` as (l, sigma_f) (:439-448) and is only meaningful for a scalar length scale, where both agree.
+    """
+    ordered = [np.atleast_1d(np.asarray(hyperparameters[key], dtype=np.float64)).ravel()
+               for key in ("length_scale", "sigma_f", "sigma_n")]
+    predictive_variance = np.asarray(predictive_variance, dtype=np.float64)
+    if hess_inv is None:                                   # :406-408
+        return predictive_variance.reshape(-1, 1)
+    theta = np.concatenate(ordered)
+    P = theta.size
+    hess_inv = np.asarray(hess_inv, dtype=np.float64)
+    if fixed_sigma_n:                                      # :410-412, padded to the full parameter count
+        padded = np.zeros((P, P))
+        padded[:P - 1, :P - 1] = hess_inv
+        hess_inv = padded
+    Xp = np.asarray(Xpred, dtype=np.float64)
+    if Xp.ndim == 1:
+        Xp = Xp.reshape(-1, 1)
+    be = backend
+    if be is None:
+        be = shared_backend()
+        Xc, yc = _train_arrays(Xtrain, ytrain)
+        be.set_train(Xc, yc)
+    if be.factor_key is None:
+        be.factorize(kernel_kind(kernel), theta)
+    pv = np.broadcast_to(predictive_variance.reshape(-1), (Xp.shape[0],)) if predictive_variance.size else None
+    mv = be.marginal_variance(np.ascontiguousarray(Xp), hess_inv, pv)
+    return mv.reshape(-1, 1)
 
 
 def predict_f(hyp, x, y, xtest, kernel, return_full_cov=False, neig=0):

@@ -245,8 +245,14 @@ class B200GPSurrogate(_GPBase):
         self.ytrain = np.atleast_2d(ydata.copy())
 
     def get_marginal_variance(self, Xpred):
-        raise NotImplementedError(
-            "marginal_variance_BBQ (gp_functions.py:376-454) is outside the accelerated path (SURVEY.md section 8f-2)")
+        """custom_surrogate.py:144-163: re-optimise with the analytic gradient to obtain the inverse Hessian, then
+        add the hyper-parameter uncertainty of the mean (BBQ) to the predictive variance."""
+        self.optimize(fixed_sigma_n=self.fixed_sigma_n, eval_gradient=True, return_hess_inv=True)
+        assert self.hess_inv is not None
+        _, fvar = self.predict(Xpred)          # leaves the factor of the optimised hyper-parameters on the device
+        return _gpf.marginal_variance_BBQ(self.Xtrain, self.ytrain, self.pre_predict(Xpred), self.kernel,
+                                          self.hyperparameters, self.hess_inv, self.fixed_sigma_n,
+                                          predictive_variance=fvar, backend=self.backend)
 
     def select_kernel(self, kernel):
         """custom_surrogate.py:213-238: name or callable -> kernel callable; unknown names raise RuntimeError."""

@@ -118,6 +118,20 @@ ellm = np.array([0.5, 0.8, 1.1, 1.4])
 Ks, dKs = Matern(length_scale=ellm, nu=2.5)(Xm, eval_gradient=True)   # gradient w.r.t. log(length_scale)
 out["matern_sklearn"] = {"seed": 5, "n": 40, "D": 4, "length_scale": L(ellm), "K": L(Ks), "dK_dlogl": L(dKs)}
 
+# ---- marginal_variance_BBQ (gp_functions.py:376-454), scalar length scale ----------------------------------
+Xb, yb = oracle.synthetic_problem(80, 2)
+Xcb = np.random.default_rng(3).random((37, 2))
+hypb = {"length_scale": np.array([0.7]), "sigma_f": np.array([1.5]), "sigma_n": np.array([0.3])}
+rngb = np.random.default_rng(11)
+Ab = rngb.standard_normal((3, 3))
+Hb = Ab @ Ab.T / 3 + 0.1 * np.eye(3)
+pvb = rngb.random(37).reshape(-1, 1)
+out["bbq"] = {"N": 80, "D": 2, "M": 37, "seed": 3, "hyp": [0.7, 1.5, 0.3], "hess_inv": L(Hb), "pred_var": L(pvb.ravel()),
+              "mv": L(G.marginal_variance_BBQ(Xb, yb, Xcb, RBF, hypb, Hb, False, predictive_variance=pvb).ravel()),
+              "mv_fixed_sn": L(G.marginal_variance_BBQ(Xb, yb, Xcb, RBF, hypb, Hb[:2, :2], True,
+                                                       predictive_variance=pvb).ravel()),
+              "note": "gp_functions.marginal_variance_BBQ, scalar length scale"}
+
 path = os.path.join(ROOT, "tests", "golden", "reference_kats.json")
 with open(path, "w") as f:
     json.dump(out, f)

@@ -451,3 +451,49 @@ def test_baseline_shape_predict_vs_oracle(backend, baseline_golden):
     m, v = backend.predict(Xc)
     assert np.max(np.abs(m.ravel() - np.array(c["mean"]))) <= PRED_RTOL * np.abs(c["mean"]).max()
     assert rel_err(v, c["var"]) <= PRED_RTOL
+
+
+def test_marginal_variance_bbq(backend, golden):
+    """gp_functions.marginal_variance_BBQ: the reference's golden values (scalar length scale) and the oracle's
+    generalisation for ARD / Matern."""
+    from profit_b200 import RBF, Matern52, gp_functions as gpf
+
+    c = golden["bbq"]
+    X, y = oracle.synthetic_problem(c["N"], c["D"])
+    Xc = np.random.default_rng(c["seed"]).random((c["M"], c["D"]))
+    H = np.array(c["hess_inv"])
+    hyp = {"length_scale": np.array([c["hyp"][0]]), "sigma_f": np.array([c["hyp"][1]]), "sigma_n": np.array([c["hyp"][2]])}
+    pv = np.array(c["pred_var"]).reshape(-1, 1)
+    mv = gpf.marginal_variance_BBQ(X, y, Xc, RBF, hyp, H, predictive_variance=pv)
+    assert mv.shape == (c["M"], 1) and rel_err(mv.ravel(), c["mv"]) <= PRED_RTOL
+    mv2 = gpf.marginal_variance_BBQ(X, y, Xc, RBF, hyp, H[:2, :2], fixed_sigma_n=True, predictive_variance=pv)
+    assert rel_err(mv2.ravel(), c["mv_fixed_sn"]) <= PRED_RTOL
+    assert np.array_equal(gpf.marginal_variance_BBQ(X, y, Xc, RBF, hyp, None, predictive_variance=pv), pv)
+    # ARD Matern, more points than one chunk row block
+    X, y = oracle.synthetic_problem(333, 5)
+    Xc = np.random.default_rng(8).random((257, 5))
+    ell = np.linspace(0.6, 1.2, 5)
+    rng = np.random.default_rng(5)
+    A = rng.standard_normal((7, 7))
+    H = A @ A.T / 7 + 0.05 * np.eye(7)
+    hyp = {"length_scale": ell, "sigma_f": np.array([1.5]), "sigma_n": np.array([0.3])}
+    mv = gpf.marginal_variance_BBQ(X, y, Xc, Matern52, hyp, H)
+    ref = oracle.marginal_variance_bbq(X, y, Xc, oracle.matern52, ell, 1.5, 0.3, H)
+    assert rel_err(mv, ref) <= PRED_RTOL
+
+
+def test_get_marginal_variance_through_the_surrogate(backend, golden):
+    from profit_b200 import B200GPSurrogate
+
+    c = golden["c0_train"]
+    X, y = np.array(c["X"])[:120], np.array(c["y"])[:120]
+    s = B200GPSurrogate()
+    s.train(X, y)
+    Xc = np.random.default_rng(1).random((50, 2))
+    mv = s.get_marginal_variance(Xc)
+    _, fvar = s.predict(Xc)
+    assert mv.shape == (50, 1) and s.hess_inv.shape == (3, 3)
+    assert np.all(mv >= fvar - 1e-12)                       # H^-1 is positive definite: the marginal term only adds
+    ref = oracle.marginal_variance_bbq(X, y, Xc, oracle.rbf, s.hyperparameters["length_scale"][0],
+                                       s.hyperparameters["sigma_f"][0], s.hyperparameters["sigma_n"][0], s.hess_inv, fvar)
+    assert rel_err(mv, ref) <= 1e-7

@@ -95,6 +95,19 @@ def test_multi_output(golden):
     assert rel_err(g, c["grad"]) <= 1e-11
 
 
+def test_marginal_variance_bbq(golden):
+    c = golden["bbq"]
+    X, y = oracle.synthetic_problem(c["N"], c["D"])
+    Xc = np.random.default_rng(c["seed"]).random((c["M"], c["D"]))
+    H = np.array(c["hess_inv"])
+    mv = oracle.marginal_variance_bbq(X, y, Xc, oracle.rbf, c["hyp"][0], c["hyp"][1], c["hyp"][2], H, np.array(c["pred_var"]))
+    assert rel_err(mv.ravel(), c["mv"]) <= 1e-12
+    Hp = np.zeros((3, 3))
+    Hp[:2, :2] = H[:2, :2]
+    mv2 = oracle.marginal_variance_bbq(X, y, Xc, oracle.rbf, *c["hyp"], Hp, np.array(c["pred_var"]))
+    assert rel_err(mv2.ravel(), c["mv_fixed_sn"]) <= 1e-12
+
+
 def test_matern_against_sklearn_vectors(golden):
     c = golden["matern_sklearn"]
     X = np.random.default_rng(c["seed"]).random((c["n"], c["D"]))
