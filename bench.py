@@ -156,6 +156,31 @@ def cpu_nll_grad_sample(n_sample, steps=1):
             "sample_seconds": best, "scaled_seconds": full}
 
 
+def unmodified_reference_sample(n=2048):
+    """If the unmodified reference is installed (baseline/_ref, git-ignored), time ITS
+    negative_log_likelihood_cholesky(eval_gradient=True) once on a small RBF problem.  Informational: the reference has
+    no Matern-5/2 kernel and its O(N^3 P) trace cannot reach N=16384 in memory or time, so the headline CPU number
+    comes from the oracle port, which is the faster CPU algorithm."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref, "profit")):
+        return None
+    try:
+        sys.path.insert(0, ref)
+        from profit.sur.gp.backend.gp_functions import negative_log_likelihood_cholesky
+        from profit.sur.gp.backend.python_kernels import RBF
+        from threadpoolctl import threadpool_limits
+
+        X, y = synthetic_problem(n, DIM)
+        with threadpool_limits(limits=len(os.sched_getaffinity(0))):
+            t0 = time.perf_counter()
+            negative_log_likelihood_cholesky(theta_ref(DIM), X, y, RBF, eval_gradient=True)
+            dt = time.perf_counter() - t0
+        return {"what": f"unmodified profit negative_log_likelihood_cholesky(eval_gradient=True), RBF ARD, N={n}, D={DIM}",
+                "seconds": dt, "evals_per_s": 1.0 / dt}
+    except Exception as exc:  # the reference is optional here
+        return {"error": repr(exc)}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -174,7 +199,7 @@ def run_reference(args):
             "config": workload_config(),
             "cpu_baseline": {"value": 1.0 / sec, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": 1.0 / sec, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "gpu_launches": 0, "unmodified_reference_sample": unmodified_reference_sample()}
     print(json.dumps(line), flush=True)
 
 

@@ -1,0 +1,58 @@
+"""Drop-in check with the reference's own code on the GPU box: proFit (installed, unmodified, into the git-ignored
+baseline/_ref by `pip install --no-deps --target baseline/_ref <reference>`) drives `Surrogate["B200"]` through its
+registry and its active-learning acquisition loop, next to its own `Surrogate["Custom"]` on the same inputs."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "baseline", "_ref")
+
+_SCRIPT = r'''
+import numpy as np
+from profit.sur import Surrogate
+from profit.sur.gp import GaussianProcess
+from profit.al.aquisition_functions import SimpleExploration
+import profit_b200.surrogate as ps                      # self-registers as Surrogate["B200"]
+
+assert Surrogate["B200"] is ps.B200GPSurrogate and issubclass(Surrogate["B200"], GaussianProcess)
+rng = np.random.default_rng(0)
+X = rng.random((150, 2)); y = (np.sin(3 * X[:, 0]) + np.cos(2 * X[:, 1]) + 0.05 * rng.standard_normal(150)).reshape(-1, 1)
+Xc = rng.random((400, 2))
+
+ref = Surrogate["Custom"](); ref.train(X, y)
+gpu = Surrogate["B200"]();   gpu.train(X, y)
+hr = np.concatenate([ref.hyperparameters[k] for k in ("length_scale", "sigma_f", "sigma_n")])
+hg = np.concatenate([gpu.hyperparameters[k] for k in ("length_scale", "sigma_f", "sigma_n")])
+assert np.allclose(hr, hg, rtol=1e-4), (hr, hg)
+assert gpu.kernel.__name__ == "RBF"                      # asserted by the reference's own integration tests
+mr, vr = ref.predict(Xc); mg, vg = gpu.predict(Xc)
+assert mg.shape == mr.shape and vg.shape == vr.shape
+assert np.allclose(mr, mg, rtol=1e-4, atol=1e-6) and np.allclose(vr, vg, rtol=1e-3)
+
+# same hyper-parameters -> the two backends must agree to the north-star tolerance
+gpu.hyperparameters = {k: v.copy() for k, v in ref.hyperparameters.items()}
+mg, vg = gpu.predict(Xc)
+assert np.max(np.abs(mg - mr)) <= 1e-8 * np.abs(mr).max() and np.max(np.abs(vg - vr) / vr) <= 1e-8
+
+# the reference's acquisition loop (aquisition_functions.py:63-74) drives predict / add_training_data / optimize
+picks = {}
+for name, sur in (("ref", ref), ("gpu", gpu)):
+    af = SimpleExploration(Xc, sur, None)
+    picks[name] = af.find_next_candidates(2)
+    assert sur.Xtrain.shape[0] == 152
+assert np.allclose(picks["ref"][0], picks["gpu"][0]), picks   # identical first pick (same model, same candidates)
+print("profit integration ok", hg)
+'''
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "profit")), reason="reference not installed in baseline/_ref")
+def test_profit_drives_the_b200_surrogate(built_lib, tmp_path):
+    script = tmp_path / "integration.py"
+    script.write_text(_SCRIPT)
+    env = dict(os.environ, PYTHONPATH=REF + os.pathsep + ROOT, PYTHONDONTWRITEBYTECODE="1")
+    out = subprocess.run([sys.executable, str(script)], env=env, capture_output=True, text=True, timeout=900, cwd=str(tmp_path))
+    assert out.returncode == 0 and "profit integration ok" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
