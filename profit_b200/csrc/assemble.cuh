@@ -230,7 +230,7 @@ kernel_matrix_kernel(const double* __restrict__ XsA, int na, const double* __res
 // (gp_functions.py:169-180 with the trace written as an elementwise contraction).  Partial sums per CTA go to
 // part[cta][DP+2] (slots: l_0..l_{DP-1}, sf, sn) and are reduced in a fixed order by reduce_partials_kernel.
 template <int KIND, int DP>
-__global__ void __launch_bounds__(AS_THREADS)
+__global__ void __launch_bounds__(AS_THREADS, (DP <= 16) ? 2 : 1)
 grad_contract_kernel(const double* __restrict__ Xs, const double* __restrict__ XsT, long long ldt, int n, double sf2,
                      const double* __restrict__ Kinv, long long ldk, const double* __restrict__ alpha,
                      long long lda, int n_out, double* __restrict__ part) {
@@ -245,51 +245,39 @@ grad_contract_kernel(const double* __restrict__ Xs, const double* __restrict__ X
   if (active) {
     for (int e = threadIdx.x; e < AS_TM * DP; e += AS_THREADS)
       xi[e / DP][e % DP] = Xs[(long long)(row0 + e / DP) * DP + e % DP];
-    const int cp = threadIdx.x & 63, rg = threadIdx.x >> 6;
-    const int c = col0 + 2 * cp;
-    double xj0[DP], xj1[DP];
+    // thread owns ONE column (128 column lanes) and every second row of the tile: half the registers of a
+    // two-column layout, two CTAs per SM
+    const int cl = threadIdx.x & 127, rg = threadIdx.x >> 7;
+    const int c = col0 + cl;
+    double xj[DP];
 #pragma unroll
-    for (int d = 0; d < DP; ++d) {
-      const double2 v = *reinterpret_cast<const double2*>(XsT + (long long)d * ldt + c);
-      xj0[d] = v.x;
-      xj1[d] = v.y;
-    }
+    for (int d = 0; d < DP; ++d) xj[d] = XsT[(long long)d * ldt + c];
     __syncthreads();
-    for (int rr = rg; rr < AS_TM; rr += 4) {
-      const int r = row0 + rr;
-      if (r >= n || c > r) continue;
-      const double2 kin = *reinterpret_cast<const double2*>(Kinv + (long long)r * ldk + c);
-      double aa0 = 0.0, aa1 = 0.0;
-      for (int o = 0; o < n_out; ++o) {
-        const double ar = alpha[(long long)o * lda + r];
-        aa0 = fma(ar, alpha[(long long)o * lda + c], aa0);
-        aa1 = fma(ar, alpha[(long long)o * lda + c + 1], aa1);
-      }
-      double w0 = n_out * kin.x - aa0, w1 = n_out * kin.y - aa1;
-      w0 = (c == r) ? w0 : 2.0 * w0;
-      w1 = (c + 1 == r) ? w1 : 2.0 * w1;
-      if (c >= n) w0 = 0.0;
-      if (c + 1 > r || c + 1 >= n) w1 = 0.0;
-      double u0[DP], u1[DP];
-      double a0 = 0.0, a1 = 0.0;
+    if (c < n) {
+      for (int rr = rg; rr < AS_TM; rr += 2) {
+        const int r = row0 + rr;
+        if (r >= n || c > r) continue;
+        const double kin = Kinv[(long long)r * ldk + c];
+        double aa = 0.0;
+        for (int o = 0; o < n_out; ++o) aa = fma(alpha[(long long)o * lda + r], alpha[(long long)o * lda + c], aa);
+        double w = n_out * kin - aa;
+        w = (c == r) ? w : 2.0 * w;
+        double u2[DP];
+        double d2 = 0.0;
 #pragma unroll
-      for (int d = 0; d < DP; ++d) {
-        const double x = xi[rr][d];
-        const double v0 = x - xj0[d], v1 = x - xj1[d];
-        u0[d] = v0 * v0;
-        u1[d] = v1 * v1;
-        a0 += u0[d];
-        a1 += u1[d];
-      }
-      double k0, g0, k1, g1;
-      kern_eval<KIND>(a0, sf2, k0, g0);
-      kern_eval<KIND>(a1, sf2, k1, g1);
-      const double wg0 = w0 * g0, wg1 = w1 * g1;
+        for (int d = 0; d < DP; ++d) {
+          const double v = xi[rr][d] - xj[d];
+          u2[d] = v * v;
+          d2 += u2[d];
+        }
+        double k0, g0;
+        kern_eval<KIND>(d2, sf2, k0, g0);
+        const double wg = w * g0;
 #pragma unroll
-      for (int d = 0; d < DP; ++d) acc[d] = fma(wg0, u0[d], fma(wg1, u1[d], acc[d]));
-      acc[DP] = fma(w0, k0, fma(w1, k1, acc[DP]));
-      if (c == r) acc[DP + 1] += w0;
-      if (c + 1 == r) acc[DP + 1] += w1;
+        for (int d = 0; d < DP; ++d) acc[d] = fma(wg, u2[d], acc[d]);
+        acc[DP] = fma(w, k0, acc[DP]);
+        if (c == r) acc[DP + 1] += w;
+      }
     }
   }
   // fixed-order block reduction

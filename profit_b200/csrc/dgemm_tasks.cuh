@@ -107,6 +107,17 @@ dgemm_tasks_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
     for (int ni = 0; ni < NI; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
 
+  if constexpr (EPI == EPI_STORE) {
+    // C = alpha*acc + beta*C reads the old tile in the epilogue: pull it into L2 now, behind the main loop.
+    if (ep.beta != 0.0 && t < WN / 16) {
+#pragma unroll
+      for (int mi = 0; mi < MI; ++mi) {
+        const double* line = ep.C + (long long)(task.c_row + wm0 + mi * 8 + g) * ep.ldc + task.c_col + wn0 + 16 * t;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
+      }
+    }
+  }
+
   for (int kt = 0; kt < task.nk; ++kt) {
     const int s = kt % STAGES;
     const uint32_t ph = (kt / STAGES) & 1;
