@@ -121,6 +121,7 @@ struct gpb_handle_s {
   size_t dbbq_cap = 0;
 
   cudaEvent_t ev0[GPB_NUM_STAGES], ev1[GPB_NUM_STAGES];
+  cudaEvent_t evx[3];   // scratch timing events (gradient tail, predict chunk phases, debug GEMM)
   bool ev_used[GPB_NUM_STAGES];
   double stage_ms[GPB_NUM_STAGES];
 };
@@ -937,6 +938,7 @@ int gpb_create(int device, gpb_handle_t* out) {
     cudaEventCreate(&h->ev0[s]);
     cudaEventCreate(&h->ev1[s]);
   }
+  for (int s = 0; s < 3; ++s) cudaEventCreate(&h->evx[s]);
   stages_reset(h);
   cudaMalloc(&h->dscal, 64 * sizeof(double));
   cudaMalloc(&h->dinfo, sizeof(int));
@@ -974,6 +976,7 @@ int gpb_destroy(gpb_handle_t h) {
     cudaEventDestroy(h->ev0[s]);
     cudaEventDestroy(h->ev1[s]);
   }
+  for (int s = 0; s < 3; ++s) cudaEventDestroy(h->evx[s]);
   for (cudaEvent_t e : h->events) cudaEventDestroy(e);
   cudaStreamDestroy(h->stream2);
   cudaStreamDestroy(h->stream);
@@ -1046,9 +1049,7 @@ int gpb_nll(gpb_handle_t h, int kind, const double* theta, int n_ell, int want_g
     stage_begin(h, GPB_STAGE_SYRK);
     if ((rc = run_plan(h, w, w.syrk, false))) return rc;
     stage_end(h, GPB_STAGE_SYRK);
-    cudaEvent_t g0, g1;  // the GRAD stage has two pieces; time the second with its own pair and add
-    cudaEventCreate(&g0);
-    cudaEventCreate(&g1);
+    cudaEvent_t g0 = h->evx[0], g1 = h->evx[1];  // the GRAD stage has two pieces; time the second with its own pair
     cudaEventRecord(g0, h->stream);
     dim3 grid((unsigned)(w.Np / AS_TN), (unsigned)(w.Np / AS_TM));
     const size_t ncta = (size_t)grid.x * grid.y;
@@ -1061,17 +1062,11 @@ int gpb_nll(gpb_handle_t h, int kind, const double* theta, int n_ell, int want_g
     stage_end(h, GPB_STAGE_TOTAL);
     double host[64];
     CK(cudaMemcpyAsync(host, h->dscal, (1 + width) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    if ((rc = check_info(h))) {
-      cudaEventDestroy(g0);
-      cudaEventDestroy(g1);
-      return rc;
-    }
+    if ((rc = check_info(h))) return rc;
     stages_collect(h);
     float gms = 0.f;
     cudaEventElapsedTime(&gms, g0, g1);
     h->stage_ms[GPB_STAGE_GRAD] += gms;
-    cudaEventDestroy(g0);
-    cudaEventDestroy(g1);
     *nll = host[0];
     // dnll_p = 0.5 * sum_ij A_ij dK_ij,p   (gp_functions.py:180) with the per-parameter factors of
     // python_kernels.py:49-55 pulled out of the sums.
@@ -1167,10 +1162,7 @@ int gpb_predict(gpb_handle_t h, const double* Xc, long long M, int add_data_vari
   stages_reset(h);
   stage_begin(h, GPB_STAGE_TOTAL);
   double cross_ms = 0.0, var_ms = 0.0;
-  cudaEvent_t e0, e1, e2;
-  cudaEventCreate(&e0);
-  cudaEventCreate(&e1);
-  cudaEventCreate(&e2);
+  cudaEvent_t e0 = h->evx[0], e1 = h->evx[1], e2 = h->evx[2];
   for (long long c0 = 0; c0 < M; c0 += Mc) {
     const long long mc = std::min(Mc, M - c0);
     CK(cudaMemcpyAsync(h->dXc, Xc + c0 * h->D, (size_t)mc * h->D * sizeof(double), cudaMemcpyDefault, h->stream));
@@ -1223,9 +1215,6 @@ int gpb_predict(gpb_handle_t h, const double* Xc, long long M, int add_data_vari
   stages_collect(h);
   h->stage_ms[GPB_STAGE_CROSS] = cross_ms;
   h->stage_ms[GPB_STAGE_VAR] = var_ms;
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
-  cudaEventDestroy(e2);
   return 0;
 }
 
@@ -1431,9 +1420,7 @@ int gpb_debug_gemm(gpb_handle_t h, const double* A, const double* B, double* C, 
   ep.ldct = 0;
   ep.alpha = alpha;
   ep.beta = beta;
-  cudaEvent_t e0, e1;
-  cudaEventCreate(&e0);
-  cudaEventCreate(&e1);
+  cudaEvent_t e0 = h->evx[0], e1 = h->evx[1];
   cudaEventRecord(e0, h->stream);
   for (int r = 0; r < reps; ++r)
     if ((rc = launch_gemm(h, w, cfg, EPI_STORE, M_DBG_A, M_DBG_B, p.d_tasks, (int)p.tasks.size(), ep))) return rc;
@@ -1442,8 +1429,6 @@ int gpb_debug_gemm(gpb_handle_t h, const double* A, const double* B, double* C, 
   float t = 0.f;
   cudaEventElapsedTime(&t, e0, e1);
   if (ms) *ms = t / reps;
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
   p.clear();
   return 0;
 }

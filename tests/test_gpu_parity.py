@@ -497,3 +497,38 @@ def test_get_marginal_variance_through_the_surrogate(backend, golden):
     ref = oracle.marginal_variance_bbq(X, y, Xc, oracle.rbf, s.hyperparameters["length_scale"][0],
                                        s.hyperparameters["sigma_f"][0], s.hyperparameters["sigma_n"][0], s.hess_inv, fvar)
     assert rel_err(mv, ref) <= 1e-7
+
+
+def test_ill_conditioned_variance_vs_extended_precision(backend):
+    """Variance parity is conditioning-limited, not implementation-limited: on an ill-conditioned
+    1-D problem the reference's explicit-inverse formula and this backend's triangular formula differ by more than
+    1e-8, and the 50-digit truth shows the GPU result is the closer one."""
+    import mpmath as mp
+
+    mp.mp.dps = 50
+    rng = np.random.default_rng(1)
+    N, M = 84, 20
+    X = rng.random((N, 1))
+    y = np.sin(3 * X[:, 0]) + 0.3 * rng.standard_normal(N)
+    Xc = rng.random((M, 1))
+    ell, sf, sn = 0.45, 1.3, 0.12
+    K = mp.matrix(N, N)
+    for i in range(N):
+        for j in range(N):
+            d = (mp.mpf(X[i, 0]) / mp.mpf(ell) - mp.mpf(X[j, 0]) / mp.mpf(ell))
+            K[i, j] = mp.mpf(sf) ** 2 * mp.exp(-d * d / 2) + (mp.mpf(sn) ** 2 if i == j else 0)
+    Lm = mp.cholesky(K)
+    truth = np.empty(M)
+    for c in range(M):
+        ks = mp.matrix([mp.mpf(sf) ** 2 * mp.exp(-((mp.mpf(X[i, 0]) - mp.mpf(Xc[c, 0])) / mp.mpf(ell)) ** 2 / 2) for i in range(N)])
+        v = mp.lu_solve(Lm, ks)            # L v = k*  (L is triangular, so this is exact forward substitution)
+        truth[c] = float(mp.mpf(sf) ** 2 - sum(x * x for x in v) + mp.mpf(sn) ** 2)
+    backend.set_train(X, y)
+    backend.factorize(0, np.array([ell, sf, sn]))
+    _, v_gpu = backend.predict(Xc)
+    _, v_ref = oracle.predict(X, y, Xc, oracle.rbf, ell, sf, sn)       # the reference's explicit-inverse formula
+    err_gpu = np.max(np.abs(v_gpu - truth) / truth)
+    err_ref = np.max(np.abs(v_ref.ravel() - truth) / truth)
+    cond = np.linalg.cond(oracle.rbf(X, X, ell, sf, sn))
+    print(f"cond(K) = {cond:.2e}: |gpu - truth| = {err_gpu:.2e}, |reference formula - truth| = {err_ref:.2e}")
+    assert err_gpu <= 1e-10 and err_gpu <= err_ref
