@@ -34,7 +34,7 @@ using namespace gpb;
 namespace {
 
 enum MatId { M_L = 0, M_U, M_W, M_DINV, M_KST, M_PART, M_DBG_A, M_DBG_B, M_DBG_C, M_NONE };
-enum GemmCfg { CFG_128x128 = 0, CFG_128x64 = 1, CFG_64x128 = 2, NUM_CFG };
+enum GemmCfg { CFG_128x128 = 0, CFG_128x64 = 1, CFG_64x128 = 2, CFG_32x128 = 3, CFG_32x64 = 4, NUM_CFG };
 
 struct Launch {
   int type;  // 0 = diag block, 1 = tile GEMM
@@ -225,6 +225,8 @@ void cfg_tile(int cfg, int* bm, int* bn) {
   switch (cfg) {
     case CFG_128x128: *bm = 128; *bn = 128; break;
     case CFG_128x64: *bm = 128; *bn = 64; break;
+    case CFG_32x128: *bm = 32; *bn = 128; break;
+    case CFG_32x64: *bm = 32; *bn = 64; break;
     default: *bm = 64; *bn = 128; break;
   }
 }
@@ -243,6 +245,8 @@ int launch_gemm(H* h, Workspace& w, int cfg, int epi, int matA, int matB, const 
     switch (cfg) {
       case CFG_128x128: return launch_cfg<128, 128, 64, 32, 4, EPI_STORE, 1>(h, stream, tA, tB, d_tasks, ntasks, ep);
       case CFG_128x64: return launch_cfg<128, 64, 32, 32, 4, EPI_STORE, 2>(h, stream, tA, tB, d_tasks, ntasks, ep);
+      case CFG_32x128: return launch_cfg<32, 128, 16, 32, 4, EPI_STORE, 2>(h, stream, tA, tB, d_tasks, ntasks, ep);
+      case CFG_32x64: return launch_cfg<32, 64, 16, 16, 4, EPI_STORE, 2>(h, stream, tA, tB, d_tasks, ntasks, ep);
       default: return launch_cfg<64, 128, 32, 32, 4, EPI_STORE, 2>(h, stream, tA, tB, d_tasks, ntasks, ep);
     }
   } else {
@@ -259,6 +263,14 @@ int g_cfg_update = CFG_128x64;  // trailing updates / trtri / syrk / predict   (
 int g_outer_blocks = 0;         // outer panel width of the Cholesky in 128-blocks; 0 = by size (env GPB_OUTER_BLOCKS)
 int g_lookahead = 1;            // overlap the next panel factorisation with the trailing update (env GPB_LOOKAHEAD)
 
+// Small launches are latency-bound (one CTA takes ~15 us for a 128x64x128 tile on its own SM): cut the tiles finer
+// so the same work spreads over more SMs.  `coarse` is the configuration used for large launches.
+int g_fine_below = 148;          // launches with fewer 128-blocks than this use the fine tiles (env GPB_FINE_BELOW)
+int cfg_for_blocks(int coarse, int nblocks) {
+  if (nblocks >= g_fine_below) return coarse;
+  return (coarse == CFG_64x128) ? CFG_32x128 : CFG_32x64;
+}
+
 struct TaskSink {
   Plan& p;
   size_t begin;
@@ -270,6 +282,12 @@ struct TaskSink {
     } else if (cfg == CFG_128x64) {
       for (int hlf = 0; hlf < 2; ++hlf)
         p.tasks.push_back({a_row, a_k, b_row + 64 * hlf, b_k, nk, c_row, c_col + 64 * hlf, aux});
+    } else if (cfg == CFG_32x128) {
+      for (int q = 0; q < 4; ++q) p.tasks.push_back({a_row + 32 * q, a_k, b_row, b_k, nk, c_row + 32 * q, c_col, aux});
+    } else if (cfg == CFG_32x64) {
+      for (int q = 0; q < 4; ++q)
+        for (int hlf = 0; hlf < 2; ++hlf)
+          p.tasks.push_back({a_row + 32 * q, a_k, b_row + 64 * hlf, b_k, nk, c_row + 32 * q, c_col + 64 * hlf, aux});
     } else {
       for (int hlf = 0; hlf < 2; ++hlf)
         p.tasks.push_back({a_row + 64 * hlf, a_k, b_row, b_k, nk, c_row + 64 * hlf, c_col, aux});
@@ -319,15 +337,19 @@ void build_potrf_plan(Workspace& w) {
       p.launches.push_back(dg);
       {  // panel solve: L_ik = A_ik W_kk^T, in place (64-row tiles own all the columns they read)
         TaskSink s(p);
-        for (int i = k + 1; i <= aug; ++i) s.block(CFG_64x128, i * 128, k * 128, k * 128, 0, 8, i * 128, k * 128);
-        s.finish(CFG_64x128, EPI_STORE, M_L, M_DINV, M_L, M_NONE, 1.0, 0.0, false);
+        const int tc = cfg_for_blocks(CFG_64x128, aug - k);
+        for (int i = k + 1; i <= aug; ++i) s.block(tc, i * 128, k * 128, k * 128, 0, 8, i * 128, k * 128);
+        s.finish(tc, EPI_STORE, M_L, M_DINV, M_L, M_NONE, 1.0, 0.0, false);
         if (s.last >= 0) p.launches[s.last].stream = ps;
       }
       {  // update the remaining columns of the current outer panel with block column k
         TaskSink s(p);
+        int nblk = 0;
+        for (int j = k + 1; j < Je; ++j) nblk += aug - j + 1;
+        const int uc = cfg_for_blocks(cfg, nblk);
         for (int j = k + 1; j < Je; ++j)
-          for (int i = j; i <= aug; ++i) s.block(cfg, i * 128, k * 128, j * 128, k * 128, 8, i * 128, j * 128);
-        s.finish(cfg, EPI_STORE, M_L, M_L, M_L, M_NONE, -1.0, 1.0, false);
+          for (int i = j; i <= aug; ++i) s.block(uc, i * 128, k * 128, j * 128, k * 128, 8, i * 128, j * 128);
+        s.finish(uc, EPI_STORE, M_L, M_L, M_L, M_NONE, -1.0, 1.0, false);
         if (s.last >= 0) p.launches[s.last].stream = ps;
       }
     }
@@ -337,9 +359,12 @@ void build_potrf_plan(Workspace& w) {
   auto emit_update = [&](int J, int jb0, int jb1, int stream, int wait_ev, int rec_ev) {
     const int J0 = J * OB, Je = std::min(J0 + OB, Nb);
     TaskSink s(p);
+    int nblk = 0;
+    for (int j = jb0; j < jb1; ++j) nblk += aug - j + 1;
+    const int uc = cfg_for_blocks(cfg, nblk);
     for (int j = jb0; j < jb1; ++j)
-      for (int i = j; i <= aug; ++i) s.block(cfg, i * 128, J0 * 128, j * 128, J0 * 128, 8 * (Je - J0), i * 128, j * 128);
-    s.finish(cfg, EPI_STORE, M_L, M_L, M_L, M_NONE, -1.0, 1.0, false);
+      for (int i = j; i <= aug; ++i) s.block(uc, i * 128, J0 * 128, j * 128, J0 * 128, 8 * (Je - J0), i * 128, j * 128);
+    s.finish(uc, EPI_STORE, M_L, M_L, M_L, M_NONE, -1.0, 1.0, false);
     if (s.last >= 0) {
       p.launches[s.last].stream = stream;
       p.launches[s.last].wait_ev = wait_ev;
@@ -385,14 +410,18 @@ void build_trtri_plan(Workspace& w) {
   std::vector<Node> nodes;
   const int top = build_nodes(0, Nb, nodes);
   for (int hgt = 1; hgt <= top; ++hgt) {
+    int nblk = 0;
+    for (const Node& nd : nodes)
+      if (nd.height == hgt) nblk += (nd.mid - nd.a) * (nd.b - nd.mid);
+    const int hc = cfg_for_blocks(cfg, nblk);
     {  // T = U11 L21^T  -> scratch in the strict upper triangle of Lbuf
       TaskSink s(p);
       for (const Node& nd : nodes)
         if (nd.height == hgt)
           for (int m = nd.a; m < nd.mid; ++m)
             for (int n = nd.mid; n < nd.b; ++n)
-              s.block(cfg, m * 128, m * 128, n * 128, m * 128, 8 * (nd.mid - m), m * 128, n * 128);
-      s.finish(cfg, EPI_STORE, M_U, M_L, M_L, M_NONE, 1.0, 0.0, true);
+              s.block(hc, m * 128, m * 128, n * 128, m * 128, 8 * (nd.mid - m), m * 128, n * 128);
+      s.finish(hc, EPI_STORE, M_U, M_L, M_L, M_NONE, 1.0, 0.0, true);
     }
     {  // U12 = -T W22^T, mirrored into W21
       TaskSink s(p);
@@ -400,8 +429,8 @@ void build_trtri_plan(Workspace& w) {
         if (nd.height == hgt)
           for (int m = nd.a; m < nd.mid; ++m)
             for (int n = nd.mid; n < nd.b; ++n)
-              s.block(cfg, m * 128, nd.mid * 128, n * 128, nd.mid * 128, 8 * (n - nd.mid + 1), m * 128, n * 128);
-      s.finish(cfg, EPI_STORE, M_L, M_W, M_U, M_W, -1.0, 0.0, true);
+              s.block(hc, m * 128, nd.mid * 128, n * 128, nd.mid * 128, 8 * (n - nd.mid + 1), m * 128, n * 128);
+      s.finish(hc, EPI_STORE, M_L, M_W, M_U, M_W, -1.0, 0.0, true);
     }
   }
 }
@@ -409,7 +438,7 @@ void build_trtri_plan(Workspace& w) {
 void build_syrk_plan(Workspace& w) {
   Plan& p = w.syrk;
   p.clear();
-  const int Nb = (int)w.Nb, cfg = g_cfg_update;
+  const int Nb = (int)w.Nb, cfg = cfg_for_blocks(g_cfg_update, (int)(w.Nb * (w.Nb + 1) / 2));
   TaskSink s(p);
   for (int i = 0; i < Nb; ++i)
     for (int j = 0; j <= i; ++j) s.block(cfg, i * 128, i * 128, j * 128, i * 128, 8 * (Nb - i), i * 128, j * 128);
@@ -949,6 +978,7 @@ int gpb_create(int device, gpb_handle_t* out) {
   if (const char* e = getenv("GPB_CFG_UPDATE")) g_cfg_update = std::max(0, std::min(1, atoi(e)));
   if (const char* e = getenv("GPB_OUTER_BLOCKS")) g_outer_blocks = std::max(0, std::min(16, atoi(e)));
   if (const char* e = getenv("GPB_LOOKAHEAD")) g_lookahead = atoi(e) != 0;
+  if (const char* e = getenv("GPB_FINE_BELOW")) g_fine_below = atoi(e);
   *out = h;
   return 0;
 }
