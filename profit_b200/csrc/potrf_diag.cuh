@@ -22,30 +22,32 @@
 namespace gpb {
 
 constexpr int NB = 128;            // block size of the tile algorithms
-constexpr int DIAG_THREADS = 256;
+constexpr int DIAG_RB = 8;                       // rows per register sub-block; the CTA has 32 * DIAG_RB threads
+constexpr int DIAG_NA = NB / DIAG_RB;           // register row blocks per thread
+constexpr int DIAG_THREADS = 32 * DIAG_RB;
 constexpr int DIAG_TRI = NB * (NB + 1) / 2;                       // 8256 packed entries
 constexpr int DIAG_SMEM = (2 * DIAG_TRI + 2 * NB) * (int)sizeof(double);
 
-__host__ __device__ constexpr bool diag_owned(int a, int b) { return 32 * b <= 8 * a + 7; }
+__host__ __device__ constexpr bool diag_owned(int a, int b) { return 32 * b <= DIAG_RB * a + DIAG_RB - 1; }
 __device__ __forceinline__ int diag_colbase(int j) { return NB * j - (j * (j - 1)) / 2; }   // column j, rows j..127
 __device__ __forceinline__ int diag_rowbase(int j) { return (j * (j + 1)) / 2; }            // row j, cols 0..j
 
 // Eight consecutive column steps j = 8*JA .. 8*JA+7.  Everything that depends on j/8 (which register sub-blocks are
 // live, which are masked) is a compile-time property of the instantiation, so the step body is straight-line code.
 template <int JA, bool FACTOR>
-__device__ __forceinline__ void diag_block8(double (&av)[16][4], double (&rv)[16][4], double* ccomp, double* rcomp,
+__device__ __forceinline__ void diag_block8(double (&av)[DIAG_NA][4], double (&rv)[DIAG_NA][4], double* ccomp, double* rcomp,
                                             double* dvec, int ty, int tx, int tid, int k0, int n_valid, int* info) {
-  constexpr int JB = JA / 4;
+  constexpr int JB = JA * DIAG_RB / 32;
 #pragma unroll 1
-  for (int jj = 0; jj < 8; ++jj) {
-    const int j = 8 * JA + jj;
+  for (int jj = 0; jj < DIAG_RB; ++jj) {
+    const int j = DIAG_RB * JA + jj;
     double* col = ccomp + diag_colbase(j) - j;   // col[i] = c_ij for i >= j (reads below j stay inside the store)
     double* row = rcomp + diag_rowbase(j);       // row[m] = r_jm for m <= j
     // ---- publish the now-final column j of A and row j of R
     if (tx == (j & 31)) {
-      if (ty >= jj) col[8 * JA + ty] = av[JA][JB];
+      if (ty >= jj) col[DIAG_RB * JA + ty] = av[JA][JB];
 #pragma unroll
-      for (int a = JA + 1; a < 16; ++a) col[8 * a + ty] = av[a][JB];
+      for (int a = JA + 1; a < DIAG_NA; ++a) col[DIAG_RB * a + ty] = av[a][JB];
     }
     if (ty == jj) {
 #pragma unroll
@@ -68,14 +70,14 @@ __device__ __forceinline__ void diag_block8(double (&av)[16][4], double (&rv)[16
     }
     rk[JB] = (32 * JB + tx <= j) ? row[32 * JB + tx] : 0.0;
 #pragma unroll
-    for (int a0 = JA; a0 < 16; a0 += 4) {
+    for (int a0 = JA; a0 < DIAG_NA; a0 += 4) {
       double ci[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u)
-        if (a0 + u < 16) ci[u] = col[8 * (a0 + u) + ty] * invd;
+        if (a0 + u < DIAG_NA) ci[u] = col[DIAG_RB * (a0 + u) + ty] * invd;
 #pragma unroll
       for (int u = 0; u < 4; ++u)
-        if (a0 + u < 16) {
+        if (a0 + u < DIAG_NA) {
 #pragma unroll
           for (int b = 0; b < 4; ++b)
             if (diag_owned(a0 + u, b)) {
@@ -109,27 +111,28 @@ potrf_diag_kernel(double* __restrict__ A, long long lda, int k0_first, double* _
   const int tid = threadIdx.x, ty = tid >> 5, tx = tid & 31;
   double* Ablk = A + (long long)k0 * lda + k0;
 
-  double av[16][4], rv[16][4];
+  double av[DIAG_NA][4], rv[DIAG_NA][4];
 #pragma unroll
-  for (int a = 0; a < 16; ++a)
+  for (int a = 0; a < DIAG_NA; ++a)
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
       av[a][b] = rv[a][b] = 0.0;
       if (diag_owned(a, b)) {
-        const int i = 8 * a + ty, k = 32 * b + tx;
+        const int i = DIAG_RB * a + ty, k = 32 * b + tx;
         if (k <= i) av[a][b] = Ablk[(long long)i * lda + k];
         if (k == i) rv[a][b] = 1.0;
       }
     }
 
-#define GPB_DIAG_BLK(JA) diag_block8<JA, FACTOR>(av, rv, ccomp, rcomp, dvec, ty, tx, tid, k0, n_valid, info);
+#define GPB_DIAG_BLK(JA) \
+  if constexpr (JA < DIAG_NA) diag_block8<JA, FACTOR>(av, rv, ccomp, rcomp, dvec, ty, tx, tid, k0, n_valid, info);
   GPB_DIAG_BLK(0) GPB_DIAG_BLK(1) GPB_DIAG_BLK(2) GPB_DIAG_BLK(3) GPB_DIAG_BLK(4) GPB_DIAG_BLK(5) GPB_DIAG_BLK(6)
   GPB_DIAG_BLK(7) GPB_DIAG_BLK(8) GPB_DIAG_BLK(9) GPB_DIAG_BLK(10) GPB_DIAG_BLK(11) GPB_DIAG_BLK(12)
   GPB_DIAG_BLK(13) GPB_DIAG_BLK(14) GPB_DIAG_BLK(15)
 #undef GPB_DIAG_BLK
   __syncthreads();
   if (tid < NB) rsv[tid] = FACTOR ? 1.0 / sqrt(dvec[tid]) : 1.0 / dvec[tid];
-  if (logdet != nullptr && tid >= 128 && tid < 160) {
+  if (logdet != nullptr && tid >= 128 && tid < 160) {  // warp 4 (exists for every DIAG_RB >= 8)
     const int lane = tid - 128;
     double s = 0.0;
     for (int q = 0; q < 4; ++q) {
@@ -141,10 +144,10 @@ potrf_diag_kernel(double* __restrict__ A, long long lda, int k0_first, double* _
   }
   __syncthreads();
 
-  for (int a = 0; a < 16; ++a)
+  for (int a = 0; a < DIAG_NA; ++a)
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
-      const int i = 8 * a + ty, k = 32 * b + tx;
+      const int i = DIAG_RB * a + ty, k = 32 * b + tx;
       double l = 0.0, w = 0.0;
       if (k < i) l = ccomp[diag_colbase(k) + i - k] * rsv[k];
       else if (k == i) l = sqrt(dvec[i]);
