@@ -101,19 +101,31 @@ def acquisition_argmax(backend, Xpred, add_data_variance=True, mask=None):
     return gather_argmax(-np.inf, -1)
 
 
-def multistart_optimize(xtrain, ytrain, starts, kernel, fixed_sigma_n=False, eval_gradient=True, backend=None):
+def multistart_optimize(xtrain, ytrain, starts, kernel, fixed_sigma_n=False, eval_gradient=True, backend=None,
+                        streams=1):
     """Run ``gp_functions.optimize`` from every start in ``starts`` (R, P), restarts sharded r -> rank r mod G.
+
+    ``streams`` > 1 runs that many restarts of this rank concurrently, each on its own device handle and stream
+    (host threads; the C calls release the GIL).  One evaluation cannot fill the GPU while its Cholesky walks the
+    panel chain, so independent restarts overlap: measured on B200 +2 % at N=16384, +13 % at N=8192, +47 % at
+    N=4096 with two streams (tools/concurrent_restarts.py).
 
     Returns (best_theta, best_nll, table) where table has one row per restart: [restart, nll, theta...].
     """
+    import threading
+
     from . import gp_functions as gpf
-    from .backend import shared_backend
+    from .backend import GPBackend, shared_backend
 
     rank, ws = world()
-    be = backend or shared_backend()
     starts = np.atleast_2d(np.asarray(starts, dtype=np.float64))
-    rows = []
-    for r in range(rank, starts.shape[0], ws):
+    mine = list(range(rank, starts.shape[0], ws))
+    streams = max(1, min(int(streams), len(mine) or 1))
+    first = backend or shared_backend()
+    backends = [first] + [GPBackend(first.device) for _ in range(streams - 1)]
+    rows, lock = [], threading.Lock()
+
+    def one(r, be):
         try:
             theta = gpf.optimize(xtrain, ytrain, starts[r], kernel, fixed_sigma_n=fixed_sigma_n,
                                  eval_gradient=eval_gradient, backend=be)
@@ -121,8 +133,24 @@ def multistart_optimize(xtrain, ytrain, starts, kernel, fixed_sigma_n=False, eva
             nll = gpf.negative_log_likelihood_cholesky(full, xtrain, ytrain, kernel, backend=be)
         except np.linalg.LinAlgError:
             theta, nll = starts[r][:-1] if fixed_sigma_n else starts[r], np.inf
-        rows.append(np.concatenate([[r, nll], theta]))
+        with lock:
+            rows.append(np.concatenate([[r, nll], theta]))
+
+    def worker(k):
+        for r in mine[k::streams]:
+            one(r, backends[k])
+
+    if streams == 1:
+        worker(0)
+    else:
+        threads = [threading.Thread(target=worker, args=(k,)) for k in range(streams)]
+        for th in threads:
+            th.start()
+        for th in threads:
+            th.join()
+        for be in backends[1:]:
+            be.close()
     width = 2 + (starts.shape[1] - (1 if fixed_sigma_n else 0))
-    local = np.array(rows) if rows else np.empty((0, width))
+    local = np.array(sorted(rows, key=lambda row: row[0])) if rows else np.empty((0, width))
     best, table = gather_argmin_rows(local) if len(local) or ws > 1 else (None, local)
     return best[2:], float(best[1]), table

@@ -377,6 +377,8 @@ def test_acquisition_argmax_and_multistart_single_rank(backend):
     starts = theta * 10 ** (np.array([[0.0], [0.3], [-0.3]]) * np.ones((3, theta.size)))
     best, best_nll, table = multistart_optimize(X, y, starts, RBF, eval_gradient=True, backend=backend)
     assert table.shape == (3, 2 + theta.size) and np.isfinite(best_nll)
+    best2, best_nll2, table2 = multistart_optimize(X, y, starts, RBF, eval_gradient=True, backend=backend, streams=2)
+    assert np.allclose(table2, table, rtol=1e-9) and best_nll2 == best_nll     # concurrency does not change results
     single = gpf.optimize(X, y, theta, RBF, eval_gradient=True, backend=backend)
     assert best_nll <= oracle.nll_cholesky(single, X, y, oracle.rbf) + 1e-6
     assert abs(best_nll - oracle.nll_cholesky(best, X, y, oracle.rbf)) <= 1e-8 * abs(best_nll)
@@ -532,3 +534,29 @@ def test_ill_conditioned_variance_vs_extended_precision(backend):
     cond = np.linalg.cond(oracle.rbf(X, X, ell, sf, sn))
     print(f"cond(K) = {cond:.2e}: |gpu - truth| = {err_gpu:.2e}, |reference formula - truth| = {err_ref:.2e}")
     assert err_gpu <= 1e-10 and err_gpu <= err_ref
+
+
+def test_argument_errors_are_reported_not_crashed(backend):
+    """Status codes of the C ABI surface as the reference's exception types (include/gpb.h conventions)."""
+    from profit_b200 import GPBackend, RBF
+
+    X = np.random.default_rng(0).random((20, 3))
+    y = X[:, 0]
+    with pytest.raises(ValueError):
+        backend.set_train(np.random.default_rng(0).random((20, 40)), y)      # D > 32
+    with pytest.raises(ValueError):
+        backend.set_train(X, np.zeros((20, 200)))                             # n_out > 128
+    with pytest.raises(ValueError):
+        backend.set_train(X, np.zeros(19))                                    # mismatched rows
+    backend.set_train(X, y)
+    with pytest.raises(ValueError):
+        backend.nll(0, np.array([1.0, 1.0, 1.0, 0.1]))                        # n_ell = 2 is neither 1 nor D = 3
+    with pytest.raises(ValueError):
+        backend.nll(7, np.array([1.0, 1.0, 0.1]))                             # unknown kernel kind
+    with pytest.raises(ValueError):
+        RBF(X, X, np.array([1.0, 2.0]), 1.0, 0.0)                             # length_scale of the wrong size
+    fresh = GPBackend(0)
+    with pytest.raises(RuntimeError):
+        fresh.nll(0, np.array([1.0, 1.0, 0.1]))                               # no training set yet
+    fresh.close()
+    assert backend.nll(0, np.array([1.0, 1.0, 0.1])) == backend.nll(0, np.array([1.0, 1.0, 0.1]))
