@@ -73,6 +73,10 @@ dgemm_tasks_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     mbar_init_fence();
   }
   __syncthreads();
+  // Small (single-wave) launches sit on the Cholesky's panel chain: let the next kernel's CTAs come up while this
+  // one runs.  Everything above is independent of the previous kernel; everything below may read its output.
+  if (gridDim.x <= 296) pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == NCW) {
     // ---------------- TMA producer ----------------

@@ -47,6 +47,7 @@ struct Launch {
   int stream = 0;    // 0 = main stream, 1 = panel (look-ahead) stream
   int wait_ev = -1;  // event to wait for before the launch (index into the handle's event pool)
   int rec_ev = -1;   // event recorded after the launch
+  int pdl = 0;       // launch with programmatic stream serialization (overlaps the launch with the previous kernel)
 };
 
 struct Plan {
@@ -206,7 +207,7 @@ void set_mat(Workspace& w, int id, double* p, long long rows, long long cols, lo
 // ------------------------------------------------------------------------------------------------ GEMM launch
 template <int BM, int BN, int WM, int WN, int ST, int EPI, int MINB>
 int launch_cfg(H* h, cudaStream_t stream, const CUtensorMap& tA, const CUtensorMap& tB, const GemmTask* tasks,
-               int ntasks, const GemmEpilogue& ep) {
+               int ntasks, const GemmEpilogue& ep, bool pdl) {
   auto kern = dgemm_tasks_kernel<BM, BN, WM, WN, ST, EPI, MINB>;
   constexpr int smem = GemmSmem<BM, BN, ST>::BYTES;
   static bool configured = false;
@@ -215,7 +216,21 @@ int launch_cfg(H* h, cudaStream_t stream, const CUtensorMap& tA, const CUtensorM
     configured = true;
   }
   constexpr int threads = (BM / WM) * (BN / WN) * 32 + 32;
-  kern<<<ntasks, threads, smem, stream>>>(tA, tB, tasks, ep);
+  if (pdl) {
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3((unsigned)ntasks);
+    lc.blockDim = dim3((unsigned)threads);
+    lc.dynamicSmemBytes = smem;
+    lc.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at;
+    lc.numAttrs = 1;
+    CK(cudaLaunchKernelEx(&lc, kern, tA, tB, tasks, ep));
+  } else {
+    kern<<<ntasks, threads, smem, stream>>>(tA, tB, tasks, ep);
+  }
   h->launches++;
   CK(cudaGetLastError());
   return 0;
@@ -232,7 +247,7 @@ void cfg_tile(int cfg, int* bm, int* bn) {
 }
 
 int launch_gemm(H* h, Workspace& w, int cfg, int epi, int matA, int matB, const GemmTask* d_tasks, int ntasks,
-                const GemmEpilogue& ep, cudaStream_t stream = nullptr) {
+                const GemmEpilogue& ep, cudaStream_t stream = nullptr, bool pdl = false) {
   if (!stream) stream = h->stream;
   if (ntasks <= 0) return 0;
   int bm, bn;
@@ -243,16 +258,16 @@ int launch_gemm(H* h, Workspace& w, int cfg, int epi, int matA, int matB, const 
   if ((rc = get_map(h, w, matB, bn, &tB))) return rc;
   if (epi == EPI_STORE) {
     switch (cfg) {
-      case CFG_128x128: return launch_cfg<128, 128, 64, 32, 4, EPI_STORE, 1>(h, stream, tA, tB, d_tasks, ntasks, ep);
-      case CFG_128x64: return launch_cfg<128, 64, 32, 32, 4, EPI_STORE, 2>(h, stream, tA, tB, d_tasks, ntasks, ep);
-      case CFG_32x128: return launch_cfg<32, 128, 16, 32, 4, EPI_STORE, 2>(h, stream, tA, tB, d_tasks, ntasks, ep);
-      case CFG_32x64: return launch_cfg<32, 64, 16, 16, 4, EPI_STORE, 2>(h, stream, tA, tB, d_tasks, ntasks, ep);
-      default: return launch_cfg<64, 128, 32, 32, 4, EPI_STORE, 2>(h, stream, tA, tB, d_tasks, ntasks, ep);
+      case CFG_128x128: return launch_cfg<128, 128, 64, 32, 4, EPI_STORE, 1>(h, stream, tA, tB, d_tasks, ntasks, ep, pdl);
+      case CFG_128x64: return launch_cfg<128, 64, 32, 32, 4, EPI_STORE, 2>(h, stream, tA, tB, d_tasks, ntasks, ep, pdl);
+      case CFG_32x128: return launch_cfg<32, 128, 16, 32, 4, EPI_STORE, 2>(h, stream, tA, tB, d_tasks, ntasks, ep, pdl);
+      case CFG_32x64: return launch_cfg<32, 64, 16, 16, 4, EPI_STORE, 2>(h, stream, tA, tB, d_tasks, ntasks, ep, pdl);
+      default: return launch_cfg<64, 128, 32, 32, 4, EPI_STORE, 2>(h, stream, tA, tB, d_tasks, ntasks, ep, pdl);
     }
   } else {
     switch (cfg) {
-      case CFG_128x128: return launch_cfg<128, 128, 64, 32, 4, EPI_COLSQ, 1>(h, stream, tA, tB, d_tasks, ntasks, ep);
-      case CFG_128x64: return launch_cfg<128, 64, 32, 32, 4, EPI_COLSQ, 2>(h, stream, tA, tB, d_tasks, ntasks, ep);
+      case CFG_128x128: return launch_cfg<128, 128, 64, 32, 4, EPI_COLSQ, 1>(h, stream, tA, tB, d_tasks, ntasks, ep, pdl);
+      case CFG_128x64: return launch_cfg<128, 64, 32, 32, 4, EPI_COLSQ, 2>(h, stream, tA, tB, d_tasks, ntasks, ep, pdl);
       default: return fail(h, -1, "no column-norm epilogue for this tile configuration");
     }
   }
@@ -261,6 +276,7 @@ int launch_gemm(H* h, Workspace& w, int cfg, int epi, int matA, int matB, const 
 // ------------------------------------------------------------------------------------------------ plans
 int g_cfg_update = CFG_128x64;  // trailing updates / trtri / syrk / predict   (env GPB_CFG_UPDATE)
 int g_outer_blocks = 0;         // outer panel width of the Cholesky in 128-blocks; 0 = by size (env GPB_OUTER_BLOCKS)
+int g_pdl = 1;                  // programmatic dependent launch along the panel chain (env GPB_PDL)
 int g_lookahead = 1;            // overlap the next panel factorisation with the trailing update (env GPB_LOOKAHEAD)
 
 // Small launches are latency-bound (one CTA takes ~15 us for a 128x64x128 tile on its own SM): cut the tiles finer
@@ -329,18 +345,25 @@ void build_potrf_plan(Workspace& w) {
   auto evM = [&](int J) { return nJ + J; };
   p.num_events = la ? 2 * nJ : 0;
 
+  // Programmatic dependent launch pays off only while the chain is the bottleneck (measured: potrf N=4096
+  // 2.50 -> 2.39 ms, but N=8192 8.30 -> 8.60 ms: early-resident dependents then take SMs from the updates).
+  const int pdl = (Nb <= 40) ? 1 : 0;
   auto emit_panel = [&](int J) {
     const int J0 = J * OB, Je = std::min(J0 + OB, Nb);
     for (int k = J0; k < Je; ++k) {
       Launch dg{0, k, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
       dg.stream = ps;
+      dg.pdl = pdl;
       p.launches.push_back(dg);
       {  // panel solve: L_ik = A_ik W_kk^T, in place (64-row tiles own all the columns they read)
         TaskSink s(p);
         const int tc = cfg_for_blocks(CFG_64x128, aug - k);
         for (int i = k + 1; i <= aug; ++i) s.block(tc, i * 128, k * 128, k * 128, 0, 8, i * 128, k * 128);
         s.finish(tc, EPI_STORE, M_L, M_DINV, M_L, M_NONE, 1.0, 0.0, false);
-        if (s.last >= 0) p.launches[s.last].stream = ps;
+        if (s.last >= 0) {
+          p.launches[s.last].stream = ps;
+          p.launches[s.last].pdl = pdl;
+        }
       }
       {  // update the remaining columns of the current outer panel with block column k
         TaskSink s(p);
@@ -350,7 +373,10 @@ void build_potrf_plan(Workspace& w) {
         for (int j = k + 1; j < Je; ++j)
           for (int i = j; i <= aug; ++i) s.block(uc, i * 128, k * 128, j * 128, k * 128, 8, i * 128, j * 128);
         s.finish(uc, EPI_STORE, M_L, M_L, M_L, M_NONE, -1.0, 1.0, false);
-        if (s.last >= 0) p.launches[s.last].stream = ps;
+        if (s.last >= 0) {
+          p.launches[s.last].stream = ps;
+          p.launches[s.last].pdl = pdl;
+        }
       }
     }
     if (la) p.launches.back().rec_ev = evP(J);
@@ -473,7 +499,20 @@ int run_plan(H* h, Workspace& w, Plan& p, bool factor_diag) {
     cudaStream_t st = (multi && L.stream == 1) ? h->stream2 : h->stream;
     if (multi && L.wait_ev >= 0) CK(cudaStreamWaitEvent(st, h->events[L.wait_ev], 0));
     if (L.type == 0) {
-      if (factor_diag)
+      if (factor_diag && L.pdl && g_pdl) {
+        cudaLaunchConfig_t lc{};
+        lc.gridDim = dim3(1);
+        lc.blockDim = dim3(DIAG_THREADS);
+        lc.dynamicSmemBytes = DIAG_SMEM;
+        lc.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        lc.attrs = at;
+        lc.numAttrs = 1;
+        CK(cudaLaunchKernelEx(&lc, potrf_diag_kernel<true>, w.Lbuf, (long long)w.Np, L.k * 128,
+                              w.Dinv + (long long)L.k * 128 * 128, w.logdet + L.k, h->dinfo, (int)w.N));
+      } else if (factor_diag)
         potrf_diag_kernel<true><<<1, DIAG_THREADS, DIAG_SMEM, st>>>(
             w.Lbuf, w.Np, L.k * 128, w.Dinv + (long long)L.k * 128 * 128, w.logdet + L.k, h->dinfo, (int)w.N);
       else
@@ -489,7 +528,8 @@ int run_plan(H* h, Workspace& w, Plan& p, bool factor_diag) {
       ep.ldct = (L.matCt == M_NONE) ? 0 : w.mat[L.matCt].ld;
       ep.alpha = L.alpha;
       ep.beta = L.beta;
-      int rc = launch_gemm(h, w, L.cfg, L.epi, L.matA, L.matB, p.d_tasks + L.task_off, L.ntasks, ep, st);
+      int rc = launch_gemm(h, w, L.cfg, L.epi, L.matA, L.matB, p.d_tasks + L.task_off, L.ntasks, ep, st,
+                           L.pdl && g_pdl && !(multi && L.wait_ev >= 0));
       if (rc) return rc;
     }
     if (multi && L.rec_ev >= 0) CK(cudaEventRecord(h->events[L.rec_ev], st));
@@ -979,6 +1019,7 @@ int gpb_create(int device, gpb_handle_t* out) {
   if (const char* e = getenv("GPB_OUTER_BLOCKS")) g_outer_blocks = std::max(0, std::min(16, atoi(e)));
   if (const char* e = getenv("GPB_LOOKAHEAD")) g_lookahead = atoi(e) != 0;
   if (const char* e = getenv("GPB_FINE_BELOW")) g_fine_below = atoi(e);
+  if (const char* e = getenv("GPB_PDL")) g_pdl = atoi(e) != 0;
   *out = h;
   return 0;
 }

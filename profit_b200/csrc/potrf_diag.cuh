@@ -19,6 +19,8 @@
 #include <cuda_runtime.h>
 #include <math.h>
 
+#include "ptx.cuh"
+
 namespace gpb {
 
 constexpr int NB = 128;            // block size of the tile algorithms
@@ -110,6 +112,8 @@ potrf_diag_kernel(double* __restrict__ A, long long lda, int k0_first, double* _
   double* rsv = dvec + NB;               // 1/sqrt(d_j)  (FACTOR)  or  1/L_jj
   const int tid = threadIdx.x, ty = tid >> 5, tx = tid & 31;
   double* Ablk = A + (long long)k0 * lda + k0;
+  pdl_launch_dependents();   // the panel solve that follows may start its prologue now
+  pdl_wait();                // ... and this block reads what the previous update wrote
 
   double av[DIAG_NA][4], rv[DIAG_NA][4];
 #pragma unroll
