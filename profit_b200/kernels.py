@@ -41,10 +41,27 @@ def Matern52(X, Y, length_scale=1, sigma_f=1, sigma_n=0, eval_gradient=False):
     return _evaluate(KIND_MATERN52, X, Y, length_scale, sigma_f, sigma_n, eval_gradient)
 
 
+def LinearEmbedding(X, Y, R, sigma_f=1e-6, sigma_n=0, eval_gradient=False):
+    r"""Linear-embedding kernel of Garnett (2014), python_kernels.py:60-114:
+    K = sf^2 exp(-1/2 (x-y)^T R^T R (x-y)) + sn^2 I, i.e. the squared-exponential kernel with unit length scale on the
+    projected inputs X R^T.  ``R`` is a (d, D) matrix or its flattening.
+
+    Only the kernel matrix is provided: the reference's derivative w.r.t. R (:108-110) is marked "TODO: check"
+    upstream and only has consistent shapes for d = 1, so there is nothing to be faithful to.
+    """
+    if eval_gradient:
+        raise NotImplementedError("dK/dR of LinearEmbedding is unverified upstream (python_kernels.py:106) and not provided")
+    X = np.atleast_2d(np.asarray(X, dtype=np.float64))
+    R = np.asarray(R, dtype=np.float64)
+    R = R.reshape(R.size // X.shape[-1], X.shape[-1])
+    Yp = X if Y is None else np.atleast_2d(np.asarray(Y, dtype=np.float64))
+    return _evaluate(KIND_RBF, X @ R.T, Yp @ R.T, 1.0, sigma_f, sigma_n, False)
+
+
 RBF.gpb_kind = KIND_RBF
 Matern52.gpb_kind = KIND_MATERN52
 
-_BY_NAME = {"RBF": RBF, "Matern52": Matern52, "Matern5/2": Matern52}
+_BY_NAME = {"RBF": RBF, "Matern52": Matern52, "Matern5/2": Matern52}   # kernels the NLL / predict paths run on device
 
 
 def select_kernel(kernel):

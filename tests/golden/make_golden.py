@@ -132,6 +132,14 @@ out["bbq"] = {"N": 80, "D": 2, "M": 37, "seed": 3, "hyp": [0.7, 1.5, 0.3], "hess
                                                        predictive_variance=pvb).ravel()),
               "note": "gp_functions.marginal_variance_BBQ, scalar length scale"}
 
+# ---- LinearEmbedding kernel matrix (python_kernels.py:60-105; its gradient is unverified upstream) ---------
+from profit.sur.gp.backend.python_kernels import LinearEmbedding  # noqa: E402
+
+rngl = np.random.default_rng(4)
+Xl, Yl, Rl = rngl.random((23, 5)), rngl.random((17, 5)), rngl.standard_normal((2, 5))
+out["linear_embedding"] = {"seed": 4, "n": 23, "m": 17, "D": 5, "d": 2, "sigma_f": 1.3, "sigma_n": 0.2,
+                           "K": L(LinearEmbedding(Xl, Yl, Rl.ravel(), 1.3, 0.2))}
+
 path = os.path.join(ROOT, "tests", "golden", "reference_kats.json")
 with open(path, "w") as f:
     json.dump(out, f)

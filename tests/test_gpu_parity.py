@@ -560,3 +560,15 @@ def test_argument_errors_are_reported_not_crashed(backend):
         fresh.nll(0, np.array([1.0, 1.0, 0.1]))                               # no training set yet
     fresh.close()
     assert backend.nll(0, np.array([1.0, 1.0, 0.1])) == backend.nll(0, np.array([1.0, 1.0, 0.1]))
+
+
+def test_linear_embedding_kernel_matrix(backend, golden):
+    from profit_b200 import LinearEmbedding
+
+    c = golden["linear_embedding"]
+    rng = np.random.default_rng(c["seed"])
+    X, Y, R = rng.random((c["n"], c["D"])), rng.random((c["m"], c["D"])), rng.standard_normal((c["d"], c["D"]))
+    K = LinearEmbedding(X, Y, R.ravel(), c["sigma_f"], c["sigma_n"])
+    assert np.allclose(K, c["K"], rtol=1e-12, atol=1e-15)
+    with pytest.raises(NotImplementedError):
+        LinearEmbedding(X, Y, R, eval_gradient=True)
