@@ -210,10 +210,10 @@ int launch_cfg(H* h, cudaStream_t stream, const CUtensorMap& tA, const CUtensorM
                int ntasks, const GemmEpilogue& ep, bool pdl) {
   auto kern = dgemm_tasks_kernel<BM, BN, WM, WN, ST, EPI, MINB>;
   constexpr int smem = GemmSmem<BM, BN, ST>::BYTES;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {};   // the attribute is per device; one process may hold handles on several GPUs
+  if (!configured[h->device & 63]) {
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
+    configured[h->device & 63] = true;
   }
   constexpr int threads = (BM / WM) * (BN / WN) * 32 + 32;
   if (pdl) {
