@@ -572,3 +572,21 @@ def test_linear_embedding_kernel_matrix(backend, golden):
     assert np.allclose(K, c["K"], rtol=1e-12, atol=1e-15)
     with pytest.raises(NotImplementedError):
         LinearEmbedding(X, Y, R, eval_gradient=True)
+
+
+def test_objective_survives_a_singular_covariance(backend, capsys):
+    """gp_functions.negative_log_likelihood keeps the optimiser alive when the Cholesky factorisation fails
+    (the reference falls back to an eigen-decomposition, gp_functions.py:271-301; here: on-device jitter retry),
+    while negative_log_likelihood_cholesky itself raises like the reference's does."""
+    from profit_b200 import RBF, gp_functions as gpf
+
+    X = np.repeat(np.random.default_rng(0).random((10, 2)), 3, axis=0)      # every point three times
+    y = np.sin(X[:, 0])
+    hyp = np.array([0.5, 1.0, 0.0])                                          # no noise: exactly singular
+    with pytest.raises(np.linalg.LinAlgError):
+        gpf.negative_log_likelihood_cholesky(hyp, X, y, RBF, eval_gradient=True)
+    with np.errstate(divide="ignore"):
+        nll, g = gpf.negative_log_likelihood(np.log10(np.array([0.5, 1.0, 1e-12])), X, y, RBF, eval_gradient=True,
+                                             log_scale_hyp=True)
+    assert np.isfinite(nll) and np.all(np.isfinite(g)) and g.shape == (3,)
+    assert "retrying with diagonal jitter" in capsys.readouterr().out
