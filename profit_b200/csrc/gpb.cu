@@ -276,6 +276,7 @@ int launch_gemm(H* h, Workspace& w, int cfg, int epi, int matA, int matB, const 
 // ------------------------------------------------------------------------------------------------ plans
 int g_cfg_update = CFG_128x64;  // trailing updates / trtri / syrk / predict   (env GPB_CFG_UPDATE)
 int g_outer_blocks = 0;         // outer panel width of the Cholesky in 128-blocks; 0 = by size (env GPB_OUTER_BLOCKS)
+int g_diag4 = 1;                // rank-4 diagonal-block kernel (env GPB_DIAG4=0 selects the rank-1 one)
 int g_pdl = 1;                  // programmatic dependent launch along the panel chain (env GPB_PDL)
 int g_lookahead = 1;            // overlap the next panel factorisation with the trailing update (env GPB_LOOKAHEAD)
 
@@ -499,7 +500,20 @@ int run_plan(H* h, Workspace& w, Plan& p, bool factor_diag) {
     cudaStream_t st = (multi && L.stream == 1) ? h->stream2 : h->stream;
     if (multi && L.wait_ev >= 0) CK(cudaStreamWaitEvent(st, h->events[L.wait_ev], 0));
     if (L.type == 0) {
-      if (factor_diag && L.pdl && g_pdl) {
+      if (factor_diag && g_diag4) {
+        cudaLaunchConfig_t lc{};
+        lc.gridDim = dim3(1);
+        lc.blockDim = dim3(DIAG_THREADS);
+        lc.dynamicSmemBytes = DIAG4_SMEM;
+        lc.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        lc.attrs = at;
+        lc.numAttrs = (L.pdl && g_pdl) ? 1 : 0;
+        CK(cudaLaunchKernelEx(&lc, potrf_diag4_kernel, w.Lbuf, (long long)w.Np, L.k * 128,
+                              w.Dinv + (long long)L.k * 128 * 128, w.logdet + L.k, h->dinfo, (int)w.N));
+      } else if (factor_diag && L.pdl && g_pdl) {
         cudaLaunchConfig_t lc{};
         lc.gridDim = dim3(1);
         lc.blockDim = dim3(DIAG_THREADS);
@@ -1002,7 +1016,8 @@ int gpb_create(int device, gpb_handle_t* out) {
     return -2;
   }
   h->encode = reinterpret_cast<EncodeTiledFn>(fn);
-  if (cudaFuncSetAttribute(potrf_diag_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM) != cudaSuccess ||
+  if (cudaFuncSetAttribute(potrf_diag4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG4_SMEM) != cudaSuccess ||
+      cudaFuncSetAttribute(potrf_diag_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM) != cudaSuccess ||
       cudaFuncSetAttribute(potrf_diag_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM) != cudaSuccess) {
     delete h;
     return -2;
@@ -1020,6 +1035,7 @@ int gpb_create(int device, gpb_handle_t* out) {
   if (const char* e = getenv("GPB_LOOKAHEAD")) g_lookahead = atoi(e) != 0;
   if (const char* e = getenv("GPB_FINE_BELOW")) g_fine_below = atoi(e);
   if (const char* e = getenv("GPB_PDL")) g_pdl = atoi(e) != 0;
+  if (const char* e = getenv("GPB_DIAG4")) g_diag4 = atoi(e) != 0;
   *out = h;
   return 0;
 }
