@@ -278,6 +278,7 @@ int g_cfg_update = CFG_128x64;  // trailing updates / trtri / syrk / predict   (
 int g_outer_blocks = 0;         // outer panel width of the Cholesky in 128-blocks; 0 = by size (env GPB_OUTER_BLOCKS)
 int g_diag4 = 1;                // rank-4 diagonal-block kernel (env GPB_DIAG4=0 selects the rank-1 one)
 int g_pdl = 1;                  // programmatic dependent launch along the panel chain (env GPB_PDL)
+int g_tail_blocks = 32;         // the last this-many block columns use single-block panels (env GPB_TAIL_BLOCKS)
 int g_lookahead = 1;            // overlap the next panel factorisation with the trailing update (env GPB_LOOKAHEAD)
 
 // Small launches are latency-bound (one CTA takes ~15 us for a 128x64x128 tile on its own SM): cut the tiles finer
@@ -337,9 +338,16 @@ void build_potrf_plan(Workspace& w) {
   // matrices the factorisation is bound by the per-column-block chain and narrow panels shorten it
   // (measured: N=4096 potrf 3.15 / 3.02 / 2.84 ms with 4 / 2 / 1 blocks, N=16384 48.2 / 48.4 / 50.8 ms).
   const int Nb = (int)w.Nb, cfg = g_cfg_update;
-  const int OB = g_outer_blocks > 0 ? g_outer_blocks : (Nb <= 32 ? 1 : (Nb <= 64 ? 2 : 4));
   const int aug = Nb;  // block-row index of the y^T rows
-  const int nJ = (Nb + OB - 1) / OB;
+  // Panel boundaries: wide panels while the trailing matrix is large, single-block panels for the last
+  // g_tail_blocks block columns, where the factorisation is chain-bound anyway.
+  std::vector<int> pb{0};
+  while (pb.back() < Nb) {
+    const int left = Nb - pb.back();
+    int wdt = g_outer_blocks > 0 ? g_outer_blocks : (left > 64 ? 4 : (left > g_tail_blocks ? 2 : 1));
+    pb.push_back(std::min(Nb, pb.back() + wdt));
+  }
+  const int nJ = (int)pb.size() - 1;
   const bool la = g_lookahead != 0;
   const int ps = la ? 1 : 0;           // stream of the panel work
   auto evP = [&](int J) { return J; };
@@ -350,7 +358,7 @@ void build_potrf_plan(Workspace& w) {
   // 2.50 -> 2.39 ms, but N=8192 8.30 -> 8.60 ms: early-resident dependents then take SMs from the updates).
   const int pdl = (Nb <= 40) ? 1 : 0;
   auto emit_panel = [&](int J) {
-    const int J0 = J * OB, Je = std::min(J0 + OB, Nb);
+    const int J0 = pb[J], Je = pb[J + 1];
     for (int k = J0; k < Je; ++k) {
       Launch dg{0, k, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
       dg.stream = ps;
@@ -384,7 +392,7 @@ void build_potrf_plan(Workspace& w) {
   };
   // columns [jb0, jb1) (in 128-blocks) updated with panel J
   auto emit_update = [&](int J, int jb0, int jb1, int stream, int wait_ev, int rec_ev) {
-    const int J0 = J * OB, Je = std::min(J0 + OB, Nb);
+    const int J0 = pb[J], Je = pb[J + 1];
     TaskSink s(p);
     int nblk = 0;
     for (int j = jb0; j < jb1; ++j) nblk += aug - j + 1;
@@ -401,9 +409,8 @@ void build_potrf_plan(Workspace& w) {
   };
 
   emit_panel(0);
-  for (int J = 0; J < nJ; ++J) {
-    const int next0 = std::min((J + 1) * OB, Nb), next1 = std::min((J + 2) * OB, Nb);
-    if (next0 >= Nb) break;
+  for (int J = 0; J + 1 < nJ; ++J) {
+    const int next0 = pb[J + 1], next1 = pb[J + 2];
     if (la) {
       const bool has_t2 = next1 < Nb;
       // T2(J) first so that the big launch is queued early on the main stream
@@ -1035,6 +1042,7 @@ int gpb_create(int device, gpb_handle_t* out) {
   if (const char* e = getenv("GPB_LOOKAHEAD")) g_lookahead = atoi(e) != 0;
   if (const char* e = getenv("GPB_FINE_BELOW")) g_fine_below = atoi(e);
   if (const char* e = getenv("GPB_PDL")) g_pdl = atoi(e) != 0;
+  if (const char* e = getenv("GPB_TAIL_BLOCKS")) g_tail_blocks = std::max(0, atoi(e));
   if (const char* e = getenv("GPB_DIAG4")) g_diag4 = atoi(e) != 0;
   *out = h;
   return 0;
