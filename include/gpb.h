@@ -71,6 +71,46 @@ int gpb_predict(gpb_handle_t h, const double* Xc, long long M, int add_data_vari
 /* argmax with lowest-index tie-break, like np.argmax in aquisition_functions.py:68. v: (M). */
 int gpb_argmax(gpb_handle_t h, const double* v, long long M, long long* idx, double* val);
 
+/* Append m observed points to a factorised model without refactorising -- the in-place extension the reference
+ * leaves as a TODO in GPSurrogate.add_training_data (custom_surrogate.py:122-134, ":132 TODO: Update Ky").
+ * Per point O(N^2): l = L^-1 k(X, x), d^2 = sf^2 + sn^2 - |l|^2, new row of L^-1 is [-(L^-T l)^T/d, 1/d]; alpha, z and
+ * log|K| follow.  Afterwards gpb_predict / gpb_marginal_variance see N + m training points at the same theta.
+ * Returns N + 1 (LAPACK-style) when the extended matrix is not SPD; the model is then left unchanged for that
+ * point.  When the padded capacity is exhausted the library re-uploads and refactorises internally.
+ * Xnew: (m, d), ynew: (m, n_out). */
+int gpb_append_train(gpb_handle_t h, const double* Xnew, const double* ynew, long long m);
+
+/* Acquisition functions of profit/al/aquisition_functions.py evaluated on the device. */
+enum {
+  GPB_ACQ_VARIANCE = 0,         /* SimpleExploration.calculate_loss              (:107-119)  params: none            */
+  GPB_ACQ_DISTANCE_PENALTY = 1, /* ExplorationWithDistancePenalty.calculate_loss (:146-158)  [weight, d, last[d]]    */
+  GPB_ACQ_WEIGHTED = 2,         /* WeightedExploration.calculate_loss            (:183-198)  [weight]                */
+  GPB_ACQ_POI = 3,              /* ProbabilityOfImprovement.calculate_loss       (:212-220)  [ymax[n_out]]           */
+  GPB_ACQ_EI = 4,               /* ExpectedImprovement.calculate_loss/sigma_part (:253-276)  none                    */
+  GPB_ACQ_EI2 = 5               /* ExpectedImprovement2.calculate_loss           (:303-315)  [xi, find_min, ymax[]]  */
+};
+
+/* The once-per-batch transform of the predictive mean (M, n_out) -> out (M, n_out):
+ *   GPB_ACQ_WEIGHTED: AcquisitionFunction.normalize(mu) column-wise (:76-84, :200-201); no params.
+ *   GPB_ACQ_EI:       ExpectedImprovement.mu_part (:262-269), params = [xi, find_min, ymax[n_out]]:
+ *                     normalize(max(+-mu - ymax, 0)) - xi.
+ * n_out <= 16.  out may alias mean. */
+int gpb_acq_prepare(gpb_handle_t h, int kind, const double* mean, long long M, int n_out, const double* params,
+                    int n_params, double* out);
+
+/* Loss of one acquisition function for every candidate, summed over outputs (axis=1), and the pick
+ * idx = np.argmax(loss * mask) of AcquisitionFunction._find_next_candidates (:63-68): `visited` (host, n_visited
+ * indices) are the rows whose mask is 0 -- they compete with value loss*0 exactly as in the reference; NaN ordering
+ * and the lowest-index tie-break follow np.argmax.
+ *   term : (M, n_out)  predictive mean (POI, EI2) | gpb_acq_prepare output (WEIGHTED, EI) | NULL otherwise
+ *   var  : (M)         predictive or marginal variance
+ *   extra: (M, n_out) standard-normal draws (POI) | (M, d) candidate coordinates (DISTANCE_PENALTY) | NULL otherwise
+ *   loss_out: (M) or NULL (the unmasked loss, what calculate_loss returns); val may be NULL.
+ * Inputs left on the device by gpb_predict never travel to the host: only (idx, val) come back. */
+int gpb_acquire(gpb_handle_t h, int kind, const double* term, const double* var, const double* extra, long long M,
+                int n_out, const double* params, int n_params, const long long* visited, int n_visited, double* loss_out,
+                long long* idx, double* val);
+
 /* Dense kernel matrix and derivative tensor -- python_kernels.RBF (python_kernels.py:8-57) and the Matern-5/2
  * twin.  K: (na, nb); dK: (na, nb, n_ell + 2) or NULL. */
 int gpb_kernel_matrix(gpb_handle_t h, int kind, const double* Xa, long long na, const double* Xb, long long nb, int d,

@@ -11,6 +11,9 @@ from . import _lib
 KIND_RBF = 0
 KIND_MATERN52 = 1
 
+# acquisition kinds of gpb_acquire (include/gpb.h)
+ACQ_VARIANCE, ACQ_DISTANCE_PENALTY, ACQ_WEIGHTED, ACQ_POI, ACQ_EI, ACQ_EI2 = range(6)
+
 
 class GPBackend:
     def __init__(self, device=None):
@@ -110,6 +113,55 @@ class GPBackend:
         val = ctypes.c_double()
         _lib.check(self._lib.gpb_argmax(self._h, _lib.ptr(v), int(v.shape[0]), ctypes.byref(idx), ctypes.byref(val)),
                    self._h, "argmax")
+        return int(idx.value), float(val.value)
+
+    # -- active learning ------------------------------------------------------------------------------
+    def append_train(self, X_new, y_new):
+        """Extend the factorised model by the rows (X_new, y_new) in O(N^2) per row (gpb_append_train)."""
+        X_new = _lib.as_f64(X_new)
+        y_new = _lib.as_f64(y_new)
+        if X_new.ndim != 2 or int(X_new.shape[1]) != self.d:
+            raise ValueError(f"X should have shape (m, {self.d}) but has shape {tuple(X_new.shape)}")
+        m = int(X_new.shape[0])
+        if y_new.ndim == 1:
+            y_new = y_new.reshape(m, -1)
+        if tuple(y_new.shape) != (m, self.n_out):
+            raise ValueError(f"y should have shape ({m}, {self.n_out}) but has shape {tuple(y_new.shape)}")
+        if m == 0:
+            return
+        self.resident_key = self.factor_key = None
+        _lib.check(self._lib.gpb_append_train(self._h, _lib.ptr(X_new), _lib.ptr(y_new), m), self._h, "append_train")
+        self.n += m
+
+    def acq_prepare(self, kind, mean, params=(), out=None):
+        """Once-per-batch transform of the predictive mean (M, n_out): normalize(mu) for ACQ_WEIGHTED, the
+        ExpectedImprovement.mu_part for ACQ_EI.  ``mean`` / ``out`` may be numpy arrays or torch CUDA tensors."""
+        mean = _lib.as_f64(mean)
+        M = int(mean.shape[0])
+        n_out = 1 if mean.ndim == 1 else int(mean.shape[1])
+        params = np.ascontiguousarray(params, dtype=np.float64).ravel()
+        if out is None:
+            out = np.empty((M, n_out))
+        st = self._lib.gpb_acq_prepare(self._h, int(kind), _lib.ptr(mean), M, n_out,
+                                       _lib.ptr(params) if params.size else None, int(params.size), _lib.ptr(out))
+        _lib.check(st, self._h, "acq_prepare")
+        return out
+
+    def acquire(self, kind, var, term=None, extra=None, params=(), visited=(), n_out=1, loss_out=None):
+        """Loss of acquisition function ``kind`` over all candidates and ``np.argmax(loss * mask)`` (mask zero on the
+        ``visited`` rows) -> (index, masked value).  ``loss_out`` (numpy (M,) or torch CUDA) receives the unmasked
+        loss when given; device-resident inputs stay on the device and only the pick comes back."""
+        var = _lib.as_f64(var)
+        M = int(var.shape[0])
+        params = np.ascontiguousarray(params, dtype=np.float64).ravel()
+        vis = (ctypes.c_longlong * max(1, len(visited)))(*[int(v) for v in visited])
+        idx = ctypes.c_longlong()
+        val = ctypes.c_double()
+        st = self._lib.gpb_acquire(self._h, int(kind), _lib.ptr(None if term is None else _lib.as_f64(term)),
+                                   _lib.ptr(var), _lib.ptr(None if extra is None else _lib.as_f64(extra)), M, int(n_out),
+                                   _lib.ptr(params) if params.size else None, int(params.size), vis, len(visited),
+                                   _lib.ptr(loss_out), ctypes.byref(idx), ctypes.byref(val))
+        _lib.check(st, self._h, "acquire")
         return int(idx.value), float(val.value)
 
     # -- dense twins ----------------------------------------------------------------------------------

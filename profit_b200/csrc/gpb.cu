@@ -25,6 +25,7 @@
 #include <string>
 #include <vector>
 
+#include "acquisition.cuh"
 #include "assemble.cuh"
 #include "dgemm_tasks.cuh"
 #include "potrf_diag.cuh"
@@ -120,6 +121,10 @@ struct gpb_handle_s {
   size_t dkm_cap = 0;
   double* dbbq = nullptr;     // marginal-variance scratch
   size_t dbbq_cap = 0;
+  double* dapp = nullptr;     // append-point scratch: k row block, l, U l, scalars
+  size_t dapp_cap = 0;
+  double* dacq = nullptr;     // acquisition scratch: staged host inputs, block partials, statistics
+  size_t dacq_cap = 0;
 
   cudaEvent_t ev0[GPB_NUM_STAGES], ev1[GPB_NUM_STAGES];
   cudaEvent_t evx[3];   // scratch timing events (gradient tail, predict chunk phases, debug GEMM)
@@ -698,40 +703,6 @@ __global__ void zero_aug_kernel(double* __restrict__ L, long long np) {
   if (e < 128 * np) L[np * np + e] = 0.0;
 }
 
-// argmax with lowest-index tie break (np.argmax semantics, NaN-free input assumed)
-__global__ void __launch_bounds__(1024) argmax_kernel(const double* __restrict__ v, long long n, double* __restrict__ oval,
-                                                      long long* __restrict__ oidx) {
-  __shared__ double sv[1024];
-  __shared__ long long si[1024];
-  double bv = -INFINITY;
-  long long bi = 0x7fffffffffffffffLL;
-  for (long long k = threadIdx.x; k < n; k += 1024) {
-    const double x = v[k];
-    if (x > bv || (x == bv && k < bi)) {
-      bv = x;
-      bi = k;
-    }
-  }
-  sv[threadIdx.x] = bv;
-  si[threadIdx.x] = bi;
-  __syncthreads();
-  for (int off = 512; off > 0; off >>= 1) {
-    if ((int)threadIdx.x < off) {
-      const double x = sv[threadIdx.x + off];
-      const long long k = si[threadIdx.x + off];
-      if (x > sv[threadIdx.x] || (x == sv[threadIdx.x] && k < si[threadIdx.x])) {
-        sv[threadIdx.x] = x;
-        si[threadIdx.x] = k;
-      }
-    }
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    oval[0] = sv[0];
-    oidx[0] = si[0];
-  }
-}
-
 // ------------------------------------------------------------------------------------------------ helpers
 void stage_begin(H* h, int s) {
   cudaEventRecord(h->ev0[s], h->stream);
@@ -807,7 +778,7 @@ int cross_dispatch(H* h, Workspace& w, const double* dXc, long long mc, double* 
 #define GPB_CM(DPV)                                                                                                  \
   case DPV:                                                                                                          \
     cross_mean_kernel<KIND, DPV><<<grid, AS_THREADS, 0, h->stream>>>(dXc, (int)mc, h->D, h->hyp, h->dXsT, w.Np, (int)w.N, \
-                                                                    (int)w.Np, w.alpha, w.Np, h->n_out, KsT, ldk, mean); \
+                                                                    (int)w.Np, w.alpha, w.Np, mean ? h->n_out : 0, KsT, ldk, mean); \
     break;
   switch (h->DP) {
     GPB_CM(4) GPB_CM(8) GPB_CM(12) GPB_CM(16) GPB_CM(24) GPB_CM(32)
@@ -902,6 +873,72 @@ int invert_diag_blocks(H* h, Workspace& w) {
   h->launches++;
   CK(cudaGetLastError());
   return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ active learning
+// Device address of `count` doubles at `p`: device pointers pass through, host data is staged at *cursor.
+int acq_stage_in(H* h, const double* p, size_t count, double** cursor, const double** out) {
+  *out = nullptr;
+  if (!p) return 0;
+  if (is_device_ptr(p)) {
+    *out = p;
+    return 0;
+  }
+  CK(cudaMemcpyAsync(*cursor, p, count * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  *out = *cursor;
+  *cursor += count;
+  return 0;
+}
+
+int acq_grid(long long M) {
+  const long long want = (M + ACQ_THREADS - 1) / ACQ_THREADS;
+  return (int)std::max<long long>(1, std::min<long long>(want, 148 * 8));
+}
+
+// stats[2c], stats[2c+1] = column-wise min / max of v (M, ncol) [after sqrt when transform == 1]
+int acq_minmax(H* h, const double* v, long long M, int ncol, int transform, double* part, double* stats) {
+  const int nblk = acq_grid(M);
+  acq_minmax_partial_kernel<<<dim3(nblk, ncol), ACQ_THREADS, 0, h->stream>>>(v, M, ncol, transform, part);
+  acq_minmax_final_kernel<<<ncol, ACQ_THREADS, 0, h->stream>>>(part, nblk, stats);
+  h->launches += 2;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int fill_acq_args(H* h, AcqArgs& a, int kind, long long M, int n_out, const double* params, int n_params) {
+  memset(&a, 0, sizeof(a));
+  a.kind = kind;
+  a.M = M;
+  a.n_out = n_out;
+  auto need = [&](int n) { return n_params >= n && (n == 0 || params); };
+  switch (kind) {
+    case ACQ_VARIANCE: return 0;
+    case ACQ_DISTANCE_PENALTY:   // [c1, d, last_0 .. last_{d-1}]
+      if (!need(2)) return fail(h, -1, "distance penalty: params = [weight, d, last point...]");
+      a.p0 = params[0];
+      a.d = (int)params[1];
+      if (a.d < 1 || a.d > ACQ_MAX_DIM || !need(2 + a.d)) return fail(h, -1, "distance penalty: bad dimension");
+      for (int k = 0; k < a.d; ++k) a.last[k] = params[2 + k];
+      return 0;
+    case ACQ_WEIGHTED:           // [weight]
+      if (!need(1)) return fail(h, -1, "weighted exploration: params = [weight]");
+      a.p0 = params[0];
+      return 0;
+    case ACQ_POI:                // [ymax_0 ..]
+      if (!need(n_out)) return fail(h, -1, "probability of improvement: params = [ymax per output]");
+      for (int o = 0; o < n_out; ++o) a.ymax[o] = params[o];
+      return 0;
+    case ACQ_EI:                 // loss: none;  prepare: [xi, find_min, ymax_0 ..]
+      if (n_params == 0) return 0;
+      // fallthrough
+    case ACQ_EI2:                // [xi, find_min, ymax_0 ..]
+      if (!need(2 + n_out)) return fail(h, -1, "expected improvement: params = [xi, find_min, ymax per output]");
+      a.p0 = params[0];
+      a.p1 = params[1];
+      for (int o = 0; o < n_out; ++o) a.ymax[o] = params[2 + o];
+      return 0;
+    default: return fail(h, -1, "unknown acquisition kind");
+  }
 }
 
 // Dense K(Xa, Xb) [+ dK] from device-resident raw inputs into device outputs (kernel_matrix_kernel).
@@ -1071,6 +1108,8 @@ int gpb_destroy(gpb_handle_t h) {
   cudaFree(h->dstage2);
   cudaFree(h->dkm);
   cudaFree(h->dbbq);
+  cudaFree(h->dapp);
+  cudaFree(h->dacq);
   for (int s = 0; s < GPB_NUM_STAGES; ++s) {
     cudaEventDestroy(h->ev0[s]);
     cudaEventDestroy(h->ev1[s]);
@@ -1319,19 +1358,8 @@ int gpb_predict(gpb_handle_t h, const double* Xc, long long M, int add_data_vari
 
 int gpb_argmax(gpb_handle_t h, const double* v, long long M, long long* idx, double* val) {
   if (!h || !v || M < 1 || !idx) return fail(h, -1, "gpb_argmax: bad argument");
-  CK(cudaSetDevice(h->device));
-  int rc = ensure_cap(h, &h->dstage, &h->dstage_cap, (size_t)M + 2);
-  if (rc) return rc;
-  CK(cudaMemcpyAsync(h->dstage + 2, v, (size_t)M * sizeof(double), cudaMemcpyDefault, h->stream));
-  argmax_kernel<<<1, 1024, 0, h->stream>>>(h->dstage + 2, M, h->dstage, reinterpret_cast<long long*>(h->dstage + 1));
-  h->launches++;
-  CK(cudaGetLastError());
-  double hv[2];
-  CK(cudaMemcpyAsync(hv, h->dstage, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
-  if (val) *val = hv[0];
-  memcpy(idx, &hv[1], sizeof(long long));
-  return 0;
+  // the plain variance acquisition without a mask is exactly np.argmax
+  return gpb_acquire(h, ACQ_VARIANCE, nullptr, v, nullptr, M, 1, nullptr, 0, nullptr, 0, nullptr, idx, val);
 }
 
 int gpb_kernel_matrix(gpb_handle_t h, int kind, const double* Xa, long long na, const double* Xb, long long nb, int d,
@@ -1428,6 +1456,173 @@ int gpb_marginal_variance(gpb_handle_t h, const double* Xc, long long M, const d
     CK(cudaMemcpyAsync(out + c0, dout, (size_t)mc * sizeof(double), cudaMemcpyDefault, h->stream));
     CK(cudaStreamSynchronize(h->stream));
   }
+  return 0;
+}
+
+int gpb_append_train(gpb_handle_t h, const double* Xnew, const double* ynew, long long m) {
+  int rc = need_train(h);
+  if (rc) return rc;
+  if (!h->factor_ready) return fail(h, -3, "gpb_append_train: call gpb_factorize first");
+  if (!Xnew || !ynew || m < 1) return fail(h, -1, "gpb_append_train: bad argument");
+  CK(cudaSetDevice(h->device));
+  const int D = h->D, n_out = h->n_out;
+  for (long long p = 0; p < m; ++p) {
+    Workspace& w = h->ws;
+    const long long N = w.N, Np = w.Np;
+    if (N == Np) {
+      // The padded block is full: grow by re-uploading [X; Xnew[p:]] and refactorising at the current theta.
+      const long long rem = m - p, tot = N + rem;
+      double *tx = nullptr, *ty = nullptr;
+      CK(cudaMalloc(&tx, (size_t)tot * D * sizeof(double)));
+      CK(cudaMalloc(&ty, (size_t)tot * n_out * sizeof(double)));
+      cudaError_t e1 = cudaMemcpyAsync(tx, h->dX, (size_t)N * D * sizeof(double), cudaMemcpyDeviceToDevice, h->stream);
+      cudaError_t e2 = cudaMemcpyAsync(ty, h->dy, (size_t)N * n_out * sizeof(double), cudaMemcpyDeviceToDevice, h->stream);
+      cudaError_t e3 = cudaMemcpyAsync(tx + N * D, Xnew + p * D, (size_t)rem * D * sizeof(double), cudaMemcpyDefault, h->stream);
+      cudaError_t e4 = cudaMemcpyAsync(ty + N * n_out, ynew + p * n_out, (size_t)rem * n_out * sizeof(double), cudaMemcpyDefault, h->stream);
+      cudaError_t e5 = cudaStreamSynchronize(h->stream);
+      double theta[MAX_D + 2];
+      const int n_ell = h->hyp.n_ell, kind = h->hyp.kind;
+      for (int d = 0; d < n_ell; ++d) theta[d] = h->hyp.ell[d];
+      theta[n_ell] = h->hyp.sf;
+      theta[n_ell + 1] = h->hyp.sn;
+      rc = (e1 || e2 || e3 || e4 || e5) ? fail(h, -2, "gpb_append_train: staging copy failed") : 0;
+      if (!rc) rc = gpb_set_train(h, tx, ty, tot, D, n_out);
+      if (!rc) rc = gpb_factorize(h, kind, theta, n_ell);
+      cudaFree(tx);
+      cudaFree(ty);
+      return rc;
+    }
+    // scratch: [32 x Np] K* rows (cross_mean_kernel writes whole 32-row groups) | l | U l | scalars | new y
+    if ((rc = ensure_cap(h, &h->dapp, &h->dapp_cap, (size_t)34 * Np + 320))) return rc;
+    double* kst = h->dapp;
+    double* lvec = kst + (size_t)32 * Np;
+    double* tvec = lvec + Np;
+    double* scal = tvec + Np;        // [0] = 1/d, [1 + o] = z_o[N]
+    double* dynew = scal + 129;      // n_out values
+    double* dxnew = dynew + 128;     // D values
+    CK(cudaMemcpyAsync(dxnew, Xnew + p * D, (size_t)D * sizeof(double), cudaMemcpyDefault, h->stream));
+    CK(cudaMemcpyAsync(dynew, ynew + p * n_out, (size_t)n_out * sizeof(double), cudaMemcpyDefault, h->stream));
+    CK(cudaMemsetAsync(h->dinfo, 0, sizeof(int), h->stream));
+    rc = (h->hyp.kind == KIND_RBF) ? cross_dispatch<KIND_RBF>(h, w, dxnew, 1, kst, Np, nullptr)
+                                   : cross_dispatch<KIND_MATERN52>(h, w, dxnew, 1, kst, Np, nullptr);
+    if (rc) return rc;
+    // l = W[0:N, 0:N] k
+    trigemv_kernel<<<(unsigned)((N + 7) / 8), 256, 0, h->stream>>>(w.Wbuf, Np, N, true, kst, 1, 0, 1, lvec, 1, 0);
+    const double kss = h->hyp.sf * h->hyp.sf + h->hyp.sn * h->hyp.sn;
+    append_pivot_kernel<<<1, 1024, 0, h->stream>>>(lvec, N, kss, dynew, n_out, w.Lbuf + Np * Np, Np,
+                                                  w.logdet + N / 128, scal, h->dinfo);
+    h->launches += 2;
+    CK(cudaGetLastError());
+    if ((rc = check_info(h))) return rc;   // not SPD with the new point: nothing has been modified
+    // t = U[0:N, 0:N] l;  new row of W / column of U;  alpha update
+    trigemv_kernel<<<(unsigned)((N + 7) / 8), 256, 0, h->stream>>>(w.Ubuf, Np, N, false, lvec, 1, 0, 1, tvec, 1, 0);
+    append_update_kernel<<<(unsigned)((N + 1 + 255) / 256), 256, 0, h->stream>>>(tvec, N, scal, n_out, w.Wbuf, w.Ubuf, Np,
+                                                                                w.alpha, Np);
+    // the raw point joins the resident training set; refresh the scaled copies
+    CK(cudaMemcpyAsync(h->dX + N * D, dxnew, (size_t)D * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->dy + N * n_out, dynew, (size_t)n_out * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    w.N = N + 1;
+    {
+      const long long tot = Np * h->DP;
+      prescale_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(h->dX, (int)w.N, h->hyp, h->DP, h->dXs,
+                                                                          h->dXsT, Np, (int)Np);
+    }
+    h->launches += 3;
+    CK(cudaGetLastError());
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int gpb_acq_prepare(gpb_handle_t h, int kind, const double* mean, long long M, int n_out, const double* params,
+                    int n_params, double* out) {
+  if (!h || !mean || !out || M < 1 || n_out < 1 || n_out > ACQ_MAX_OUT) return fail(h, -1, "gpb_acq_prepare: bad argument");
+  if (kind != ACQ_WEIGHTED && kind != ACQ_EI) return fail(h, -1, "gpb_acq_prepare: kind has no prepare step");
+  CK(cudaSetDevice(h->device));
+  AcqArgs a;
+  int rc = 0;
+  if (kind == ACQ_EI) {
+    if (n_params == 0) return fail(h, -1, "expected improvement: params = [xi, find_min, ymax per output]");
+    if ((rc = fill_acq_args(h, a, kind, M, n_out, params, n_params))) return rc;
+  } else {   // normalize(mu) has no parameters
+    memset(&a, 0, sizeof(a));
+    a.kind = kind;
+    a.M = M;
+    a.n_out = n_out;
+  }
+  const size_t tot = (size_t)M * n_out;
+  const int nblk = acq_grid(M);
+  const bool out_dev = is_device_ptr(out);
+  if ((rc = ensure_cap(h, &h->dacq, &h->dacq_cap, 2 * tot + (size_t)2 * nblk * n_out + 2 * ACQ_MAX_OUT + 64))) return rc;
+  double* cur = h->dacq;
+  const double* dmean = nullptr;
+  if ((rc = acq_stage_in(h, mean, tot, &cur, &dmean))) return rc;
+  double* dout = out_dev ? out : cur;
+  if (!out_dev) cur += tot;
+  double* part = cur;
+  double* stats = part + (size_t)2 * nblk * n_out;
+  const int grid = acq_grid((long long)tot);
+  acq_prepare_kernel<<<grid, ACQ_THREADS, 0, h->stream>>>(0, a, dmean, stats, dout);
+  h->launches++;
+  if ((rc = acq_minmax(h, dout, M, n_out, 0, part, stats))) return rc;
+  acq_prepare_kernel<<<grid, ACQ_THREADS, 0, h->stream>>>(1, a, dmean, stats, dout);
+  h->launches++;
+  CK(cudaGetLastError());
+  if (!out_dev) CK(cudaMemcpyAsync(out, dout, tot * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int gpb_acquire(gpb_handle_t h, int kind, const double* term, const double* var, const double* extra, long long M,
+                int n_out, const double* params, int n_params, const long long* visited, int n_visited, double* loss_out,
+                long long* idx, double* val) {
+  if (!h || !var || !idx || M < 1 || n_out < 1 || n_out > ACQ_MAX_OUT || n_visited < 0 || (n_visited > 0 && !visited))
+    return fail(h, -1, "gpb_acquire: bad argument");
+  CK(cudaSetDevice(h->device));
+  AcqArgs a;
+  int rc = fill_acq_args(h, a, kind, M, n_out, params, n_params);
+  if (rc) return rc;
+  a.n_visited = n_visited;
+  const bool need_term = kind == ACQ_WEIGHTED || kind == ACQ_POI || kind == ACQ_EI || kind == ACQ_EI2;
+  const bool need_extra = kind == ACQ_POI || kind == ACQ_DISTANCE_PENALTY;
+  if ((need_term && !term) || (need_extra && !extra)) return fail(h, -1, "gpb_acquire: missing input array for this kind");
+  const size_t n_term = need_term ? (size_t)M * n_out : 0;
+  const size_t n_extra = need_extra ? (size_t)M * (kind == ACQ_POI ? n_out : a.d) : 0;
+  const int nblk = acq_grid(M);
+  const bool loss_dev = loss_out && is_device_ptr(loss_out);
+  const size_t cap = n_term + n_extra + (size_t)2 * M + (size_t)4 * nblk + n_visited + 64;
+  if ((rc = ensure_cap(h, &h->dacq, &h->dacq_cap, cap))) return rc;
+  double* cur = h->dacq;
+  const double *dterm = nullptr, *dvar = nullptr, *dextra = nullptr;
+  if ((rc = acq_stage_in(h, need_term ? term : nullptr, n_term, &cur, &dterm))) return rc;
+  if ((rc = acq_stage_in(h, var, (size_t)M, &cur, &dvar))) return rc;
+  if ((rc = acq_stage_in(h, need_extra ? extra : nullptr, n_extra, &cur, &dextra))) return rc;
+  double* dloss = nullptr;
+  if (loss_out) {
+    dloss = loss_dev ? loss_out : cur;
+    if (!loss_dev) cur += M;
+  }
+  double* part = cur;                 // min/max partials, then arg-max partial values
+  long long* pidx = reinterpret_cast<long long*>(part + (size_t)2 * nblk);
+  double* stats = part + (size_t)3 * nblk;       // [0..1] min/max, [2] winner value, [3] winner index
+  long long* dvis = reinterpret_cast<long long*>(stats + 8);
+  if (n_visited > 0) {
+    for (int k = 0; k < n_visited; ++k)
+      if (visited[k] < 0 || visited[k] >= M) return fail(h, -1, "gpb_acquire: visited index out of range");
+    CK(cudaMemcpyAsync(dvis, visited, (size_t)n_visited * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+  }
+  if (kind == ACQ_DISTANCE_PENALTY || kind == ACQ_WEIGHTED || kind == ACQ_EI)
+    if ((rc = acq_minmax(h, dvar, M, 1, kind == ACQ_EI ? 1 : 0, part, stats))) return rc;
+  acq_loss_kernel<<<nblk, ACQ_THREADS, 0, h->stream>>>(a, dterm, dvar, dextra, stats, dvis, dloss, part, pidx);
+  acq_argmax_final_kernel<<<1, ACQ_THREADS, 0, h->stream>>>(part, pidx, nblk, stats + 2, reinterpret_cast<long long*>(stats + 3));
+  h->launches += 2;
+  CK(cudaGetLastError());
+  double hv[2];
+  CK(cudaMemcpyAsync(hv, stats + 2, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (loss_out && !loss_dev) CK(cudaMemcpyAsync(loss_out, dloss, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (val) *val = hv[0];
+  memcpy(idx, &hv[1], sizeof(long long));
   return 0;
 }
 

@@ -158,14 +158,23 @@ class B200GPSurrogate(_GPBase):
             self._backend = GPBackend(self._device)
         return self._backend
 
+    @staticmethod
+    def _data_key(X, y):
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        return (X.shape, y.shape, hash(X.tobytes()), hash(y.tobytes())) if X.size < (1 << 22) else None
+
     def _upload(self):
         X = np.ascontiguousarray(self.Xtrain, dtype=np.float64)
         y = np.ascontiguousarray(self.ytrain, dtype=np.float64)
-        key = (X.shape, y.shape, hash(X.tobytes()), hash(y.tobytes())) if X.size < (1 << 22) else None
+        key = self._data_key(X, y)
         be = self.backend
         if key is None or key != be.resident_key:
             be.set_train(X, y)
             be.resident_key = key
+
+    def _factor_key(self, resident_key):
+        return (resident_key, self._theta().tobytes(), getattr(self.kernel, "__name__", str(self.kernel)))
 
     def _theta(self, with_sigma_n=True):
         keys = ("length_scale", "sigma_f", "sigma_n")
@@ -226,19 +235,42 @@ class B200GPSurrogate(_GPBase):
                                          add_data_variance=1 if add_data_variance else 0)
         return mean, var.reshape(-1, 1)
 
+    def predict_into(self, Xpred, out_mean=None, out_var=None, add_data_variance=True):
+        """``predict`` for callers that keep everything on the device: ``Xpred`` (M, d), ``out_mean`` (M, n_out) and
+        ``out_var`` (M,) are torch CUDA tensors (or numpy arrays); either output may be None to skip it."""
+        self._ensure_factor()
+        self.backend.predict(Xpred, add_data_variance=1 if add_data_variance else 0, out_mean=out_mean,
+                             out_var=out_var, want_mean=out_mean is not None, want_var=out_var is not None)
+
     def _ensure_factor(self):
         self._upload()
-        theta = self._theta()
         be = self.backend
-        key = (be.resident_key, theta.tobytes(), getattr(self.kernel, "__name__", str(self.kernel)))
+        key = self._factor_key(be.resident_key)
         if be.resident_key is None or key != be.factor_key:
-            be.factorize(kernel_kind(self.kernel), theta)
+            be.factorize(kernel_kind(self.kernel), self._theta())
             be.factor_key = key
 
     def add_training_data(self, X, y):
-        """custom_surrogate.py:122-134: append rows; hyper-parameters are not re-optimised here."""
+        """custom_surrogate.py:122-134: append rows; hyper-parameters are not re-optimised here.
+
+        The reference leaves "Update Ky" as a TODO (:132) and refactorises on the next predict.  Here, when the
+        device holds the factor of exactly this model, the factor is extended in place (O(N^2) per row)."""
+        X = np.asarray(X, dtype=np.float64)
+        y = np.asarray(y, dtype=np.float64)
+        be = self._backend
+        extend = False
+        if be is not None and self.trained and be.resident_key is not None and callable(self.kernel):
+            old_key = self._data_key(self.Xtrain, self.ytrain)
+            extend = old_key == be.resident_key and be.factor_key == self._factor_key(old_key)
         self.Xtrain = np.concatenate([self.Xtrain, X], axis=0)
         self.ytrain = np.concatenate([self.ytrain, y], axis=0)
+        if extend:
+            try:
+                be.append_train(X.reshape(-1, self.Xtrain.shape[1]), y.reshape(X.shape[0], -1))
+            except np.linalg.LinAlgError:
+                return      # left to the next predict, which refactorises (and raises there like the reference)
+            be.resident_key = self._data_key(self.Xtrain, self.ytrain)
+            be.factor_key = self._factor_key(be.resident_key)
 
     def set_ytrain(self, ydata):
         """custom_surrogate.py:136-142."""

@@ -155,3 +155,51 @@ def test_oracle_against_live_reference():
     a = G.negative_log_likelihood_cholesky(theta, X, y, oracle.matern52, eval_gradient=True)
     b = oracle.nll_cholesky(theta, X, y, oracle.matern52, eval_gradient=True)
     assert abs(a[0] - b[0]) <= 1e-13 * abs(a[0]) and rel_err(b[1], a[1]) <= 1e-12
+
+
+# ------------------------------------------------------------------------------------------ acquisition oracle
+def test_acquisition_oracle_reproduces_reference_losses():
+    """oracle/acq_oracle.py against the losses the unmodified reference classes produced (make_golden_acq.py)."""
+    import json
+    import os
+
+    from oracle import acq_oracle as A
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(root, "tests", "golden", "acquisition_kats.json")) as f:
+        k = json.load(f)
+    N, D, M, NS = k["N"], k["D"], k["M"], k["NS"]
+    X, y = oracle.synthetic_problem(N, D)
+    Xpred = np.random.default_rng(k["pred_seed"]).random((M, D))
+    mu, var = np.array(k["mean"]).reshape(-1, 1), np.array(k["var"]).reshape(-1, 1)
+    # the stored mean / variance are the reference surrogate's; the GP oracle agrees with them
+    theta = np.array(k["theta"])
+    m_o, v_o = oracle.predict(X, y, Xpred, oracle.rbf, theta[:D], theta[D], theta[D + 1])
+    assert np.allclose(m_o, mu, rtol=1e-9, atol=1e-12) and np.allclose(v_o, var, rtol=1e-9)
+    vout = np.full((NS, 1), np.nan)
+    vout[:N] = y
+    C = k["cases"]
+
+    def same(ref, mine):
+        assert np.allclose(mine, ref, rtol=1e-13, atol=0)
+
+    same(C["simple_exploration"]["loss"], A.loss_variance(var))
+    for key in ("exploration_with_distance_penalty_w10", "exploration_with_distance_penalty_w3.5"):
+        same(C[key]["loss"], A.loss_distance_penalty(var, Xpred, np.array(C[key]["last_point"]), C[key]["weight"]))
+        assert np.array_equal(C[key]["last_point"], X[N - 1])
+    for key in ("weighted_exploration_w0.5", "weighted_exploration_w0.2"):
+        same(C[key]["mu_normalized"], A.normalize(mu).ravel())
+        same(C[key]["loss"], A.loss_weighted(A.normalize(mu), var, C[key]["weight"]))
+    c = C["probability_of_improvement"]
+    np.random.seed(c["np_random_seed"])
+    same(c["loss"], A.loss_poi(mu, var, np.random.standard_normal(mu.shape), np.array(c["ymax"])))
+    for key in ("expected_improvement_xi0.01_min0", "expected_improvement_xi0.05_min1"):
+        imp = A.ei_mu_part(mu.copy(), vout, C[key]["xi"], C[key]["find_min"])
+        same(C[key]["improvement"], imp.ravel())
+        same(C[key]["loss"], A.loss_ei(imp, var))
+    for key in ("expected_improvement_2_xi0.01_min0", "expected_improvement_2_xi0.05_min1"):
+        same(C[key]["loss"], A.loss_ei2(mu.copy(), var, vout, C[key]["xi"], C[key]["find_min"]))
+    for key, c in C.items():
+        assert A.pick(np.array(c["loss"])) == c["argmax"]
+    mp = k["masked_pick"]
+    assert A.pick(np.array(C["simple_exploration"]["loss"]), mp["visited"]) == mp["expect"]

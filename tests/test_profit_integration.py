@@ -44,6 +44,38 @@ for name, sur in (("ref", ref), ("gpu", gpu)):
     picks[name] = af.find_next_candidates(2)
     assert sur.Xtrain.shape[0] == 152
 assert np.allclose(picks["ref"][0], picks["gpu"][0]), picks   # identical first pick (same model, same candidates)
+
+# device twins of the acquisition functions: registered in the reference's registry, same losses as the reference
+# classes on the reference surrogate when both models hold the same hyper-parameters
+import types
+from profit.al.aquisition_functions import AcquisitionFunction
+import profit_b200.acquisition as pa
+
+assert AcquisitionFunction["b200_expected_improvement"] is pa.ExpectedImprovement
+assert issubclass(pa.SimpleExploration, AcquisitionFunction)
+ref2 = Surrogate["Custom"](); gpu2 = Surrogate["B200"]()
+for s2 in (ref2, gpu2):
+    s2.Xtrain, s2.ytrain, s2.ndim, s2.trained = X.copy(), y.copy(), 2, True
+    s2.kernel = s2.select_kernel("RBF")
+    s2.hyperparameters = {"length_scale": np.array([0.4]), "sigma_f": np.array([1.2]), "sigma_n": np.array([0.1])}
+vin = np.full((160, 2), np.nan); vout = np.full((160, 1), np.nan); vin[:150] = X; vout[:150] = y
+variables = types.SimpleNamespace(input=vin, output=vout)
+pairs = [("simple_exploration", {}, ()), ("exploration_with_distance_penalty", {"weight": 5}, ()),
+         ("weighted_exploration", {"weight": 0.4}, "mu"), ("expected_improvement", {"exploration_factor": 0.02}, "imp"),
+         ("expected_improvement_2", {"find_min": True}, ())]
+for label, kw, arg in pairs:
+    ra = AcquisitionFunction[label](Xc, ref2, variables, **kw)
+    ga = AcquisitionFunction["b200_" + label](Xc, gpu2, variables, **kw)
+    if arg == "mu":
+        rl, gl = ra.calculate_loss(ra.normalize(ref2.predict(Xc)[0])), ga.calculate_loss(ga.normalized_mean())
+    elif arg == "imp":
+        rl, gl = ra.calculate_loss(ra.mu_part()), ga.calculate_loss(ga.mu_part())
+    else:
+        rl, gl = ra.calculate_loss(), ga.calculate_loss()
+    assert np.all(np.abs(rl - gl) <= 1e-8 * np.abs(rl) + 1e-10 * np.abs(rl).max()), (label, np.abs(rl - gl).max())
+    assert int(np.argmax(rl)) == int(np.argmax(gl)), label
+pa.register_as_default()
+assert AcquisitionFunction["simple_exploration"] is pa.SimpleExploration
 print("profit integration ok", hg)
 '''
 
