@@ -68,6 +68,11 @@ int gpb_factorize(gpb_handle_t h, int kind, const double* theta, int n_ell);
  * Either output may be NULL. */
 int gpb_predict(gpb_handle_t h, const double* Xc, long long M, int add_data_variance, double* mean, double* var);
 
+/* Full predictive covariance -- gp_functions.predict_f with return_full_cov=True (gp_functions.py:484-490):
+ * cov = max(K(X*, X*) [+ sn^2 I if noise_on_diagonal] - K*^T K^-1 K*, 1e-10) element-wise, (M, M) row-major, and
+ * optionally the mean (M, n_out).  K*^T K^-1 K* = Vt Vt^T with Vt = K*^T L^-T: two tile GEMMs.  M <= 16384. */
+int gpb_predict_cov(gpb_handle_t h, const double* Xc, long long M, int noise_on_diagonal, double* mean, double* cov);
+
 /* argmax with lowest-index tie-break, like np.argmax in aquisition_functions.py:68. v: (M). */
 int gpb_argmax(gpb_handle_t h, const double* v, long long M, long long* idx, double* val);
 

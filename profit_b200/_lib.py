@@ -26,6 +26,7 @@ SIGNATURES = {
                                ctypes.POINTER(ctypes.c_double), _c_double_p]),
     "gpb_factorize": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _c_double_p, ctypes.c_int]),
     "gpb_predict": (ctypes.c_int, [ctypes.c_void_p, _c_double_p, _ll, ctypes.c_int, _c_double_p, _c_double_p]),
+    "gpb_predict_cov": (ctypes.c_int, [ctypes.c_void_p, _c_double_p, _ll, ctypes.c_int, _c_double_p, _c_double_p]),
     "gpb_argmax": (ctypes.c_int, [ctypes.c_void_p, _c_double_p, _ll, ctypes.POINTER(_ll),
                                   ctypes.POINTER(ctypes.c_double)]),
     "gpb_append_train": (ctypes.c_int, [ctypes.c_void_p, _c_double_p, _c_double_p, _ll]),

@@ -96,6 +96,16 @@ class GPBackend:
         _lib.check(st, self._h, "predict")
         return out_mean, out_var
 
+    def predict_cov(self, Xc, noise_on_diagonal=True, want_mean=True, out_cov=None):
+        """Full (M, M) predictive covariance [and the mean] -- predict_f(..., return_full_cov=True)."""
+        Xc = _lib.as_f64(Xc)
+        M = int(Xc.shape[0])
+        mean = np.empty((M, self.n_out)) if want_mean else None
+        cov = np.empty((M, M)) if out_cov is None else out_cov
+        st = self._lib.gpb_predict_cov(self._h, _lib.ptr(Xc), M, int(bool(noise_on_diagonal)), _lib.ptr(mean), _lib.ptr(cov))
+        _lib.check(st, self._h, "predict_cov")
+        return mean, cov
+
     def marginal_variance(self, Xc, hess_inv, predictive_variance=None):
         """dm^T H^-1 dm + predictive variance per candidate (gp_functions.marginal_variance_BBQ) -> (M,) array."""
         Xc = _lib.as_f64(Xc)

@@ -703,6 +703,37 @@ __global__ void zero_aug_kernel(double* __restrict__ L, long long np) {
   if (e < 128 * np) L[np * np + e] = 0.0;
 }
 
+// K(Xc, Xc) (+ sn^2 on the diagonal, np.eye as in python_kernels.py:41) into the padded covariance buffer; the
+// predictive covariance then subtracts Vt Vt^T from it (gp_functions.predict_f, :484-487).
+template <int KIND>
+__global__ void cov_prior_kernel(const double* __restrict__ Xc, int m, KernelHyp h, double* __restrict__ C, long long ldc,
+                                 int m_pad) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long long)m_pad * m_pad) return;
+  const int i = (int)(e / m_pad), j = (int)(e % m_pad);
+  double v = 0.0;
+  if (i < m && j < m) {
+    double d2 = 0.0;
+    for (int d = 0; d < h.D; ++d) {
+      const double l = ell_of(h, d);
+      const double u = Xc[(long long)i * h.D + d] / l - Xc[(long long)j * h.D + d] / l;
+      d2 = fma(u, u, d2);
+    }
+    double gd;
+    kern_eval<KIND>(d2, h.sf * h.sf, v, gd);
+    if (i == j) v += h.sn * h.sn;
+  }
+  C[(long long)i * ldc + j] = v;
+}
+
+// out (m x m, contiguous) = max(C, 1e-10) element-wise (gp_functions.py:488)
+__global__ void cov_finish_kernel(const double* __restrict__ C, long long ldc, int m, double* __restrict__ out) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long long)m * m) return;
+  const int i = (int)(e / m), j = (int)(e % m);
+  out[e] = fmax(C[(long long)i * ldc + j], 1e-10);
+}
+
 // ------------------------------------------------------------------------------------------------ helpers
 void stage_begin(H* h, int s) {
   cudaEventRecord(h->ev0[s], h->stream);
@@ -1353,6 +1384,91 @@ int gpb_predict(gpb_handle_t h, const double* Xc, long long M, int add_data_vari
   stages_collect(h);
   h->stage_ms[GPB_STAGE_CROSS] = cross_ms;
   h->stage_ms[GPB_STAGE_VAR] = var_ms;
+  return 0;
+}
+
+int gpb_predict_cov(gpb_handle_t h, const double* Xc, long long M, int noise_on_diagonal, double* mean, double* cov) {
+  int rc = need_train(h);
+  if (rc) return rc;
+  if (!h->factor_ready) return fail(h, -3, "gpb_predict_cov: call gpb_factorize first");
+  if (!Xc || !cov || M < 1) return fail(h, -1, "gpb_predict_cov: bad argument");
+  if (M > 16384) return fail(h, -1, "gpb_predict_cov: at most 16384 test points (the covariance is M x M)");
+  CK(cudaSetDevice(h->device));
+  Workspace& w = h->ws;
+  const long long Np = w.Np, Mp = round_up(M, 128);
+  const int D = h->D, cfg = cfg_for_blocks(g_cfg_update, (int)((Mp / 128) * w.Nb));
+  // scratch: candidates | K*^T (Mp x Np) | Vt = K*^T W^T (Mp x Np) | covariance (Mp x Mp) | mean
+  const size_t need = (size_t)M * D + 16 + 2 * (size_t)Mp * Np + (size_t)Mp * Mp + (size_t)Mp * 128;
+  if ((rc = ensure_cap(h, &h->dstage2, &h->dstage2_cap, need))) return rc;
+  double* dXc = h->dstage2;
+  double* kst = dXc + (((size_t)M * D + 15) & ~(size_t)15);   // keep the matrices 128-byte aligned for TMA
+  double* vt = kst + (size_t)Mp * Np;
+  double* cv = vt + (size_t)Mp * Np;
+  double* dmean = cv + (size_t)Mp * Mp;
+  CK(cudaMemcpyAsync(dXc, Xc, (size_t)M * D * sizeof(double), cudaMemcpyDefault, h->stream));
+  CK(cudaMemsetAsync(kst, 0, (size_t)Mp * Np * sizeof(double), h->stream));
+  rc = (h->hyp.kind == KIND_RBF) ? cross_dispatch<KIND_RBF>(h, w, dXc, M, kst, Np, mean ? dmean : nullptr)
+                                 : cross_dispatch<KIND_MATERN52>(h, w, dXc, M, kst, Np, mean ? dmean : nullptr);
+  if (rc) return rc;
+  KernelHyp hp = h->hyp;
+  if (!noise_on_diagonal) hp.sn = 0.0;
+  {
+    const long long tot = Mp * Mp;
+    if (hp.kind == KIND_RBF)
+      cov_prior_kernel<KIND_RBF><<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(dXc, (int)M, hp, cv, Mp, (int)Mp);
+    else
+      cov_prior_kernel<KIND_MATERN52><<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(dXc, (int)M, hp, cv, Mp, (int)Mp);
+    h->launches++;
+    CK(cudaGetLastError());
+  }
+  set_mat(w, M_KST, kst, Mp, Np, Np);
+  set_mat(w, M_DBG_A, vt, Mp, Np, Np);
+  Plan p;
+  {
+    // Vt[c][i] = sum_{k <= i} K*^T[c][k] W[i][k]
+    TaskSink s(p);
+    for (int ib = (int)w.Nb - 1; ib >= 0; --ib)
+      for (long long cb = 0; cb < Mp / 128; ++cb) s.block(cfg, (int)cb * 128, 0, ib * 128, 0, 8 * (ib + 1), (int)cb * 128, ib * 128);
+    s.finish(cfg, EPI_STORE, M_KST, M_W, M_DBG_A, M_NONE, 1.0, 0.0, false);
+  }
+  const size_t n1 = p.tasks.size();
+  {
+    // C -= Vt Vt^T
+    TaskSink s(p);
+    for (long long i = 0; i < Mp / 128; ++i)
+      for (long long j = 0; j < Mp / 128; ++j) s.block(cfg, (int)i * 128, 0, (int)j * 128, 0, (int)(Np / 16), (int)i * 128, (int)j * 128);
+    s.finish(cfg, EPI_STORE, M_DBG_A, M_DBG_A, M_DBG_C, M_NONE, -1.0, 1.0, false);
+  }
+  if ((rc = upload_plan(h, p))) return rc;
+  GemmEpilogue ep;
+  ep.C = vt;
+  ep.ldc = Np;
+  ep.Ct = nullptr;
+  ep.ldct = 0;
+  ep.alpha = 1.0;
+  ep.beta = 0.0;
+  if ((rc = launch_gemm(h, w, cfg, EPI_STORE, M_KST, M_W, p.d_tasks, (int)n1, ep))) return rc;
+  ep.C = cv;
+  ep.ldc = Mp;
+  ep.alpha = -1.0;
+  ep.beta = 1.0;
+  if ((rc = launch_gemm(h, w, cfg, EPI_STORE, M_DBG_A, M_DBG_A, p.d_tasks + n1, (int)(p.tasks.size() - n1), ep))) return rc;
+  const bool cov_dev = is_device_ptr(cov);
+  double* dout = cov;
+  if (!cov_dev) {
+    if ((rc = ensure_cap(h, &h->dstage, &h->dstage_cap, (size_t)M * M))) return rc;
+    dout = h->dstage;
+  }
+  {
+    const long long tot = M * M;
+    cov_finish_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(cv, Mp, (int)M, dout);
+    h->launches++;
+    CK(cudaGetLastError());
+  }
+  if (!cov_dev) CK(cudaMemcpyAsync(cov, dout, (size_t)M * M * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (mean) CK(cudaMemcpyAsync(mean, dmean, (size_t)M * h->n_out * sizeof(double), cudaMemcpyDefault, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  p.clear();
   return 0;
 }
 

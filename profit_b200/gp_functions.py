@@ -196,11 +196,9 @@ def marginal_variance_BBQ(Xtrain, ytrain, Xpred, kernel, hyperparameters, hess_i
 def predict_f(hyp, x, y, xtest, kernel, return_full_cov=False, neig=0):
     """Posterior mean and variance from a flat hyper-parameter array (gp_functions.py:457-491).
 
-    The diagonal of K** carries sigma_n^2 (:484) and the clamp is applied after it (:488).  Only the diagonal
-    is available on the accelerated path.
+    The diagonal of K** carries sigma_n^2 (:484) and the clamp is applied after it (:488), element-wise on the whole
+    matrix when ``return_full_cov`` is set.
     """
-    if return_full_cov:
-        raise NotImplementedError("full predictive covariance is not part of the accelerated path")
     hyp = np.asarray(hyp, dtype=np.float64)
     be = shared_backend()
     Xc, yc = _train_arrays(x, y)
@@ -209,7 +207,10 @@ def predict_f(hyp, x, y, xtest, kernel, return_full_cov=False, neig=0):
     xt = np.asarray(xtest, dtype=np.float64)
     if xt.ndim == 1:
         xt = xt.reshape(-1, 1)
-    mean, vstar = be.predict(np.ascontiguousarray(xt), add_data_variance=2)   # sn^2 joins before the clamp
+    if return_full_cov:
+        mean, vstar = be.predict_cov(np.ascontiguousarray(xt), noise_on_diagonal=True)
+    else:
+        mean, vstar = be.predict(np.ascontiguousarray(xt), add_data_variance=2)   # sn^2 joins before the clamp
     if yc.ndim == 1:
         mean = mean.reshape(-1)
     return mean, vstar

@@ -88,6 +88,8 @@ for (N, D, n_ell, kern_name) in ((200, 2, 2, "RBF"), (257, 3, 1, "RBF"), (512, 8
     if n_ell == 1 and kern_name == "RBF":
         f, v = G.predict_f(theta.copy(), X, y, Xc, RBF)
         case["predict_f"] = {"mean": L(f), "var": L(v)}
+        fc, Vc = G.predict_f(theta.copy(), X, y, Xc[:40], RBF, return_full_cov=True)
+        case["predict_f"]["full_cov_first40"] = L(Vc)
     cases.append(case)
 out["synthetic"] = cases
 

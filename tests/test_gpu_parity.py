@@ -590,3 +590,35 @@ def test_objective_survives_a_singular_covariance(backend, capsys):
                                              log_scale_hyp=True)
     assert np.isfinite(nll) and np.all(np.isfinite(g)) and g.shape == (3,)
     assert "retrying with diagonal jitter" in capsys.readouterr().out
+
+
+def test_predict_f_full_covariance(backend, golden):
+    """predict_f(..., return_full_cov=True) (gp_functions.py:484-490) against the reference's matrix and the oracle."""
+    from profit_b200 import RBF, Matern52, gp_functions as gpf
+
+    c = next(c for c in golden["synthetic"] if "predict_f" in c)
+    X, y = oracle.synthetic_problem(c["N"], c["D"])
+    Xc = np.random.default_rng(c["predict"]["seed"]).random((c["predict"]["M"], c["D"]))
+    theta = np.array(c["theta"])
+    f, V = gpf.predict_f(theta.copy(), X, y, Xc[:40], RBF, return_full_cov=True)
+    ref = np.array(c["predict_f"]["full_cov_first40"])
+    assert V.shape == (40, 40)
+    assert np.max(np.abs(V - ref)) <= PRED_RTOL * np.abs(ref).max()
+    assert rel_err(np.diag(V), np.array(c["predict_f"]["var"])[:40]) <= PRED_RTOL
+    assert rel_err(f.ravel(), np.array(c["predict_f"]["mean"]).ravel()[:40]) <= PRED_RTOL
+    # larger, ragged, Matern, ARD: oracle
+    X2, y2 = oracle.synthetic_problem(700, 5)
+    th2 = np.concatenate([np.linspace(0.6, 1.2, 5), [1.5, 0.3]])
+    Xc2 = np.random.default_rng(2).random((333, 5))
+    f2, V2 = gpf.predict_f(th2.copy(), X2, y2, Xc2, Matern52, return_full_cov=True)
+    fo, Vo = oracle.predict_f_full_cov(th2, X2, y2, Xc2, oracle.matern52)
+    assert np.max(np.abs(V2 - Vo)) <= PRED_RTOL * np.abs(Vo).max() and np.allclose(V2, V2.T, rtol=0, atol=1e-12)
+    assert rel_err(f2.ravel(), fo.ravel()) <= PRED_RTOL
+    # device output buffer
+    import torch
+
+    backend.set_train(X2, y2)
+    backend.factorize(1, th2)
+    out = torch.empty((333, 333), dtype=torch.float64, device="cuda:0")
+    backend.predict_cov(Xc2, noise_on_diagonal=True, want_mean=False, out_cov=out)
+    assert np.array_equal(out.cpu().numpy(), V2)

@@ -203,3 +203,13 @@ def test_acquisition_oracle_reproduces_reference_losses():
         assert A.pick(np.array(c["loss"])) == c["argmax"]
     mp = k["masked_pick"]
     assert A.pick(np.array(C["simple_exploration"]["loss"]), mp["visited"]) == mp["expect"]
+
+
+def test_oracle_full_covariance_matches_reference(golden):
+    c = next(c for c in golden["synthetic"] if "predict_f" in c)
+    X, y = oracle.synthetic_problem(c["N"], c["D"])
+    Xc = np.random.default_rng(c["predict"]["seed"]).random((c["predict"]["M"], c["D"]))[:40]
+    f, V = oracle.predict_f_full_cov(np.array(c["theta"]), X, y, Xc, oracle.rbf)
+    ref = np.array(c["predict_f"]["full_cov_first40"])
+    assert np.max(np.abs(V - ref)) <= 1e-10 * np.abs(ref).max()
+    assert np.allclose(f.ravel(), np.array(c["predict_f"]["mean"]).ravel()[:40], rtol=1e-9, atol=1e-12)
