@@ -80,6 +80,14 @@ struct Workspace {
   double *Lbuf = nullptr, *Ubuf = nullptr, *Wbuf = nullptr, *Dinv = nullptr;
   double *logdet = nullptr, *alpha = nullptr;
   Plan potrf, trtri, syrk;
+  // Early triangular inverse: the sub-trees of the trtri recursion that only need the leading blocks of L run on a
+  // low-priority stream while the Cholesky is still in its chain-bound second half (see build_trtri_plan).
+  static constexpr int MAX_PHASE = 4;
+  int n_phase = 0;
+  Plan trtri_phase[MAX_PHASE];   // phase i: nodes inside [0, phase_cut[i]) that are not in an earlier phase
+  int phase_cut[MAX_PHASE] = {}; // in 128-blocks
+  int phase_ev[MAX_PHASE] = {};  // potrf-plan event after which L[0:cut, 0:cut] is final
+  Plan trtri_late;               // the remaining nodes
   std::map<std::pair<int, int>, CUtensorMap> maps;
 };
 
@@ -89,6 +97,8 @@ struct gpb_handle_s {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;   // high-priority panel stream for the Cholesky look-ahead
+  cudaStream_t stream3 = nullptr;   // low-priority stream of the early triangular inverse
+  cudaEvent_t ev_early = nullptr;   // recorded on stream3 after the last early phase
   std::vector<cudaEvent_t> events;
   std::string err;
   EncodeTiledFn encode = nullptr;
@@ -285,6 +295,9 @@ int g_diag4 = 1;                // rank-4 diagonal-block kernel (env GPB_DIAG4=0
 int g_pdl = 1;                  // programmatic dependent launch along the panel chain (env GPB_PDL)
 int g_tail_blocks = 32;         // the last this-many block columns use single-block panels (env GPB_TAIL_BLOCKS)
 int g_lookahead = 1;            // overlap the next panel factorisation with the trailing update (env GPB_LOOKAHEAD)
+int g_early_trtri = 1;          // start the triangular inverse of the leading blocks during the Cholesky (env GPB_EARLY_TRTRI)
+int g_early_cfg = CFG_32x128;   // tiles of the early phases: short CTAs delay the trailing updates least; -1 = as late (env GPB_EARLY_CFG)
+int g_early_mask = 0xF;         // which of the cut points {1/4, 1/2, 3/4, 7/8} are used (env GPB_EARLY_MASK)
 
 // Small launches are latency-bound (one CTA takes ~15 us for a 128x64x128 tile on its own SM): cut the tiles finer
 // so the same work spreads over more SMs.  `coarse` is the configuration used for large launches.
@@ -358,6 +371,21 @@ void build_potrf_plan(Workspace& w) {
   auto evP = [&](int J) { return J; };
   auto evM = [&](int J) { return nJ + J; };
   p.num_events = la ? 2 * nJ : 0;
+  // Cut points of the early triangular inverse: L[0:c, 0:c] is final once the panel that contains block column
+  // c - 1 has been factored and solved (event evP of that panel).
+  w.n_phase = 0;
+  if (la && g_early_trtri && Nb >= 48) {   // below ~6k rows the whole factorisation is chain-bound: nothing to gain
+    const int cuts[Workspace::MAX_PHASE] = {Nb / 4, Nb / 2, 3 * Nb / 4, 7 * Nb / 8};
+    for (int ci = 0; ci < Workspace::MAX_PHASE; ++ci) {
+      if (!((g_early_mask >> ci) & 1)) continue;
+      const int c = cuts[ci];
+      int J = 0;
+      while (pb[J + 1] < c) ++J;
+      w.phase_cut[w.n_phase] = c;
+      w.phase_ev[w.n_phase] = evP(J);
+      ++w.n_phase;
+    }
+  }
 
   // Programmatic dependent launch pays off only while the chain is the bottleneck (measured: potrf N=4096
   // 2.50 -> 2.39 ms, but N=8192 8.30 -> 8.60 ms: early-resident dependents then take SMs from the updates).
@@ -442,21 +470,20 @@ int build_nodes(int a, int b, std::vector<Node>& out) {
   return hgt;
 }
 
-void build_trtri_plan(Workspace& w) {
-  Plan& p = w.trtri;
+// Emit the nodes selected by `pick` level by level into plan p.
+template <class Pick>
+void emit_trtri_nodes(Plan& p, const std::vector<Node>& nodes, int top, int cfg, Pick pick, int force_cfg = -1) {
   p.clear();
-  const int Nb = (int)w.Nb, cfg = g_cfg_update;
-  std::vector<Node> nodes;
-  const int top = build_nodes(0, Nb, nodes);
   for (int hgt = 1; hgt <= top; ++hgt) {
     int nblk = 0;
     for (const Node& nd : nodes)
-      if (nd.height == hgt) nblk += (nd.mid - nd.a) * (nd.b - nd.mid);
-    const int hc = cfg_for_blocks(cfg, nblk);
+      if (nd.height == hgt && pick(nd)) nblk += (nd.mid - nd.a) * (nd.b - nd.mid);
+    if (nblk == 0) continue;
+    const int hc = force_cfg >= 0 ? force_cfg : cfg_for_blocks(cfg, nblk);
     {  // T = U11 L21^T  -> scratch in the strict upper triangle of Lbuf
       TaskSink s(p);
       for (const Node& nd : nodes)
-        if (nd.height == hgt)
+        if (nd.height == hgt && pick(nd))
           for (int m = nd.a; m < nd.mid; ++m)
             for (int n = nd.mid; n < nd.b; ++n)
               s.block(hc, m * 128, m * 128, n * 128, m * 128, 8 * (nd.mid - m), m * 128, n * 128);
@@ -465,13 +492,31 @@ void build_trtri_plan(Workspace& w) {
     {  // U12 = -T W22^T, mirrored into W21
       TaskSink s(p);
       for (const Node& nd : nodes)
-        if (nd.height == hgt)
+        if (nd.height == hgt && pick(nd))
           for (int m = nd.a; m < nd.mid; ++m)
             for (int n = nd.mid; n < nd.b; ++n)
               s.block(hc, m * 128, nd.mid * 128, n * 128, nd.mid * 128, 8 * (n - nd.mid + 1), m * 128, n * 128);
       s.finish(hc, EPI_STORE, M_L, M_W, M_U, M_W, -1.0, 0.0, true);
     }
   }
+}
+
+// w.trtri: every node (used when L is given, e.g. gpb_invert_cholesky).  w.trtri_phase[i] + w.trtri_late: the same
+// nodes split by the right end of their block range, so that phase i can run as soon as the Cholesky has finished
+// the block columns left of phase_cut[i] (a node [a, b) only reads L[a:b, a:b] and the U / W of its children).
+void build_trtri_plan(Workspace& w) {
+  const int Nb = (int)w.Nb, cfg = g_cfg_update;
+  std::vector<Node> nodes;
+  const int top = build_nodes(0, Nb, nodes);
+  emit_trtri_nodes(w.trtri, nodes, top, cfg, [](const Node&) { return true; });
+  auto phase_of = [&](const Node& nd) {
+    for (int i = 0; i < w.n_phase; ++i)
+      if (nd.b <= w.phase_cut[i]) return i;
+    return w.n_phase;
+  };
+  for (int i = 0; i < w.n_phase; ++i)
+    emit_trtri_nodes(w.trtri_phase[i], nodes, top, cfg, [&](const Node& nd) { return phase_of(nd) == i; }, g_early_cfg);
+  emit_trtri_nodes(w.trtri_late, nodes, top, cfg, [&](const Node& nd) { return phase_of(nd) == w.n_phase; });
 }
 
 void build_syrk_plan(Workspace& w) {
@@ -496,8 +541,8 @@ int upload_plan(H* h, Plan& p) {
   return 0;
 }
 
-int run_plan(H* h, Workspace& w, Plan& p, bool factor_diag) {
-  const bool multi = p.num_events > 0;
+int run_plan(H* h, Workspace& w, Plan& p, bool factor_diag, cudaStream_t only_stream = nullptr) {
+  const bool multi = p.num_events > 0 && !only_stream;
   if (multi) {
     while ((int)h->events.size() < p.num_events + 2) {
       cudaEvent_t e;
@@ -509,7 +554,7 @@ int run_plan(H* h, Workspace& w, Plan& p, bool factor_diag) {
     CK(cudaStreamWaitEvent(h->stream2, h->events[p.num_events], 0));
   }
   for (const Launch& L : p.launches) {
-    cudaStream_t st = (multi && L.stream == 1) ? h->stream2 : h->stream;
+    cudaStream_t st = only_stream ? only_stream : ((multi && L.stream == 1) ? h->stream2 : h->stream);
     if (multi && L.wait_ev >= 0) CK(cudaStreamWaitEvent(st, h->events[L.wait_ev], 0));
     if (L.type == 0) {
       if (factor_diag && g_diag4) {
@@ -579,6 +624,9 @@ void free_ws(Workspace& w) {
   w.Lbuf = w.Ubuf = w.Wbuf = w.Dinv = w.logdet = w.alpha = nullptr;
   w.potrf.clear();
   w.trtri.clear();
+  w.trtri_late.clear();
+  for (Plan& p : w.trtri_phase) p.clear();
+  w.n_phase = 0;
   w.syrk.clear();
   w.maps.clear();
   w.N = w.Np = w.Nb = 0;
@@ -616,14 +664,17 @@ int ensure_inverse_buffers(H* h, Workspace& w) {
   build_syrk_plan(w);
   int rc = upload_plan(h, w.trtri);
   if (rc) return rc;
+  for (int i = 0; i < w.n_phase; ++i)
+    if ((rc = upload_plan(h, w.trtri_phase[i]))) return rc;
+  if ((rc = upload_plan(h, w.trtri_late))) return rc;
   return upload_plan(h, w.syrk);
 }
 
 // ------------------------------------------------------------------------------------------------ small kernels
 // Seed the diagonal tiles of U (= W_kk^T, upper) and W (= W_kk, lower) from the inverted diagonal blocks.
 __global__ void seed_diag_kernel(const double* __restrict__ Dinv, double* __restrict__ U, double* __restrict__ W,
-                                 long long ld) {
-  const int k = blockIdx.x;
+                                 long long ld, int k0) {
+  const int k = k0 + blockIdx.x;
   const double* src = Dinv + (long long)k * 128 * 128;
   for (int e = threadIdx.x; e < 128 * 128; e += blockDim.x) {
     const int i = e >> 7, j = e & 127;
@@ -822,7 +873,9 @@ int cross_dispatch(H* h, Workspace& w, const double* dXc, long long mc, double* 
 }
 
 // Stages shared by gpb_nll and gpb_factorize: K(theta) -> L, z, logdet.
-int assemble_and_factor(H* h) {
+// early_inverse: also queue the early phases of the triangular inverse (the caller must have called
+// ensure_inverse_buffers and must finish with triangular_inverse(h, w, true)).
+int assemble_and_factor(H* h, bool early_inverse = false) {
   Workspace& w = h->ws;
   stage_begin(h, GPB_STAGE_ASSEMBLE);
   CK(cudaMemsetAsync(h->dinfo, 0, sizeof(int), h->stream));
@@ -845,18 +898,38 @@ int assemble_and_factor(H* h) {
   stage_begin(h, GPB_STAGE_POTRF);
   rc = run_plan(h, w, w.potrf, true);
   if (rc) return rc;
+  if (early_inverse && w.n_phase > 0) {
+    // The Cholesky launches above are only queued; stream3 picks up each phase when its event fires.
+    int k0 = 0;
+    for (int i = 0; i < w.n_phase; ++i) {
+      CK(cudaStreamWaitEvent(h->stream3, h->events[w.phase_ev[i]], 0));
+      if (w.phase_cut[i] > k0) {
+        seed_diag_kernel<<<(unsigned)(w.phase_cut[i] - k0), 256, 0, h->stream3>>>(w.Dinv, w.Ubuf, w.Wbuf, w.Np, k0);
+        h->launches++;
+        CK(cudaGetLastError());
+        k0 = w.phase_cut[i];
+      }
+      if ((rc = run_plan(h, w, w.trtri_phase[i], false, h->stream3))) return rc;
+    }
+    CK(cudaEventRecord(h->ev_early, h->stream3));
+  }
   stage_end(h, GPB_STAGE_POTRF);
   return 0;
 }
 
 // U = L^-T, W = L^-1 from L and the inverted diagonal blocks.
-int triangular_inverse(H* h, Workspace& w) {
+// early_done: the phases queued by assemble_and_factor(h, true) cover the leading blocks; finish the rest.
+int triangular_inverse(H* h, Workspace& w, bool early_done = false) {
   int rc = ensure_inverse_buffers(h, w);
   if (rc) return rc;
-  seed_diag_kernel<<<(unsigned)w.Nb, 256, 0, h->stream>>>(w.Dinv, w.Ubuf, w.Wbuf, w.Np);
+  const bool early = early_done && w.n_phase > 0;
+  const int k0 = early ? w.phase_cut[w.n_phase - 1] : 0;
+  seed_diag_kernel<<<(unsigned)(w.Nb - k0), 256, 0, h->stream>>>(w.Dinv, w.Ubuf, w.Wbuf, w.Np, k0);
   h->launches++;
   CK(cudaGetLastError());
-  return run_plan(h, w, w.trtri, false);
+  if (!early) return run_plan(h, w, w.trtri, false);
+  CK(cudaStreamWaitEvent(h->stream, h->ev_early, 0));
+  return run_plan(h, w, w.trtri_late, false);
 }
 
 int compute_alpha(H* h, Workspace& w, int n_out) {
@@ -1072,14 +1145,16 @@ int gpb_create(int device, gpb_handle_t* out) {
   }
   // A blocking stream: implicitly ordered with the legacy default stream, which is what torch uses by default,
   // so device pointers handed in by the caller are safe to read without an explicit cross-stream event.
-  if (cudaStreamCreate(&h->stream) != cudaSuccess) {
-    delete h;
-    return -2;
-  }
+  // Priorities: panel chain (stream2) highest, main stream in the middle, early triangular inverse (stream3) lowest,
+  // so that the fill-in work never delays a trailing update the chain is waiting for.
   {
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
-    if (cudaStreamCreateWithPriority(&h->stream2, cudaStreamDefault, hi) != cudaSuccess) {
+    const int mid = (hi < lo - 1) ? lo - 1 : lo;   // numerically lower = higher priority
+    if (cudaStreamCreateWithPriority(&h->stream, cudaStreamDefault, mid) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&h->stream2, cudaStreamDefault, hi) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&h->stream3, cudaStreamNonBlocking, lo) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_early, cudaEventDisableTiming) != cudaSuccess) {
       delete h;
       return -2;
     }
@@ -1108,6 +1183,9 @@ int gpb_create(int device, gpb_handle_t* out) {
   if (const char* e = getenv("GPB_CFG_UPDATE")) g_cfg_update = std::max(0, std::min(1, atoi(e)));
   if (const char* e = getenv("GPB_OUTER_BLOCKS")) g_outer_blocks = std::max(0, std::min(16, atoi(e)));
   if (const char* e = getenv("GPB_LOOKAHEAD")) g_lookahead = atoi(e) != 0;
+  if (const char* e = getenv("GPB_EARLY_TRTRI")) g_early_trtri = atoi(e) != 0;
+  if (const char* e = getenv("GPB_EARLY_CFG")) g_early_cfg = atoi(e);
+  if (const char* e = getenv("GPB_EARLY_MASK")) g_early_mask = atoi(e);
   if (const char* e = getenv("GPB_FINE_BELOW")) g_fine_below = atoi(e);
   if (const char* e = getenv("GPB_PDL")) g_pdl = atoi(e) != 0;
   if (const char* e = getenv("GPB_TAIL_BLOCKS")) g_tail_blocks = std::max(0, atoi(e));
@@ -1148,6 +1226,8 @@ int gpb_destroy(gpb_handle_t h) {
   for (int s = 0; s < 3; ++s) cudaEventDestroy(h->evx[s]);
   for (cudaEvent_t e : h->events) cudaEventDestroy(e);
   cudaStreamDestroy(h->stream2);
+  cudaStreamDestroy(h->stream3);
+  cudaEventDestroy(h->ev_early);
   cudaStreamDestroy(h->stream);
   delete h;
   return 0;
@@ -1204,13 +1284,14 @@ int gpb_nll(gpb_handle_t h, int kind, const double* theta, int n_ell, int want_g
   h->factor_ready = false;
   stages_reset(h);
   stage_begin(h, GPB_STAGE_TOTAL);
-  if ((rc = assemble_and_factor(h))) return rc;
+  if (want_grad && (rc = ensure_inverse_buffers(h, w))) return rc;
+  if ((rc = assemble_and_factor(h, want_grad != 0))) return rc;
   nll_kernel<<<1, 1024, 0, h->stream>>>(w.Lbuf + w.Np * w.Np, w.Np, h->n_out, w.Np, w.N, w.logdet, (int)w.Nb, h->dscal);
   h->launches++;
   const int P = n_ell + 2, width = h->DP + 2;
   if (want_grad) {
     stage_begin(h, GPB_STAGE_TRTRI);
-    if ((rc = triangular_inverse(h, w))) return rc;
+    if ((rc = triangular_inverse(h, w, true))) return rc;
     stage_end(h, GPB_STAGE_TRTRI);
     stage_begin(h, GPB_STAGE_GRAD);
     if ((rc = compute_alpha(h, w, h->n_out))) return rc;
@@ -1271,9 +1352,10 @@ int gpb_factorize(gpb_handle_t h, int kind, const double* theta, int n_ell) {
   h->factor_ready = false;
   stages_reset(h);
   stage_begin(h, GPB_STAGE_TOTAL);
-  if ((rc = assemble_and_factor(h))) return rc;
+  if ((rc = ensure_inverse_buffers(h, w))) return rc;
+  if ((rc = assemble_and_factor(h, true))) return rc;
   stage_begin(h, GPB_STAGE_TRTRI);
-  if ((rc = triangular_inverse(h, w))) return rc;
+  if ((rc = triangular_inverse(h, w, true))) return rc;
   stage_end(h, GPB_STAGE_TRTRI);
   stage_begin(h, GPB_STAGE_GRAD);
   if ((rc = compute_alpha(h, w, h->n_out))) return rc;

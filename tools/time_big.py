@@ -1,0 +1,18 @@
+"""Stage times of NLL+gradient at the two large shapes (quick A/B of environment switches)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import oracle
+from profit_b200 import GPBackend, KIND_RBF
+be = GPBackend(0)
+for (N, D) in ((8192, 16), (16384, 10)):
+    X, y = oracle.synthetic_problem(N, D)
+    theta = np.concatenate([np.linspace(0.6, 1.2, D), [1.5, 0.3]])
+    be.set_train(X, y)
+    be.nll(KIND_RBF, theta, want_grad=True)
+    best = None
+    for _ in range(3):
+        be.nll(KIND_RBF, theta, want_grad=True)
+        st = be.stage_ms()
+        if best is None or st["total"] < best["total"]: best = st
+    print(f"N={N:6d}: potrf {best['potrf']:7.3f} trtri {best['trtri']:7.3f} syrk {best['syrk']:7.3f} total {best['total']:8.3f} ms", flush=True)
