@@ -45,8 +45,9 @@ struct Launch {
   size_t task_off;
   int ntasks;
   int epi;
-  int stream = 0;    // 0 = main stream, 1 = panel (look-ahead) stream
+  int stream = 0;    // 0 = main stream, 1 = panel (look-ahead) stream, 2 = second trailing-update stream
   int wait_ev = -1;  // event to wait for before the launch (index into the handle's event pool)
+  int wait_ev2 = -1; // optional second event
   int rec_ev = -1;   // event recorded after the launch
   int pdl = 0;       // launch with programmatic stream serialization (overlaps the launch with the previous kernel)
 };
@@ -98,6 +99,7 @@ struct gpb_handle_s {
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;   // high-priority panel stream for the Cholesky look-ahead
   cudaStream_t stream3 = nullptr;   // low-priority stream of the early triangular inverse
+  cudaStream_t stream4 = nullptr;   // second trailing-update stream (same priority as the main stream)
   cudaEvent_t ev_early = nullptr;   // recorded on stream3 after the last early phase
   std::vector<cudaEvent_t> events;
   std::string err;
@@ -295,6 +297,7 @@ int g_diag4 = 1;                // rank-4 diagonal-block kernel (env GPB_DIAG4=0
 int g_pdl = 1;                  // programmatic dependent launch along the panel chain (env GPB_PDL)
 int g_tail_blocks = 32;         // the last this-many block columns use single-block panels (env GPB_TAIL_BLOCKS)
 int g_lookahead = 1;            // overlap the next panel factorisation with the trailing update (env GPB_LOOKAHEAD)
+int g_split_t2 = 1;             // trailing updates as two interleaved halves on two streams (env GPB_SPLIT_T2)
 int g_early_trtri = 1;          // start the triangular inverse of the leading blocks during the Cholesky (env GPB_EARLY_TRTRI)
 int g_early_cfg = CFG_32x128;   // tiles of the early phases: short CTAs delay the trailing updates least; -1 = as late (env GPB_EARLY_CFG)
 int g_early_mask = 0xF;         // which of the cut points {1/4, 1/2, 3/4, 7/8} are used (env GPB_EARLY_MASK)
@@ -370,7 +373,9 @@ void build_potrf_plan(Workspace& w) {
   const int ps = la ? 1 : 0;           // stream of the panel work
   auto evP = [&](int J) { return J; };
   auto evM = [&](int J) { return nJ + J; };
-  p.num_events = la ? 2 * nJ : 0;
+  auto evM2 = [&](int J) { return 2 * nJ + J; };   // second half of a split trailing update
+  p.num_events = la ? 3 * nJ : 0;
+  std::vector<char> split(nJ, 0);
   // Cut points of the early triangular inverse: L[0:c, 0:c] is final once the panel that contains block column
   // c - 1 has been factored and solved (event evP of that panel).
   w.n_phase = 0;
@@ -424,18 +429,22 @@ void build_potrf_plan(Workspace& w) {
     if (la) p.launches.back().rec_ev = evP(J);
   };
   // columns [jb0, jb1) (in 128-blocks) updated with panel J
-  auto emit_update = [&](int J, int jb0, int jb1, int stream, int wait_ev, int rec_ev) {
+  // parity: -1 = every block column, 0 / 1 = only the even / odd ones
+  auto emit_update = [&](int J, int jb0, int jb1, int stream, int wait_ev, int rec_ev, int parity = -1, int wait_ev2 = -1) {
     const int J0 = pb[J], Je = pb[J + 1];
     TaskSink s(p);
     int nblk = 0;
-    for (int j = jb0; j < jb1; ++j) nblk += aug - j + 1;
+    for (int j = jb0; j < jb1; ++j)
+      if (parity < 0 || (j & 1) == parity) nblk += aug - j + 1;
     const int uc = cfg_for_blocks(cfg, nblk);
     for (int j = jb0; j < jb1; ++j)
-      for (int i = j; i <= aug; ++i) s.block(uc, i * 128, J0 * 128, j * 128, J0 * 128, 8 * (Je - J0), i * 128, j * 128);
+      if (parity < 0 || (j & 1) == parity)
+        for (int i = j; i <= aug; ++i) s.block(uc, i * 128, J0 * 128, j * 128, J0 * 128, 8 * (Je - J0), i * 128, j * 128);
     s.finish(uc, EPI_STORE, M_L, M_L, M_L, M_NONE, -1.0, 1.0, false);
     if (s.last >= 0) {
       p.launches[s.last].stream = stream;
       p.launches[s.last].wait_ev = wait_ev;
+      p.launches[s.last].wait_ev2 = wait_ev2;
       p.launches[s.last].rec_ev = rec_ev;
     }
     return s.last >= 0;
@@ -446,9 +455,20 @@ void build_potrf_plan(Workspace& w) {
     const int next0 = pb[J + 1], next1 = pb[J + 2];
     if (la) {
       const bool has_t2 = next1 < Nb;
-      // T2(J) first so that the big launch is queued early on the main stream
-      if (has_t2) emit_update(J, next1, Nb, 0, evP(J), evM(J));
-      emit_update(J, next0, next1, 1, J > 0 ? evM(J - 1) : -1, -1);
+      // T2(J) first so that the big launch is queued early on the main stream.  While the trailing matrix is large it
+      // goes out as two halves (even / odd block columns) on two streams: the drain of one half is covered by the
+      // other, and the column -> stream map is static, so each half only depends on its own predecessor.
+      if (has_t2) {
+        split[J] = g_split_t2 && (Nb - next1) >= 16;
+        if (split[J]) {
+          emit_update(J, next1, Nb, 0, evP(J), evM(J), 0);
+          emit_update(J, next1, Nb, 2, evP(J), evM2(J), 1);
+        } else {
+          // an unsplit update touches both parities: it follows the last split one on the other stream as well
+          emit_update(J, next1, Nb, 0, evP(J), evM(J), -1, (J > 0 && split[J - 1]) ? evM2(J - 1) : -1);
+        }
+      }
+      emit_update(J, next0, next1, 1, J > 0 ? evM(J - 1) : -1, -1, -1, (J > 0 && split[J - 1]) ? evM2(J - 1) : -1);
       emit_panel(J + 1);
     } else {
       emit_update(J, next0, Nb, 0, -1, -1);
@@ -544,7 +564,7 @@ int upload_plan(H* h, Plan& p) {
 int run_plan(H* h, Workspace& w, Plan& p, bool factor_diag, cudaStream_t only_stream = nullptr) {
   const bool multi = p.num_events > 0 && !only_stream;
   if (multi) {
-    while ((int)h->events.size() < p.num_events + 2) {
+    while ((int)h->events.size() < p.num_events + 3) {
       cudaEvent_t e;
       CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
       h->events.push_back(e);
@@ -552,10 +572,13 @@ int run_plan(H* h, Workspace& w, Plan& p, bool factor_diag, cudaStream_t only_st
     // the panel stream starts after everything already queued on the main stream
     CK(cudaEventRecord(h->events[p.num_events], h->stream));
     CK(cudaStreamWaitEvent(h->stream2, h->events[p.num_events], 0));
+    CK(cudaStreamWaitEvent(h->stream4, h->events[p.num_events], 0));
   }
   for (const Launch& L : p.launches) {
-    cudaStream_t st = only_stream ? only_stream : ((multi && L.stream == 1) ? h->stream2 : h->stream);
+    cudaStream_t st = only_stream ? only_stream
+                                  : ((multi && L.stream == 1) ? h->stream2 : (multi && L.stream == 2) ? h->stream4 : h->stream);
     if (multi && L.wait_ev >= 0) CK(cudaStreamWaitEvent(st, h->events[L.wait_ev], 0));
+    if (multi && L.wait_ev2 >= 0) CK(cudaStreamWaitEvent(st, h->events[L.wait_ev2], 0));
     if (L.type == 0) {
       if (factor_diag && g_diag4) {
         cudaLaunchConfig_t lc{};
@@ -609,6 +632,8 @@ int run_plan(H* h, Workspace& w, Plan& p, bool factor_diag, cudaStream_t only_st
     // join: the main stream continues only after the panel stream has drained
     CK(cudaEventRecord(h->events[p.num_events + 1], h->stream2));
     CK(cudaStreamWaitEvent(h->stream, h->events[p.num_events + 1], 0));
+    CK(cudaEventRecord(h->events[p.num_events + 2], h->stream4));
+    CK(cudaStreamWaitEvent(h->stream, h->events[p.num_events + 2], 0));
   }
   return 0;
 }
@@ -1154,6 +1179,7 @@ int gpb_create(int device, gpb_handle_t* out) {
     if (cudaStreamCreateWithPriority(&h->stream, cudaStreamDefault, mid) != cudaSuccess ||
         cudaStreamCreateWithPriority(&h->stream2, cudaStreamDefault, hi) != cudaSuccess ||
         cudaStreamCreateWithPriority(&h->stream3, cudaStreamNonBlocking, lo) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&h->stream4, cudaStreamNonBlocking, mid) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_early, cudaEventDisableTiming) != cudaSuccess) {
       delete h;
       return -2;
@@ -1184,6 +1210,7 @@ int gpb_create(int device, gpb_handle_t* out) {
   if (const char* e = getenv("GPB_OUTER_BLOCKS")) g_outer_blocks = std::max(0, std::min(16, atoi(e)));
   if (const char* e = getenv("GPB_LOOKAHEAD")) g_lookahead = atoi(e) != 0;
   if (const char* e = getenv("GPB_EARLY_TRTRI")) g_early_trtri = atoi(e) != 0;
+  if (const char* e = getenv("GPB_SPLIT_T2")) g_split_t2 = atoi(e) != 0;
   if (const char* e = getenv("GPB_EARLY_CFG")) g_early_cfg = atoi(e);
   if (const char* e = getenv("GPB_EARLY_MASK")) g_early_mask = atoi(e);
   if (const char* e = getenv("GPB_FINE_BELOW")) g_fine_below = atoi(e);
@@ -1227,6 +1254,7 @@ int gpb_destroy(gpb_handle_t h) {
   for (cudaEvent_t e : h->events) cudaEventDestroy(e);
   cudaStreamDestroy(h->stream2);
   cudaStreamDestroy(h->stream3);
+  cudaStreamDestroy(h->stream4);
   cudaEventDestroy(h->ev_early);
   cudaStreamDestroy(h->stream);
   delete h;

@@ -129,9 +129,13 @@ def negative_log_likelihood(hyp, X, y, kernel, eval_gradient=False, log_scale_hy
 
 
 def optimize(xtrain, ytrain, a0, kernel, fixed_sigma_n=False, eval_gradient=False, return_hess_inv=False,
-             backend=None):
+             backend=None, method="bfgs", bounds=None, options=None, return_result=False):
     """Hyper-parameter optimisation, gp_functions.py:8-69: log10 transform, SciPy ``minimize(method="bfgs")``
-    with the same arguments; the training set is uploaded once and stays resident across evaluations."""
+    with the same arguments; the training set is uploaded once and stays resident across evaluations.
+
+    ``method`` / ``bounds`` / ``options`` (extensions, defaults = the reference's call at :59-66) select another SciPy
+    driver, e.g. ``method="L-BFGS-B"`` with log10 bounds as in the reference's own test (test_kernels.py:188-194);
+    ``return_result`` returns the SciPy result object as the last element."""
     from scipy.optimize import minimize
 
     a0 = np.asarray(a0, dtype=np.float64)
@@ -150,10 +154,16 @@ def optimize(xtrain, ytrain, a0, kernel, fixed_sigma_n=False, eval_gradient=Fals
     def objective(h):
         return negative_log_likelihood(h, Xc, yc, kernel, eval_gradient, True, sigma_n, backend=backend)
 
-    opt_result = minimize(objective, a0, method="bfgs", bounds=None, jac=eval_gradient)
+    opt_result = minimize(objective, a0, method=method, bounds=bounds, jac=eval_gradient, options=options)
+    out = (10**opt_result.x,)
     if return_hess_inv:
-        return 10**opt_result.x, opt_result.hess_inv
-    return 10**opt_result.x
+        hess_inv = opt_result.hess_inv
+        if hasattr(hess_inv, "todense"):          # L-BFGS-B returns a LinearOperator
+            hess_inv = np.asarray(hess_inv.todense())
+        out += (hess_inv,)
+    if return_result:
+        out += (opt_result,)
+    return out[0] if len(out) == 1 else out
 
 
 def marginal_variance_BBQ(Xtrain, ytrain, Xpred, kernel, hyperparameters, hess_inv, fixed_sigma_n=False, alpha=None,
