@@ -77,6 +77,9 @@ dgemm_tasks_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   // one runs.  Everything above is independent of the previous kernel; everything below may read its output.
   if (gridDim.x <= 296) pdl_launch_dependents();
   pdl_wait();
+#ifdef GPB_TRACE
+  const unsigned long long trace_t0 = trace_now();
+#endif
 
   if (warp == NCW) {
     // ---------------- TMA producer ----------------
@@ -222,6 +225,11 @@ dgemm_tasks_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       ep.C[static_cast<long long>(task.aux) * ep.ldc + task.c_col + c] = s;
     }
   }
+#ifdef GPB_TRACE
+  // tag: nk | BM << 16 | (beta != 0) << 28 | (Ct != nullptr) << 29 | EPI << 30; consumer warp 0 reports for the CTA
+  if (threadIdx.x == 0)
+    trace_emit(trace_t0, gridDim.x, (unsigned)task.nk | (BM << 16) | ((ep.beta != 0.0) << 28) | ((ep.Ct != nullptr) << 29) | (EPI << 30));
+#endif
 }
 
 }  // namespace gpb

@@ -1953,4 +1953,20 @@ int gpb_debug_gemm(gpb_handle_t h, const double* A, const double* B, double* C, 
   return 0;
 }
 
+#ifdef GPB_TRACE
+// Debug build only: point the CTA trace ring at a caller-provided device buffer of cap records (4 x u64 each),
+// or read back how many records were written.
+int gpb_debug_trace(gpb_handle_t h, unsigned long long* buf, unsigned int cap, unsigned int* count) {
+  if (!h) return -1;
+  CK(cudaSetDevice(h->device));
+  CK(cudaDeviceSynchronize());
+  if (count) CK(cudaMemcpyFromSymbol(count, g_trace_count, sizeof(unsigned int)));
+  unsigned int zero = 0;
+  CK(cudaMemcpyToSymbol(g_trace_buf, &buf, sizeof(buf)));
+  CK(cudaMemcpyToSymbol(g_trace_cap, &cap, sizeof(cap)));
+  CK(cudaMemcpyToSymbol(g_trace_count, &zero, sizeof(zero)));
+  return 0;
+}
+#endif
+
 }  // extern "C"

@@ -325,6 +325,9 @@ potrf_diag4_kernel(double* __restrict__ A, long long lda, int k0, double* __rest
   double* Ablk = A + (long long)k0 * lda + k0;
   pdl_launch_dependents();
   pdl_wait();
+#ifdef GPB_TRACE
+  const unsigned long long trace_t0 = trace_now();
+#endif
 
   double av[DIAG_NA][4], rv[DIAG_NA][4];
 #pragma unroll
@@ -366,6 +369,9 @@ potrf_diag4_kernel(double* __restrict__ A, long long lda, int k0, double* __rest
       Ablk[(long long)i * lda + k] = l;
       Winv[i * NB + k] = w;
     }
+#ifdef GPB_TRACE
+  if (tid == 0) trace_emit(trace_t0, 1u, 0xD1A6u);
+#endif
 }
 
 }  // namespace gpb

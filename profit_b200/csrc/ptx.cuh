@@ -81,6 +81,30 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+#ifdef GPB_TRACE
+// Debug build only (tools/trace_potrf.py): every CTA leaves {smid, start, end, grid, tag} in a global ring so that
+// the occupancy timeline of a factorisation can be reconstructed.  Not compiled into the product library.
+__device__ unsigned long long* g_trace_buf = nullptr;
+__device__ unsigned int g_trace_cap = 0;
+__device__ unsigned int g_trace_count = 0;
+__device__ __forceinline__ unsigned long long trace_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void trace_emit(unsigned long long t0, unsigned int grid, unsigned int tag) {
+  if (g_trace_buf == nullptr) return;
+  const unsigned int i = atomicAdd(&g_trace_count, 1u);
+  if (i >= g_trace_cap) return;
+  unsigned int smid;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+  g_trace_buf[4 * i + 0] = t0;
+  g_trace_buf[4 * i + 1] = trace_now();
+  g_trace_buf[4 * i + 2] = ((unsigned long long)grid << 32) | smid;
+  g_trace_buf[4 * i + 3] = tag;
+}
+#endif
+
 __device__ __forceinline__ double2 lds128(uint32_t addr) {
   double2 v;
   asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
