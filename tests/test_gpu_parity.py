@@ -622,3 +622,47 @@ def test_predict_f_full_covariance(backend, golden):
     out = torch.empty((333, 333), dtype=torch.float64, device="cuda:0")
     backend.predict_cov(Xc2, noise_on_diagonal=True, want_mean=False, out_cov=out)
     assert np.array_equal(out.cpu().numpy(), V2)
+
+
+# ------------------------------------------------------------------------------------------ reference at BASELINE shapes
+@pytest.fixture(scope="module")
+def reference_large():
+    import json
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(root, "tests", "golden", "reference_baseline_shapes.json")) as f:
+        return json.load(f)
+
+
+def test_c1_nll_gradient_against_the_unmodified_reference(backend, reference_large):
+    """BASELINE configs[1] (RBF ARD, N=4096, D=8): the reference's own negative_log_likelihood_cholesky, called
+    directly at full size (make_golden_reference_large.py), NLL and every gradient component to 1e-9 relative."""
+    from profit_b200 import RBF, gp_functions as gpf
+
+    c = reference_large["c1_nll"]
+    X, y = oracle.synthetic_problem(c["N"], c["D"])
+    nll, g = gpf.negative_log_likelihood_cholesky(np.array(c["theta"]), X, y, RBF, eval_gradient=True)
+    assert abs(nll - c["nll"]) <= NLL_RTOL * abs(c["nll"])
+    assert grad_err(g, c["grad"]) <= NLL_RTOL
+
+
+def test_c3_predict_against_the_unmodified_reference(reference_large):
+    """BASELINE configs[3] training size (N=8192, D=10, RBF ARD): the unmodified GPSurrogate.predict on 4096
+    candidates (4 chunks, each refactorising) against one device predict; mean and variance to 1e-8 relative."""
+    from profit_b200 import B200GPSurrogate
+
+    c = reference_large["c3_predict"]
+    X, y = oracle.synthetic_problem(c["N"], c["D"])
+    th = np.array(c["theta"])
+    s = B200GPSurrogate()
+    s.Xtrain, s.ytrain, s.ndim, s.trained = X, y, c["D"], True
+    s.kernel = s.select_kernel("RBF")
+    s.hyperparameters = {"length_scale": th[:-2].copy(), "sigma_f": th[-2:-1].copy(), "sigma_n": th[-1:].copy()}
+    Xc = np.random.default_rng(c["seed"]).random((c["M"], c["D"]))
+    m, v = s.predict(Xc)
+    assert m.shape == (c["M"], 1) and v.shape == (c["M"], 1)
+    mref, vref = np.array(c["mean"]), np.array(c["var"])
+    assert np.max(np.abs(m.ravel() - mref)) <= PRED_RTOL * np.abs(mref).max()
+    assert rel_err(m.ravel(), mref) <= 1e-6          # element-wise too, away from zero crossings of the mean
+    assert rel_err(v.ravel(), vref) <= PRED_RTOL

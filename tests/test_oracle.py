@@ -213,3 +213,18 @@ def test_oracle_full_covariance_matches_reference(golden):
     ref = np.array(c["predict_f"]["full_cov_first40"])
     assert np.max(np.abs(V - ref)) <= 1e-10 * np.abs(ref).max()
     assert np.allclose(f.ravel(), np.array(c["predict_f"]["mean"]).ravel()[:40], rtol=1e-9, atol=1e-12)
+
+
+def test_oracle_against_the_reference_at_c1_shape():
+    """The blocked oracle NLL + gradient at BASELINE configs[1] (N=4096, D=8) against the unmodified reference's value
+    (tests/golden/reference_baseline_shapes.json): this pins the large-N restatement the GPU tests lean on."""
+    import json
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(root, "tests", "golden", "reference_baseline_shapes.json")) as f:
+        c = json.load(f)["c1_nll"]
+    X, y = oracle.synthetic_problem(c["N"], c["D"])
+    nll, g = oracle.nll_cholesky(np.array(c["theta"]), X, y, oracle.rbf, eval_gradient=True, block=512)
+    assert abs(nll - c["nll"]) <= 1e-11 * abs(c["nll"])
+    assert np.max(np.abs(g - np.array(c["grad"])) / np.abs(c["grad"])) <= 1e-9
