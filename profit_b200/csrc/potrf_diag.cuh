@@ -341,11 +341,21 @@ potrf_diag4_kernel(double* __restrict__ A, long long lda, int k0, double* __rest
         if (k == i) rv[a][b] = 1.0;
       }
     }
+#ifdef GPB_TRACE
+  // phase stamps (debug build): the loads above are consumed by the first block, so time them with a dependent sum
+  double trace_sum = 0.0;
+  for (int a = 0; a < DIAG_NA; ++a)
+    for (int b = 0; b < 4; ++b) trace_sum += av[a][b];
+  const unsigned long long trace_t1 = (trace_sum == 1.2345e300) ? 0ull : trace_now();
+#endif
 #define GPB_DIAG4_BLK(JA) diag4_block<JA>(av, rv, sm, ccomp, rcomp, ty, tx, tid, k0, n_valid, info);
   GPB_DIAG4_BLK(0) GPB_DIAG4_BLK(1) GPB_DIAG4_BLK(2) GPB_DIAG4_BLK(3) GPB_DIAG4_BLK(4) GPB_DIAG4_BLK(5)
   GPB_DIAG4_BLK(6) GPB_DIAG4_BLK(7) GPB_DIAG4_BLK(8) GPB_DIAG4_BLK(9) GPB_DIAG4_BLK(10) GPB_DIAG4_BLK(11)
   GPB_DIAG4_BLK(12) GPB_DIAG4_BLK(13) GPB_DIAG4_BLK(14) GPB_DIAG4_BLK(15)
 #undef GPB_DIAG4_BLK
+#ifdef GPB_TRACE
+  const unsigned long long trace_t2 = trace_now();
+#endif
   if (tid < NB) sm.rsv[tid] = 1.0 / sqrt(sm.dvec[tid]);
   if (logdet != nullptr && tid >= 128 && tid < 160) {
     const int lane = tid - 128;
@@ -370,7 +380,11 @@ potrf_diag4_kernel(double* __restrict__ A, long long lda, int k0, double* __rest
       Winv[i * NB + k] = w;
     }
 #ifdef GPB_TRACE
-  if (tid == 0) trace_emit(trace_t0, 1u, 0xD1A6u);
+  if (tid == 0) {
+    trace_emit(trace_t0, 1u, 0xD1A6u);
+    trace_emit(trace_t1, 2u, 0xD1A7u);   // load phase ends at t0 of this record
+    trace_emit(trace_t2, 3u, 0xD1A8u);   // compute phase ends at t0 of this record
+  }
 #endif
 }
 

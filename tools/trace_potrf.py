@@ -42,6 +42,10 @@ tag = rec[:, 3].astype(np.int64)
 base = t0.min()
 t0, t1 = (t0 - base) * 1e-6, (t1 - base) * 1e-6      # ms
 nk, bm, has_beta, has_ct = tag & 0xFFFF, (tag >> 16) & 0xFFF, (tag >> 28) & 1, (tag >> 29) & 1
+keep = (tag != 0xD1A7) & (tag != 0xD1A8)      # phase stamps of the diag kernel, analysed at the end
+rec_all, tag_all = rec, tag
+rec, t0, t1, grid, tag, nk, bm, has_beta, has_ct = (a[keep] for a in (rec, t0, t1, grid, tag, nk, bm, has_beta, has_ct))
+n = len(rec)
 is_diag = tag == 0xD1A6
 cls = np.where(is_diag, 0, np.where(has_beta == 1, np.where(nk >= 16, 1, 2), np.where(has_ct == 1, 4, np.where(bm == 64, 3, 5))))
 names = ["diag", "update K>=256", "update K=128", "panel solve", "trtri(U,W)", "other beta=0 (T, syrk, early)"]
@@ -61,3 +65,13 @@ for a, b in zip(edges[:-1], edges[1:]):
     tot = ov.sum() / (b - a)
     parts = [ov[cls == c].sum() / (b - a) for c in range(len(names))]
     print(f"{a:7.1f}  {tot:6.1f}  " + " ".join(f"{p:6.1f}" for p in parts))
+# diag kernel phases: records 0xD1A6 (start..end), 0xD1A7 (t0 = loads done), 0xD1A8 (t0 = compute done)
+ra, rb, rc = rec_all[tag_all == 0xD1A6], rec_all[tag_all == 0xD1A7], rec_all[tag_all == 0xD1A8]
+if len(ra) and len(ra) == len(rb) == len(rc):
+    o = lambda r: r[np.argsort(r[:, 1])]
+    ra, rb, rc = o(ra), o(rb), o(rc)
+    load = (rb[:, 0].astype(np.float64) - ra[:, 0].astype(np.float64)) * 1e-3
+    comp = (rc[:, 0].astype(np.float64) - rb[:, 0].astype(np.float64)) * 1e-3
+    store = (ra[:, 1].astype(np.float64) - rc[:, 0].astype(np.float64)) * 1e-3
+    print(f"diag kernel phases (us): load {load.mean():.1f} (max {load.max():.1f}), compute {comp.mean():.1f}, "
+          f"finalise+store {store.mean():.1f}")
