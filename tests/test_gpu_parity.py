@@ -666,3 +666,57 @@ def test_c3_predict_against_the_unmodified_reference(reference_large):
     assert np.max(np.abs(m.ravel() - mref)) <= PRED_RTOL * np.abs(mref).max()
     assert rel_err(m.ravel(), mref) <= 1e-6          # element-wise too, away from zero crossings of the mean
     assert rel_err(v.ravel(), vref) <= PRED_RTOL
+
+
+def test_maximum_size_indexing_beyond_2_pow_31_elements():
+    """N = 47 002 (N^2 > 2^31, not a multiple of 128): every point has exactly one correlated partner N/2 rows away, so
+    K = [[a I, b I], [b I, a I]] up to terms below 1e-80, and NLL, gradient, mean and variance have closed forms from
+    2x2 blocks.  The partner sits in a far off-diagonal tile, which exercises the 64-bit tile addressing of the
+    assembly, the panel solves, the trailing updates, the inverse and the predict GEMM at a size near the
+    largest a B200 holds comfortably (three N x N fp64 matrices = 53 GB)."""
+    import torch
+
+    from profit_b200 import GPBackend
+
+    free, _ = torch.cuda.mem_get_info(0)
+    if free < 80e9:
+        pytest.skip("needs ~60 GB of free device memory")
+    N, h = 47002, 23501
+    ell, sf, sn = 0.05, 1.3, 0.4
+    i = np.arange(N)
+    X = np.stack([(i % h).astype(float), 0.02 * (i // h)], axis=1)
+    y = np.sin(0.37 * i) + 0.1 * np.cos(1.1 * i)
+    be = GPBackend(0)
+    try:
+        be.set_train(X, y.reshape(-1, 1))
+        nll, g = be.nll(0, np.array([ell, sf, sn]), want_grad=True)
+        Xc = X[[0, 1, 77, h - 1, h, N - 1]]
+        mean, var = be.predict(Xc)
+    finally:
+        be.close()
+    # closed form from the 2x2 blocks [[a, b], [b, a]]
+    r2 = (0.02 / ell) ** 2
+    e = np.exp(-0.5 * r2)
+    a, b = sf**2 + sn**2, sf**2 * e
+    y1, y2 = y[:h], y[h:]
+    sp, sm = a + b, a - b
+    quad = ((y1 + y2) ** 2 / (2 * sp) + (y1 - y2) ** 2 / (2 * sm)).sum()
+    ref_nll = 0.5 * quad + 0.5 * h * (np.log(sp) + np.log(sm)) + 0.5 * N * np.log(2 * np.pi)
+    assert abs(nll - ref_nll) <= NLL_RTOL * abs(ref_nll)
+    # d/dtheta of the pair terms: da, db for theta in (ell, sf, sn)
+    da = np.array([0.0, 2 * sf, 2 * sn])
+    db = np.array([sf**2 * e * r2 / ell, 2 * sf * e, 0.0])
+    u2, v2 = ((y1 + y2) ** 2).sum(), ((y1 - y2) ** 2).sum()
+    ref_g = 0.5 * (h * ((da + db) / sp + (da - db) / sm) - (da + db) * u2 / (2 * sp**2) - (da - db) * v2 / (2 * sm**2))
+    assert grad_err(g, ref_g) <= NLL_RTOL
+    # prediction at training points: k* = (sf^2, b) on (self, partner)
+    idx = np.array([0, 1, 77, h - 1, h, N - 1])
+    partner = (idx + h) % N
+    det = a * a - b * b
+    ks, kp = sf**2, b
+    al_self = (a * y[idx] - b * y[partner]) / det
+    al_part = (a * y[partner] - b * y[idx]) / det
+    ref_mean = ks * al_self + kp * al_part
+    ref_var = sf**2 - (a * ks * ks - 2 * b * ks * kp + a * kp * kp) / det + sn**2
+    assert np.allclose(mean.ravel(), ref_mean, rtol=PRED_RTOL, atol=1e-12)
+    assert np.allclose(var, ref_var, rtol=PRED_RTOL)
