@@ -720,3 +720,19 @@ def test_maximum_size_indexing_beyond_2_pow_31_elements():
     ref_var = sf**2 - (a * ks * ks - 2 * b * ks * kp + a * kp * kp) / det + sn**2
     assert np.allclose(mean.ravel(), ref_mean, rtol=PRED_RTOL, atol=1e-12)
     assert np.allclose(var, ref_var, rtol=PRED_RTOL)
+
+
+def test_overlapped_schedule_is_bit_identical_to_the_serial_one(built_lib):
+    """The look-ahead panel stream, the split trailing updates and the early triangular inverse only reorder
+    independent tile tasks: NLL, gradient and predictions must equal, bit for bit, those of the same plan issued in
+    dependency order on one stream (GPB_LOOKAHEAD=0 GPB_SPLIT_T2=0 GPB_EARLY_TRTRI=0), and repeat exactly.
+    Any difference is a missing dependency (tools/stress_streams.py; the full sweep is in profiles/)."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, GPB_STRESS_QUICK="1")
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "stress_streams.py")], env=env, capture_output=True,
+                         text=True, timeout=600)
+    assert out.returncode == 0 and "stress ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
