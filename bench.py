@@ -156,6 +156,41 @@ def cpu_nll_grad_sample(n_sample, steps=1):
             "sample_seconds": best, "scaled_seconds": full}
 
 
+def cpu_predict_sample(n_train=4096, chunk=1024, chunks=2):
+    """CPU baseline of the candidate-prediction leg: the oracle port of GPSurrogate.predict on a
+    bounded sample, both as the reference behaves (every call rebuilds alpha and K^-1, custom_surrogate.py:24-45,
+    114-116) and with the factor cached once.  The sample runs at N=n_train and is scaled to N=8192: factorisation with
+    (N/n)^3, the per-candidate work (kernel row + K^-1 quadratic form) with (N/n)^2."""
+    import oracle
+    from threadpoolctl import threadpool_info, threadpool_limits
+
+    X, y = oracle.synthetic_problem(n_train, DIM)
+    th = theta_ref(DIM)
+    ell, sf, sn = th[:-2], th[-2], th[-1]
+    Xc = np.random.default_rng(2).random((chunk * chunks, DIM))
+    ncpu = len(os.sched_getaffinity(0))
+    with threadpool_limits(limits=ncpu):
+        cores = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+        t0 = time.perf_counter()
+        alpha, Kinv = oracle.predict_cached_factor(X, y, oracle.matern52, ell, sf, sn)
+        t_factor = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        for c in range(chunks):
+            Ks = oracle.matern52(X, Xc[c * chunk:(c + 1) * chunk], ell, sf)
+            _mean = Ks.T @ alpha
+            _var = np.maximum(sf**2 - np.einsum("ic,ic->c", Ks, Kinv @ Ks), 1e-10) + sn**2
+        t_chunk = (time.perf_counter() - t0) / chunks
+    r = N_TRAIN_PRED / n_train
+    cached = chunk / (t_chunk * r**2)
+    uncached = chunk / (t_chunk * r**2 + t_factor * r**3)
+    return {"value": cached, "unit": "candidates/s", "cores": cores, "kind": "port",
+            "uncached_value": uncached,
+            "sample": f"oracle port of GPSurrogate.predict at N={n_train}, D={DIM} Matern-5/2: factor (alpha, K^-1) "
+                      f"{t_factor:.2f} s, {chunks} chunks of {chunk} candidates {t_chunk:.2f} s each; scaled to N={N_TRAIN_PRED} "
+                      f"(factor x{r**3:.0f}, chunk x{r**2:.0f}): {cached:.0f} candidates/s with the factor cached, "
+                      f"{uncached:.1f} candidates/s when every {chunk}-candidate call refactorises like the reference"}
+
+
 def unmodified_reference_sample(n=2048):
     """If the unmodified reference is installed (baseline/_ref, git-ignored), time ITS
     negative_log_likelihood_cholesky(eval_gradient=True) once on a small RBF problem.  Informational: the reference has
@@ -404,7 +439,11 @@ def run_gpu(args):
     if pred is not None and pred["variance_gemm_tflops"]:
         pred["roofline"] = {"bound": "tensor", "achieved": pred["variance_gemm_tflops"], "peak": peak,
                             "unit": "TFLOP/s", "frac": pred["variance_gemm_tflops"] / peak, "traffic": None}
-    cpu = cpu_nll_grad_sample(args.cpu_sample_n) if not args.skip_cpu else None
+    # CPU baselines: rank 0 of the single-GPU run only (the scaling runs would just repeat them)
+    want_cpu = not args.skip_cpu and world == 1
+    cpu = cpu_nll_grad_sample(args.cpu_sample_n) if want_cpu else None
+    if pred is not None and want_cpu:
+        pred["cpu_baseline"] = cpu_predict_sample()
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
