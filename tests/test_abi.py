@@ -20,7 +20,8 @@ def _header_symbols():
 def test_header_declares_the_expected_entry_points():
     syms = _header_symbols()
     for must in ("gpb_create", "gpb_destroy", "gpb_set_train", "gpb_nll", "gpb_factorize", "gpb_predict",
-                 "gpb_kernel_matrix", "gpb_cholesky", "gpb_invert_cholesky", "gpb_solve_cholesky", "gpb_argmax"):
+                 "gpb_kernel_matrix", "gpb_cholesky", "gpb_invert_cholesky", "gpb_solve_cholesky", "gpb_argmax",
+                 "gpb_append_train", "gpb_acq_prepare", "gpb_acquire", "gpb_predict_cov", "gpb_marginal_variance"):
         assert must in syms
 
 

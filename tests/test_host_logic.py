@@ -34,6 +34,22 @@ class OracleBackedFake:
         kern = oracle.rbf if kind == 0 else oracle.matern52
         return oracle.nll_cholesky(np.asarray(theta), self.X, self.y, kern, eval_gradient=want_grad)
 
+    # -- what the predict / add_training_data plumbing touches
+    def factorize(self, kind, theta):
+        self.factorizations = getattr(self, "factorizations", 0) + 1
+        self.kind, self.theta = kind, np.array(theta)
+
+    def append_train(self, X, y):
+        self.appends = getattr(self, "appends", 0) + 1
+        self.X, self.y = np.vstack([self.X, X]), np.vstack([self.y.reshape(len(self.X), -1), y])
+        self.resident_key = self.factor_key = None        # as GPBackend.append_train does; the caller re-keys
+
+    def predict(self, Xc, add_data_variance=True, **_):
+        kern = oracle.rbf if self.kind == 0 else oracle.matern52
+        m, v = oracle.predict(self.X, self.y.reshape(len(self.X), -1), np.asarray(Xc), kern, self.theta[:-2],
+                              self.theta[-2], self.theta[-1], add_data_variance=bool(add_data_variance))
+        return m, v.ravel()
+
 
 def test_select_kernel():
     assert kernels.select_kernel("RBF") is kernels.RBF
@@ -200,3 +216,61 @@ def test_registers_with_profit_when_available():
     env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + "/root/reference", PYTHONDONTWRITEBYTECODE="1")
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "registered" in out.stdout, out.stderr
+
+
+def test_add_training_data_extends_the_factor_only_when_it_is_current():
+    """custom_surrogate.py:122-134 with the in-place extension: append when the device holds the factor of exactly
+    this (data, hyper-parameters, kernel); otherwise leave it to the next predict, which re-uploads and refactorises."""
+    rng = np.random.default_rng(1)
+    X, y = rng.random((40, 2)), rng.random((40, 1))
+    s = B200GPSurrogate()
+    fake = OracleBackedFake()
+    s._backend = fake
+    s.Xtrain, s.ytrain, s.ndim, s.trained = X[:30], y[:30], 2, True
+    s.kernel = s.select_kernel("RBF")
+    s.hyperparameters = {"length_scale": np.array([0.7]), "sigma_f": np.array([1.2]), "sigma_n": np.array([0.2])}
+    Xc = rng.random((5, 2))
+    s.add_training_data(X[30:31], y[30:31])                      # nothing resident yet: no append, no factorisation
+    assert getattr(fake, "appends", 0) == 0 and getattr(fake, "factorizations", 0) == 0
+    m0, v0 = s.predict(Xc)
+    assert fake.factorizations == 1 and len(fake.X) == 31
+    s.add_training_data(X[31:33], y[31:33])                      # factor is current: extended in place
+    assert fake.appends == 1 and len(fake.X) == 33 and s.Xtrain.shape[0] == 33
+    m1, v1 = s.predict(Xc)
+    assert fake.factorizations == 1                              # ... and the next predict does not refactorise
+    rm, rv = oracle.predict(X[:33], y[:33], Xc, oracle.rbf, np.array([0.7]), 1.2, 0.2)
+    assert np.allclose(m1, rm) and np.allclose(v1.ravel(), rv.ravel())
+    s.hyperparameters["sigma_f"] = np.array([1.5])               # stale factor: no append, refactorise on demand
+    s.add_training_data(X[33:34], y[33:34])
+    assert fake.appends == 1
+    s.predict(Xc)
+    assert fake.factorizations == 2 and len(fake.X) == 34
+    s.set_ytrain(s.ytrain * 2.0)                                 # new y: a plain re-upload + refactorisation
+    s.add_training_data(X[34:35], y[34:35])
+    assert fake.appends == 1
+    s.predict(Xc)
+    assert fake.factorizations == 3 and len(fake.X) == 35
+
+
+def test_acquisition_twins_mirror_the_reference_registry():
+    from profit_b200 import acquisition as acq
+
+    labels = ("simple_exploration", "exploration_with_distance_penalty", "weighted_exploration",
+              "probability_of_improvement", "expected_improvement", "expected_improvement_2", "alternating_exploration")
+    for label in labels:
+        cls = acq._RefBase.labels["b200_" + label]
+        assert cls is acq._TWINS[label] and issubclass(cls, acq.DeviceAcquisitionFunction)
+    # constructor defaults = profit/defaults.py:93-126
+    Xp = np.zeros((4, 2))
+    assert acq.SimpleExploration(Xp, None, None).parameters == {"use_marginal_variance": False}
+    assert acq.ExplorationWithDistancePenalty(Xp, None, None).parameters == {"use_marginal_variance": False, "weight": 10}
+    assert acq.WeightedExploration(Xp, None, None).parameters == {"weight": 0.5, "use_marginal_variance": False}
+    assert acq.ExpectedImprovement(Xp, None, None).parameters == {"exploration_factor": 0.01, "find_min": False}
+    assert acq.ExpectedImprovement2(Xp, None, None).parameters == {"exploration_factor": 0.01, "find_min": False}
+    alt = acq.AlternatingAF(Xp, None, None)
+    assert alt.parameters == {"alternating_freq": 1} and alt.current_af is alt.exploration
+    alt.set_al_parameters(krun=3, unknown=1)
+    assert alt.al_parameters["krun"] == 3
+    alt.set_al_parameters(krun=0)
+    with pytest.raises(TypeError, match="B200GPSurrogate"):      # no host path: a foreign surrogate is refused
+        acq.SimpleExploration(Xp, object(), None).calculate_loss()
