@@ -14,6 +14,10 @@
  *     matrix is not SPD -> the Python layer raises numpy.linalg.LinAlgError like gp_functions.py:143 would);
  *     < 0 = bad argument (-1), CUDA failure (-2), not ready (-3).  gpb_error_string() describes the last error.
  *   - One handle = one device + one stream; calls on a handle must be serialised by the caller.
+ *   - Stream semantics for device pointers: the handle's stream is a blocking stream, i.e. it is ordered after work
+ *     already queued on the legacy default stream (the one torch uses unless told otherwise); producers on other
+ *     streams must synchronise before the call.  Every entry point is host-synchronous: when it returns, its
+ *     outputs (host or device) are complete.
  *   - There is no CPU fallback anywhere behind this interface.
  */
 #ifndef GPB_H_
