@@ -362,20 +362,29 @@ class B200GPSurrogate(_GPBase):
 
 class B200MultiOutputGPSurrogate(_GPBase):
     """Independent GP per output column -- mirror of ``MultiOutputGPSurrogate`` ("CustomMultiOutputGP",
-    custom_surrogate.py:285-451) with ``B200GPSurrogate`` children that share one device backend."""
+    custom_surrogate.py:285-451) with ``B200GPSurrogate`` children.
 
-    def __init__(self, child=B200GPSurrogate, device=None):
+    Every child owns a device handle, so its training set and factor stay resident (a prediction over all outputs
+    does not refactorise) and the children are fitted ``concurrent`` at a time on host threads -- a single
+    evaluation cannot fill the GPU while its Cholesky walks the panel chain, independent fits overlap
+    (SURVEY.md section 8 f-3).  ``share_backend=True`` keeps one handle for all children (least memory: each
+    switch between outputs then re-uploads y and refactorises)."""
+
+    def __init__(self, child=B200GPSurrogate, device=None, concurrent=2, share_backend=False):
         super().__init__()
         self.child = child
         self.models = []
         self._device = device
+        self.concurrent = int(concurrent)
+        self.share_backend = bool(share_backend)
         self._shared_backend = None
 
     def _new_child(self):
-        m = self.child()
-        if self._shared_backend is None:
-            self._shared_backend = GPBackend(self._device)
-        m._backend = self._shared_backend
+        m = self.child(self._device) if self.child is B200GPSurrogate else self.child()
+        if self.share_backend or self._shared_backend is not None:
+            if self._shared_backend is None:
+                self._shared_backend = GPBackend(self._device)
+            m._backend = self._shared_backend
         return m
 
     def pre_train(self, X, y, *args, **kwargs):
@@ -394,9 +403,20 @@ class B200MultiOutputGPSurrogate(_GPBase):
         self.hyperparameters = dict(hyperparameters) if not self.hyperparameters else self.hyperparameters
         self.fixed_sigma_n = fixed_sigma_n or self.fixed_sigma_n
         self.models = [self._new_child() for _ in range(self.output_ndim)]
-        for dim, m in enumerate(self.models):
-            m.train(self.Xtrain, self.ytrain[:, [dim]], self.kernel, dict(self.hyperparameters), self.fixed_sigma_n,
-                    False, return_hess_inv)
+
+        def fit(dim):
+            self.models[dim].train(self.Xtrain, self.ytrain[:, [dim]], self.kernel, dict(self.hyperparameters),
+                                   self.fixed_sigma_n, False, return_hess_inv)
+
+        workers = 1 if self._shared_backend is not None else max(1, min(self.concurrent, self.output_ndim))
+        if workers == 1:
+            for dim in range(self.output_ndim):
+                fit(dim)
+        else:
+            from concurrent.futures import ThreadPoolExecutor
+
+            with ThreadPoolExecutor(max_workers=workers) as pool:     # the C calls release the GIL
+                list(pool.map(fit, range(self.output_ndim)))
         self._set_hyperparameters_from_model()
         self.trained = True
 

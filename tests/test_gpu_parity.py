@@ -417,6 +417,19 @@ def test_multi_output_surrogate_equals_independent_models(backend):
         single.train(X, Y[:, [dim]], kernel="RBF", hyperparameters=dict(hyp), eval_gradient=False)
         m, v = single.predict(Xc)
         assert np.allclose(ym[:, [dim]], m, rtol=1e-9, atol=1e-12) and np.allclose(yv[:, [dim]], v, rtol=1e-9)
+    # every child keeps its own resident factor: predicting all outputs again does not refactorise
+    assert len({id(m.backend) for m in mo.models}) == 2
+    calls = []
+    for m in mo.models:
+        orig = m.backend.factorize
+        m.backend.factorize = lambda *a, _o=orig, **k: (calls.append(1), _o(*a, **k))[1]
+    ym2, yv2 = mo.predict(Xc)
+    assert not calls and np.array_equal(ym, ym2) and np.array_equal(yv, yv2)
+    # one shared handle gives the same numbers (it re-uploads and refactorises on every switch between outputs)
+    shared = B200MultiOutputGPSurrogate(share_backend=True)
+    shared.train(X, Y, kernel="RBF", hyperparameters=hyp)
+    ys, vs = shared.predict(Xc)
+    assert np.allclose(ys, ym, rtol=1e-9, atol=1e-12) and np.allclose(vs, yv, rtol=1e-9)
 
 
 # ------------------------------------------------------------------------------------------ BASELINE shapes vs oracle
