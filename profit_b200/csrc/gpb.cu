@@ -66,6 +66,13 @@ struct Plan {
   }
 };
 
+// Frees the device task list of a function-local plan on every exit path.
+struct PlanGuard {
+  Plan& p;
+  explicit PlanGuard(Plan& pl) : p(pl) {}
+  ~PlanGuard() { p.clear(); }
+};
+
 struct MatDesc {
   double* ptr = nullptr;
   long long rows = 0, cols = 0, ld = 0;
@@ -1534,6 +1541,7 @@ int gpb_predict_cov(gpb_handle_t h, const double* Xc, long long M, int noise_on_
   set_mat(w, M_KST, kst, Mp, Np, Np);
   set_mat(w, M_DBG_A, vt, Mp, Np, Np);
   Plan p;
+  PlanGuard guard(p);
   {
     // Vt[c][i] = sum_{k <= i} K*^T[c][k] W[i][k]
     TaskSink s(p);
@@ -1578,7 +1586,6 @@ int gpb_predict_cov(gpb_handle_t h, const double* Xc, long long M, int noise_on_
   if (!cov_dev) CK(cudaMemcpyAsync(cov, dout, (size_t)M * M * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   if (mean) CK(cudaMemcpyAsync(mean, dmean, (size_t)M * h->n_out * sizeof(double), cudaMemcpyDefault, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  p.clear();
   return 0;
 }
 
@@ -1699,8 +1706,11 @@ int gpb_append_train(gpb_handle_t h, const double* Xnew, const double* ynew, lon
       // The padded block is full: grow by re-uploading [X; Xnew[p:]] and refactorising at the current theta.
       const long long rem = m - p, tot = N + rem;
       double *tx = nullptr, *ty = nullptr;
-      CK(cudaMalloc(&tx, (size_t)tot * D * sizeof(double)));
-      CK(cudaMalloc(&ty, (size_t)tot * n_out * sizeof(double)));
+      if (cudaMalloc(&tx, (size_t)tot * D * sizeof(double)) != cudaSuccess ||
+          cudaMalloc(&ty, (size_t)tot * n_out * sizeof(double)) != cudaSuccess) {
+        cudaFree(tx);
+        return fail(h, -2, "gpb_append_train: out of device memory while growing the training set");
+      }
       cudaError_t e1 = cudaMemcpyAsync(tx, h->dX, (size_t)N * D * sizeof(double), cudaMemcpyDeviceToDevice, h->stream);
       cudaError_t e2 = cudaMemcpyAsync(ty, h->dy, (size_t)N * n_out * sizeof(double), cudaMemcpyDeviceToDevice, h->stream);
       cudaError_t e3 = cudaMemcpyAsync(tx + N * D, Xnew + p * D, (size_t)rem * D * sizeof(double), cudaMemcpyDefault, h->stream);
@@ -1926,6 +1936,7 @@ int gpb_debug_gemm(gpb_handle_t h, const double* A, const double* B, double* C, 
   set_mat(w, M_DBG_A, const_cast<double*>(A), M, K, K);
   set_mat(w, M_DBG_B, const_cast<double*>(B), N, K, K);
   Plan p;
+  PlanGuard guard(p);
   TaskSink s(p);
   for (long long i = 0; i < M / 128; ++i)
     for (long long j = 0; j < N / 128; ++j)
@@ -1949,7 +1960,6 @@ int gpb_debug_gemm(gpb_handle_t h, const double* A, const double* B, double* C, 
   float t = 0.f;
   cudaEventElapsedTime(&t, e0, e1);
   if (ms) *ms = t / reps;
-  p.clear();
   return 0;
 }
 
