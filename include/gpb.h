@@ -103,9 +103,17 @@ enum {
  *   GPB_ACQ_WEIGHTED: AcquisitionFunction.normalize(mu) column-wise (:76-84, :200-201); no params.
  *   GPB_ACQ_EI:       ExpectedImprovement.mu_part (:262-269), params = [xi, find_min, ymax[n_out]]:
  *                     normalize(max(+-mu - ymax, 0)) - xi.
- * n_out <= 16.  out may alias mean. */
+ * n_out <= 16.  out may alias mean.
+ *
+ * Sharded candidate sets: the normalisations are over ALL candidates.  stats_out (host, 2*n_out: [min, max] per column
+ * of the quantity being normalised on this shard) and stats_in (host, same layout: the global values) let the caller
+ * combine shards -- call once with stats_out, reduce over ranks, call again with stats_in.  Both may be NULL. */
 int gpb_acq_prepare(gpb_handle_t h, int kind, const double* mean, long long M, int n_out, const double* params,
-                    int n_params, double* out);
+                    int n_params, double* out, const double* stats_in, double* stats_out);
+
+/* Column-wise [min, max] of v (M, ncol) -> out (host, 2*ncol); transform 1 takes sqrt first.  The per-shard half of
+ * AcquisitionFunction.normalize (:76-84) for gpb_acquire's stats_in. */
+int gpb_acq_stats(gpb_handle_t h, const double* v, long long M, int ncol, int transform, double* out);
 
 /* Loss of one acquisition function for every candidate, summed over outputs (axis=1), and the pick
  * idx = np.argmax(loss * mask) of AcquisitionFunction._find_next_candidates (:63-68): `visited` (host, n_visited
@@ -115,10 +123,12 @@ int gpb_acq_prepare(gpb_handle_t h, int kind, const double* mean, long long M, i
  *   var  : (M)         predictive or marginal variance
  *   extra: (M, n_out) standard-normal draws (POI) | (M, d) candidate coordinates (DISTANCE_PENALTY) | NULL otherwise
  *   loss_out: (M) or NULL (the unmasked loss, what calculate_loss returns); val may be NULL.
- * Inputs left on the device by gpb_predict never travel to the host: only (idx, val) come back. */
+ * Inputs left on the device by gpb_predict never travel to the host: only (idx, val) come back.
+ * stats_in (host, [min, max] or NULL): global statistics of var (sqrt(var) for EI) when this call sees one shard of
+ * the candidate set (gpb_acq_stats on every shard, reduced by the caller); NULL = this call sees all candidates. */
 int gpb_acquire(gpb_handle_t h, int kind, const double* term, const double* var, const double* extra, long long M,
                 int n_out, const double* params, int n_params, const long long* visited, int n_visited, double* loss_out,
-                long long* idx, double* val);
+                long long* idx, double* val, const double* stats_in);
 
 /* Dense kernel matrix and derivative tensor -- python_kernels.RBF (python_kernels.py:8-57) and the Matern-5/2
  * twin.  K: (na, nb); dK: (na, nb, n_ell + 2) or NULL. */

@@ -31,10 +31,11 @@ SIGNATURES = {
                                   ctypes.POINTER(ctypes.c_double)]),
     "gpb_append_train": (ctypes.c_int, [ctypes.c_void_p, _c_double_p, _c_double_p, _ll]),
     "gpb_acq_prepare": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _c_double_p, _ll, ctypes.c_int, _c_double_p,
-                                       ctypes.c_int, _c_double_p]),
+                                       ctypes.c_int, _c_double_p, _c_double_p, _c_double_p]),
+    "gpb_acq_stats": (ctypes.c_int, [ctypes.c_void_p, _c_double_p, _ll, ctypes.c_int, ctypes.c_int, _c_double_p]),
     "gpb_acquire": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _c_double_p, _c_double_p, _c_double_p, _ll,
                                    ctypes.c_int, _c_double_p, ctypes.c_int, ctypes.POINTER(_ll), ctypes.c_int,
-                                   _c_double_p, ctypes.POINTER(_ll), ctypes.POINTER(ctypes.c_double)]),
+                                   _c_double_p, ctypes.POINTER(_ll), ctypes.POINTER(ctypes.c_double), _c_double_p]),
     "gpb_kernel_matrix": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _c_double_p, _ll, _c_double_p, _ll,
                                          ctypes.c_int, _c_double_p, ctypes.c_int, ctypes.c_double, ctypes.c_double,
                                          _c_double_p, _c_double_p]),

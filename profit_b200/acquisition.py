@@ -8,10 +8,17 @@ and ``gpb_acquire`` (loss + ``np.argmax(loss * mask)``) on the device, so 16 byt
 
 The surrogate must be a ``B200GPSurrogate`` (it provides ``predict_into`` and the device backend); there is no
 CPU path.  ``torch`` only supplies the device buffers.
+
+Under ``torch.distributed`` (one process per GPU, every rank running the same active-learning loop on the same
+training data) the candidate set is sharded automatically: each rank predicts and scores its contiguous shard, the
+min / max that the normalisations need are combined with one small all_gather, and the pick is one all_gather of
+(value, global index) -- so every rank arrives at the same point and keeps an identical model.  ``af.sharded =
+False`` switches that off.
 """
 import numpy as np
 
 from .backend import ACQ_DISTANCE_PENALTY, ACQ_EI, ACQ_EI2, ACQ_POI, ACQ_VARIANCE, ACQ_WEIGHTED
+from .distributed import gather_argmax, gather_concat, gather_minmax, shard_bounds, world
 
 try:  # pragma: no cover - depends on the environment
     from profit.al.aquisition_functions import AcquisitionFunction as _RefBase
@@ -67,12 +74,20 @@ class DeviceAcquisitionFunction(_RefBase):
     """Base: device buffers, the fused predict -> loss -> masked arg-max pick, and the batch loop."""
 
     kind = None
+    sharded = None          # None: shard the candidates when torch.distributed runs more than one rank
 
     def __init__(self, Xpred, surrogate, variables, **parameters):
         super().__init__(Xpred, surrogate, variables, **parameters)
         self._dev = None
 
     # -- device plumbing ------------------------------------------------------------------------------
+    def _shard(self, M):
+        rank, ws = world()
+        if self.sharded is False or ws == 1:
+            return 0, M, False
+        lo, hi = shard_bounds(M, ws, rank)
+        return lo, hi, True
+
     def _buffers(self):
         if not hasattr(self.surrogate, "predict_into"):
             raise TypeError("profit_b200 acquisition functions need a B200GPSurrogate (device predict); "
@@ -86,9 +101,11 @@ class DeviceAcquisitionFunction(_RefBase):
         n_out = int(np.atleast_2d(self.surrogate.ytrain).shape[1])
         if d is None or d["src"] is not self.Xpred or d["n_out"] != n_out:
             dev = torch.device("cuda", self.surrogate.backend.device)
-            M = Xp.shape[0]
-            d = {"src": self.Xpred, "n_out": n_out, "M": M,
-                 "X": torch.from_numpy(Xp).to(dev),
+            lo, hi, sharded = self._shard(Xp.shape[0])
+            M = hi - lo                                   # candidates held by this rank (all of them if not sharded)
+            d = {"src": self.Xpred, "n_out": n_out, "M": M, "M_total": Xp.shape[0], "lo": lo, "hi": hi,
+                 "sharded": sharded,
+                 "X": torch.from_numpy(Xp[lo:hi]).to(dev),
                  "mean": torch.empty((M, n_out), dtype=torch.float64, device=dev),
                  "var": torch.empty(M, dtype=torch.float64, device=dev),
                  "term": torch.empty((M, n_out), dtype=torch.float64, device=dev)}
@@ -96,37 +113,78 @@ class DeviceAcquisitionFunction(_RefBase):
         return d
 
     def _predict(self, want_mean=False, want_var=True):
-        """Predictive mean / variance of all candidates into the device buffers (nothing returns to the host)."""
+        """Predictive mean / variance of this rank's candidates into the device buffers (nothing returns to the host)."""
         d = self._buffers()
-        self.surrogate.predict_into(d["X"], out_mean=d["mean"] if want_mean else None,
-                                    out_var=d["var"] if want_var else None, add_data_variance=True)
+        if d["M"] > 0:
+            self.surrogate.predict_into(d["X"], out_mean=d["mean"] if want_mean else None,
+                                        out_var=d["var"] if want_var else None, add_data_variance=True)
         return d
 
     def _variance(self, use_marginal_variance=False):
         """Device predictive variance, or the host marginal variance (aquisition_functions.py:108-118)."""
         if use_marginal_variance:
             if hasattr(self.surrogate, "get_marginal_variance"):
-                return np.ascontiguousarray(self.surrogate.get_marginal_variance(self.Xpred), dtype=np.float64).ravel()
+                d = self._buffers()
+                mv = np.ascontiguousarray(self.surrogate.get_marginal_variance(self.Xpred), dtype=np.float64).ravel()
+                return np.ascontiguousarray(mv[d["lo"]:d["hi"]])
             print("Surrogate has no method 'get_marginal_variance'. Using predictive variance instead.")
         return self._predict()["var"]
 
+    def _prepare(self, kind, params=()):
+        """gpb_acq_prepare of the device mean into the ``term`` buffer, with the min / max of the normalisation
+        taken over all ranks' shards."""
+        d = self._predict(want_mean=True, want_var=False)
+        be = self.surrogate.backend
+        if not d["sharded"]:
+            be.acq_prepare(kind, d["mean"], params=params, out=d["term"])
+            return d["term"]
+        local = np.tile([np.inf, -np.inf], (d["n_out"], 1))
+        if d["M"] > 0:
+            _, local = be.acq_prepare(kind, d["mean"], params=params, out=d["term"], return_stats=True)
+        stats = gather_minmax(local)
+        if d["M"] > 0:
+            be.acq_prepare(kind, d["mean"], params=params, out=d["term"], stats_in=stats)
+        return d["term"]
+
     def _inputs(self, *loss_args):
-        """-> dict(kind, var, term, extra, params) for gpb_acquire."""
+        """-> dict(kind, var, term, extra, params) for gpb_acquire (arrays cover this rank's candidates)."""
         raise NotImplementedError
 
+    def _rows(self, arr):
+        """This rank's rows of a per-candidate argument: device tensors from ``normalized_mean`` / ``mu_part`` are
+        already local; a host array over all candidates (what the reference's callers pass) is sliced."""
+        d = self._buffers()
+        if d["sharded"] and isinstance(arr, np.ndarray) and arr.shape[0] == d["M_total"]:
+            return np.ascontiguousarray(arr[d["lo"]:d["hi"]])
+        return arr
+
+    _NEEDS_STATS = {ACQ_DISTANCE_PENALTY: 0, ACQ_WEIGHTED: 0, ACQ_EI: 1}     # kind -> transform of the variance
+
     def _acquire(self, visited, loss_out, *loss_args):
+        """(global index, value) of ``np.argmax(loss * mask)``; ``loss_out`` (M_local,) receives this rank's losses."""
         a = self._inputs(*loss_args)
         d = self._buffers()
-        return self.surrogate.backend.acquire(a["kind"], a["var"], term=a.get("term"), extra=a.get("extra"),
-                                              params=a.get("params", ()), visited=visited, n_out=d["n_out"],
-                                              loss_out=loss_out)
+        be = self.surrogate.backend
+        stats = None
+        if d["sharded"] and a["kind"] in self._NEEDS_STATS:
+            local = be.acq_stats(a["var"], self._NEEDS_STATS[a["kind"]]) if d["M"] > 0 else [[np.inf, -np.inf]]
+            stats = gather_minmax(local)[0]
+        idx, val = -1, -np.inf
+        if d["M"] > 0:
+            mine = [v - d["lo"] for v in visited if d["lo"] <= v < d["hi"]]
+            idx, val = be.acquire(a["kind"], a["var"], term=a.get("term"), extra=a.get("extra"),
+                                  params=a.get("params", ()), visited=mine, n_out=d["n_out"], loss_out=loss_out,
+                                  stats=stats)
+            idx += d["lo"]
+        return gather_argmax(val, idx) if d["sharded"] else (idx, val)
 
     # -- reference API --------------------------------------------------------------------------------
     def calculate_loss(self, *loss_args):
         """Loss per candidate as a host array (M,), like the reference's ``calculate_loss``."""
-        loss = np.empty(self._buffers()["M"])
-        self._acquire((), loss, *loss_args)
-        return loss
+        d = self._buffers()
+        loss = np.empty(d["M"])
+        self._acquire((), loss if d["M"] > 0 else None, *loss_args)
+        return gather_concat(loss, d["M_total"]) if d["sharded"] else loss
 
     def find_next_candidates(self, batch_size):
         return self._find_next_candidates(batch_size)
@@ -194,14 +252,12 @@ class WeightedExploration(DeviceAcquisitionFunction):
         super().__init__(Xpred, surrogate, variables, weight=weight, use_marginal_variance=use_marginal_variance)
 
     def _inputs(self, mu):
-        return {"kind": ACQ_WEIGHTED, "var": self._variance(self.parameters["use_marginal_variance"]), "term": mu,
-                "params": [float(self.parameters["weight"])]}
+        return {"kind": ACQ_WEIGHTED, "var": self._variance(self.parameters["use_marginal_variance"]),
+                "term": self._rows(mu), "params": [float(self.parameters["weight"])]}
 
     def normalized_mean(self):
         """``normalize(mu)`` of the current model, kept on the device (:199-200)."""
-        d = self._predict(want_mean=True, want_var=False)
-        self.surrogate.backend.acq_prepare(ACQ_WEIGHTED, d["mean"], out=d["term"])
-        return d["term"]
+        return self._prepare(ACQ_WEIGHTED)
 
     def find_next_candidates(self, batch_size):
         return self._find_next_candidates(batch_size, self.normalized_mean())
@@ -216,8 +272,9 @@ class ProbabilityOfImprovement(DeviceAcquisitionFunction):
 
     def _inputs(self, mu):
         d = self._predict()
-        noise = np.random.standard_normal((d["M"], d["n_out"]))                          # :215
-        return {"kind": ACQ_POI, "var": d["var"], "term": mu, "extra": noise,
+        noise = np.random.standard_normal((d["M_total"], d["n_out"]))                    # :215, same draws on every rank
+        noise = np.ascontiguousarray(noise[d["lo"]:d["hi"]])
+        return {"kind": ACQ_POI, "var": d["var"], "term": self._rows(mu), "extra": noise,
                 "params": self._observed_max(nan_aware=False)}                            # :216 (plain max, as written)
 
     def predicted_mean(self):
@@ -241,15 +298,13 @@ class ExpectedImprovement(DeviceAcquisitionFunction):
         super().__init__(Xpred, surrogate, variables, exploration_factor=exploration_factor, find_min=find_min)
 
     def _inputs(self, improvement):
-        return {"kind": ACQ_EI, "var": self._predict()["var"], "term": improvement}
+        return {"kind": ACQ_EI, "var": self._predict()["var"], "term": self._rows(improvement)}
 
     def mu_part(self):
         """``normalize(max(+-mu - nanmax(y), 0)) - xi`` on the device (:262-269)."""
-        d = self._predict(want_mean=True, want_var=False)
         params = np.concatenate([[float(self.parameters["exploration_factor"]), float(bool(self.parameters["find_min"]))],
                                  self._observed_max(nan_aware=True)])
-        self.surrogate.backend.acq_prepare(ACQ_EI, d["mean"], params=params, out=d["term"])
-        return d["term"]
+        return self._prepare(ACQ_EI, params)
 
     def find_next_candidates(self, batch_size):
         return self._find_next_candidates(batch_size, self.mu_part())

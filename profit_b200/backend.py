@@ -143,34 +143,50 @@ class GPBackend:
         _lib.check(self._lib.gpb_append_train(self._h, _lib.ptr(X_new), _lib.ptr(y_new), m), self._h, "append_train")
         self.n += m
 
-    def acq_prepare(self, kind, mean, params=(), out=None):
+    def acq_prepare(self, kind, mean, params=(), out=None, stats_in=None, return_stats=False):
         """Once-per-batch transform of the predictive mean (M, n_out): normalize(mu) for ACQ_WEIGHTED, the
-        ExpectedImprovement.mu_part for ACQ_EI.  ``mean`` / ``out`` may be numpy arrays or torch CUDA tensors."""
+        ExpectedImprovement.mu_part for ACQ_EI.  ``mean`` / ``out`` may be numpy arrays or torch CUDA tensors.
+        ``stats_in`` (n_out, 2) overrides the [min, max] of the normalisation (global values of a sharded candidate
+        set); ``return_stats`` also returns this shard's own (n_out, 2)."""
         mean = _lib.as_f64(mean)
         M = int(mean.shape[0])
         n_out = 1 if mean.ndim == 1 else int(mean.shape[1])
         params = np.ascontiguousarray(params, dtype=np.float64).ravel()
         if out is None:
             out = np.empty((M, n_out))
+        sin = None if stats_in is None else np.ascontiguousarray(stats_in, dtype=np.float64).reshape(n_out, 2)
+        sout = np.empty((n_out, 2)) if return_stats else None
         st = self._lib.gpb_acq_prepare(self._h, int(kind), _lib.ptr(mean), M, n_out,
-                                       _lib.ptr(params) if params.size else None, int(params.size), _lib.ptr(out))
+                                       _lib.ptr(params) if params.size else None, int(params.size), _lib.ptr(out),
+                                       _lib.ptr(sin), _lib.ptr(sout))
         _lib.check(st, self._h, "acq_prepare")
+        return (out, sout) if return_stats else out
+
+    def acq_stats(self, v, transform=0):
+        """Column-wise [min, max] of v (M,) or (M, ncol) on the device -> (ncol, 2); ``transform=1`` takes sqrt first."""
+        v = _lib.as_f64(v)
+        M = int(v.shape[0])
+        ncol = 1 if v.ndim == 1 else int(v.shape[1])
+        out = np.empty((ncol, 2))
+        _lib.check(self._lib.gpb_acq_stats(self._h, _lib.ptr(v), M, ncol, int(transform), _lib.ptr(out)), self._h, "acq_stats")
         return out
 
-    def acquire(self, kind, var, term=None, extra=None, params=(), visited=(), n_out=1, loss_out=None):
+    def acquire(self, kind, var, term=None, extra=None, params=(), visited=(), n_out=1, loss_out=None, stats=None):
         """Loss of acquisition function ``kind`` over all candidates and ``np.argmax(loss * mask)`` (mask zero on the
         ``visited`` rows) -> (index, masked value).  ``loss_out`` (numpy (M,) or torch CUDA) receives the unmasked
-        loss when given; device-resident inputs stay on the device and only the pick comes back."""
+        loss when given; device-resident inputs stay on the device and only the pick comes back.  ``stats`` = global
+        [min, max] of var (sqrt(var) for ACQ_EI) when ``var`` is one shard of the candidate set."""
         var = _lib.as_f64(var)
         M = int(var.shape[0])
         params = np.ascontiguousarray(params, dtype=np.float64).ravel()
         vis = (ctypes.c_longlong * max(1, len(visited)))(*[int(v) for v in visited])
         idx = ctypes.c_longlong()
         val = ctypes.c_double()
+        sin = None if stats is None else np.ascontiguousarray(stats, dtype=np.float64).ravel()[:2].copy()
         st = self._lib.gpb_acquire(self._h, int(kind), _lib.ptr(None if term is None else _lib.as_f64(term)),
                                    _lib.ptr(var), _lib.ptr(None if extra is None else _lib.as_f64(extra)), M, int(n_out),
                                    _lib.ptr(params) if params.size else None, int(params.size), vis, len(visited),
-                                   _lib.ptr(loss_out), ctypes.byref(idx), ctypes.byref(val))
+                                   _lib.ptr(loss_out), ctypes.byref(idx), ctypes.byref(val), _lib.ptr(sin))
         _lib.check(st, self._h, "acquire")
         return int(idx.value), float(val.value)
 

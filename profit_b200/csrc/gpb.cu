@@ -1592,7 +1592,7 @@ int gpb_predict_cov(gpb_handle_t h, const double* Xc, long long M, int noise_on_
 int gpb_argmax(gpb_handle_t h, const double* v, long long M, long long* idx, double* val) {
   if (!h || !v || M < 1 || !idx) return fail(h, -1, "gpb_argmax: bad argument");
   // the plain variance acquisition without a mask is exactly np.argmax
-  return gpb_acquire(h, ACQ_VARIANCE, nullptr, v, nullptr, M, 1, nullptr, 0, nullptr, 0, nullptr, idx, val);
+  return gpb_acquire(h, ACQ_VARIANCE, nullptr, v, nullptr, M, 1, nullptr, 0, nullptr, 0, nullptr, idx, val, nullptr);
 }
 
 int gpb_kernel_matrix(gpb_handle_t h, int kind, const double* Xa, long long na, const double* Xb, long long nb, int d,
@@ -1770,8 +1770,27 @@ int gpb_append_train(gpb_handle_t h, const double* Xnew, const double* ynew, lon
   return 0;
 }
 
+int gpb_acq_stats(gpb_handle_t h, const double* v, long long M, int ncol, int transform, double* out) {
+  if (!h || !v || !out || M < 1 || ncol < 1 || ncol > ACQ_MAX_OUT || (transform != 0 && transform != 1))
+    return fail(h, -1, "gpb_acq_stats: bad argument");
+  CK(cudaSetDevice(h->device));
+  const size_t tot = (size_t)M * ncol;
+  const int nblk = acq_grid(M);
+  int rc = ensure_cap(h, &h->dacq, &h->dacq_cap, tot + (size_t)2 * nblk * ncol + 2 * ACQ_MAX_OUT + 64);
+  if (rc) return rc;
+  double* cur = h->dacq;
+  const double* dv = nullptr;
+  if ((rc = acq_stage_in(h, v, tot, &cur, &dv))) return rc;
+  double* part = cur;
+  double* stats = part + (size_t)2 * nblk * ncol;
+  if ((rc = acq_minmax(h, dv, M, ncol, transform, part, stats))) return rc;
+  CK(cudaMemcpyAsync(out, stats, (size_t)2 * ncol * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
 int gpb_acq_prepare(gpb_handle_t h, int kind, const double* mean, long long M, int n_out, const double* params,
-                    int n_params, double* out) {
+                    int n_params, double* out, const double* stats_in, double* stats_out) {
   if (!h || !mean || !out || M < 1 || n_out < 1 || n_out > ACQ_MAX_OUT) return fail(h, -1, "gpb_acq_prepare: bad argument");
   if (kind != ACQ_WEIGHTED && kind != ACQ_EI) return fail(h, -1, "gpb_acq_prepare: kind has no prepare step");
   CK(cudaSetDevice(h->device));
@@ -1800,7 +1819,12 @@ int gpb_acq_prepare(gpb_handle_t h, int kind, const double* mean, long long M, i
   const int grid = acq_grid((long long)tot);
   acq_prepare_kernel<<<grid, ACQ_THREADS, 0, h->stream>>>(0, a, dmean, stats, dout);
   h->launches++;
-  if ((rc = acq_minmax(h, dout, M, n_out, 0, part, stats))) return rc;
+  if (!stats_in || stats_out) {
+    if ((rc = acq_minmax(h, dout, M, n_out, 0, part, stats))) return rc;
+    if (stats_out) CK(cudaMemcpyAsync(stats_out, stats, (size_t)2 * n_out * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  }
+  // statistics supplied by the caller (the global ones when the candidate set is sharded over ranks) win
+  if (stats_in) CK(cudaMemcpyAsync(stats, stats_in, (size_t)2 * n_out * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   acq_prepare_kernel<<<grid, ACQ_THREADS, 0, h->stream>>>(1, a, dmean, stats, dout);
   h->launches++;
   CK(cudaGetLastError());
@@ -1811,7 +1835,7 @@ int gpb_acq_prepare(gpb_handle_t h, int kind, const double* mean, long long M, i
 
 int gpb_acquire(gpb_handle_t h, int kind, const double* term, const double* var, const double* extra, long long M,
                 int n_out, const double* params, int n_params, const long long* visited, int n_visited, double* loss_out,
-                long long* idx, double* val) {
+                long long* idx, double* val, const double* stats_in) {
   if (!h || !var || !idx || M < 1 || n_out < 1 || n_out > ACQ_MAX_OUT || n_visited < 0 || (n_visited > 0 && !visited))
     return fail(h, -1, "gpb_acquire: bad argument");
   CK(cudaSetDevice(h->device));
@@ -1847,8 +1871,10 @@ int gpb_acquire(gpb_handle_t h, int kind, const double* term, const double* var,
       if (visited[k] < 0 || visited[k] >= M) return fail(h, -1, "gpb_acquire: visited index out of range");
     CK(cudaMemcpyAsync(dvis, visited, (size_t)n_visited * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
   }
-  if (kind == ACQ_DISTANCE_PENALTY || kind == ACQ_WEIGHTED || kind == ACQ_EI)
-    if ((rc = acq_minmax(h, dvar, M, 1, kind == ACQ_EI ? 1 : 0, part, stats))) return rc;
+  if (kind == ACQ_DISTANCE_PENALTY || kind == ACQ_WEIGHTED || kind == ACQ_EI) {
+    if (stats_in) CK(cudaMemcpyAsync(stats, stats_in, 2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    else if ((rc = acq_minmax(h, dvar, M, 1, kind == ACQ_EI ? 1 : 0, part, stats))) return rc;
+  }
   acq_loss_kernel<<<nblk, ACQ_THREADS, 0, h->stream>>>(a, dterm, dvar, dextra, stats, dvis, dloss, part, pidx);
   acq_argmax_final_kernel<<<1, ACQ_THREADS, 0, h->stream>>>(part, pidx, nblk, stats + 2, reinterpret_cast<long long*>(stats + 3));
   h->launches += 2;

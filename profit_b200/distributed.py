@@ -49,16 +49,43 @@ def _all_gather_rows(row):
 
 
 def gather_argmax(local_value, local_global_index):
-    """Global (index, value) of the maximum over ranks; ties -> lowest global index; empty shards pass -inf."""
+    """Global (index, value) of the maximum over ranks with np.argmax's order: the first NaN wins, otherwise the
+    largest value, ties -> lowest global index; ranks with an empty shard pass index -1."""
     rows = _all_gather_rows([local_value, float(local_global_index)])
     best_val, best_idx = -np.inf, -1
     for val, idx in rows:
         idx = int(idx)
         if idx < 0:
             continue
-        if val > best_val or (val == best_val and idx < best_idx):
+        if best_idx < 0:
+            better = True
+        elif np.isnan(val) != np.isnan(best_val):
+            better = bool(np.isnan(val))
+        elif not np.isnan(val) and val != best_val:
+            better = val > best_val
+        else:
+            better = idx < best_idx
+        if better:
             best_val, best_idx = val, idx
     return best_idx, best_val
+
+
+def gather_minmax(local_stats):
+    """Combine per-shard [min, max] rows (ncol, 2) into the global ones; empty shards pass [+inf, -inf]."""
+    local_stats = np.atleast_2d(np.asarray(local_stats, dtype=np.float64))
+    rows = _all_gather_rows(local_stats.ravel()).reshape(-1, local_stats.shape[0], 2)
+    return np.stack([rows[:, :, 0].min(axis=0), rows[:, :, 1].max(axis=0)], axis=1)
+
+
+def gather_concat(local, total):
+    """Concatenate the contiguous shards of a 1-D array (shard_bounds layout) -> full array of length ``total``."""
+    rank, ws = world()
+    if ws == 1:
+        return np.asarray(local, dtype=np.float64)
+    per = -(-int(total) // ws)
+    padded = np.zeros(per)
+    padded[: len(local)] = local
+    return _all_gather_rows(padded).ravel()[:total]        # shard r starts at r * per: rank-ordered rows line up
 
 
 def gather_argmin_rows(local_rows):

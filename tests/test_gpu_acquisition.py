@@ -349,3 +349,93 @@ def test_predict_variance_only_and_mean_only(backend):
     none_m, v_only = backend.predict(Xc, want_mean=False)
     assert none_v is None and none_m is None
     assert np.array_equal(m, m_only) and np.array_equal(v, v_only)
+
+
+# ------------------------------------------------------------------------------------------ sharded over ranks
+_SHARD_WORKER = r'''
+import json, os, sys, types
+sys.path.insert(0, sys.argv[1])
+import numpy as np, torch.distributed as dist
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + sys.argv[2], rank=int(sys.argv[3]), world_size=int(sys.argv[4]))
+import oracle
+from profit_b200 import B200GPSurrogate
+from profit_b200 import acquisition as acq
+
+k = json.load(open(os.path.join(sys.argv[1], "tests", "golden", "acquisition_kats.json")))
+N, D, M, NS = k["N"], k["D"], k["M"], k["NS"]
+X, y = oracle.synthetic_problem(N, D)
+Xpred = np.random.default_rng(k["pred_seed"]).random((M, D))
+vin, vout = np.full((NS, D), np.nan), np.full((NS, 1), np.nan)
+vin[:N], vout[:N] = X, y
+variables = types.SimpleNamespace(input=vin, output=vout)
+full = types.SimpleNamespace(input=X.copy(), output=y.copy())
+theta = np.array(k["theta"])
+
+def surrogate():
+    s = B200GPSurrogate(0)                      # every rank on cuda:0 here; one GPU per rank in production
+    s.Xtrain, s.ytrain, s.ndim, s.trained = X.copy(), y.copy(), D, True
+    s.kernel = s.select_kernel("RBF")
+    s.hyperparameters = {"length_scale": theta[:-2].copy(), "sigma_f": theta[-2:-1].copy(), "sigma_n": theta[-1:].copy()}
+    return s
+
+def check(loss, c):
+    ref = np.array(c["loss"]); scale = np.abs(ref).max()
+    assert loss.shape == ref.shape, (loss.shape, ref.shape)
+    assert np.all(np.abs(loss - ref) <= 1e-8 * np.abs(ref) + 1e-10 * scale), np.abs(loss - ref).max()
+
+C = k["cases"]
+s = surrogate()
+af = acq.SimpleExploration(Xpred, s, variables)
+assert af._buffers()["sharded"] and af._buffers()["M"] < M
+check(af.calculate_loss(), C["simple_exploration"])
+assert af._acquire((), None)[0] == C["simple_exploration"]["argmax"]
+assert af._acquire(tuple(k["masked_pick"]["visited"]), None)[0] == k["masked_pick"]["expect"]
+for key in ("exploration_with_distance_penalty_w10", "exploration_with_distance_penalty_w3.5"):
+    a = acq.ExplorationWithDistancePenalty(Xpred, s, variables, weight=C[key]["weight"])
+    check(a.calculate_loss(), C[key]); assert a._acquire((), None)[0] == C[key]["argmax"]
+for key in ("weighted_exploration_w0.5", "weighted_exploration_w0.2"):
+    a = acq.WeightedExploration(Xpred, s, variables, weight=C[key]["weight"])
+    check(a.calculate_loss(a.normalized_mean()), C[key])
+    check(a.calculate_loss(np.array(C[key]["mu_normalized"]).reshape(-1, 1)), C[key])    # host argument over all candidates
+    assert a._acquire((), None, a.normalized_mean())[0] == C[key]["argmax"]
+c = C["probability_of_improvement"]
+a = acq.ProbabilityOfImprovement(Xpred, s, full)
+mu = a.predicted_mean()
+np.random.seed(c["np_random_seed"]); check(a.calculate_loss(mu), c)
+for key in ("expected_improvement_xi0.01_min0", "expected_improvement_xi0.05_min1"):
+    a = acq.ExpectedImprovement(Xpred, s, variables, exploration_factor=C[key]["xi"], find_min=C[key]["find_min"])
+    imp = a.mu_part()
+    check(a.calculate_loss(imp), C[key]); assert a._acquire((), None, imp)[0] == C[key]["argmax"]
+for key in ("expected_improvement_2_xi0.01_min0", "expected_improvement_2_xi0.05_min1"):
+    a = acq.ExpectedImprovement2(Xpred, s, variables, exploration_factor=C[key]["xi"], find_min=C[key]["find_min"])
+    check(a.calculate_loss(), C[key]); assert a._acquire((), None)[0] == C[key]["argmax"]
+# the batch loop: every rank picks the same points and ends with the same model as the single-process reference run
+g = k["batch_simple_exploration"]
+s2 = surrogate(); s2.optimize = lambda *a, **kw: None
+cand = acq.SimpleExploration(Xpred, s2, variables).find_next_candidates(g["batch_size"])
+assert np.array_equal(cand, np.array(g["candidates"]))
+m, v = s2.predict(Xpred[:50])
+assert np.allclose(m.ravel(), g["mean_after"], rtol=1e-8, atol=1e-10) and np.allclose(v.ravel(), g["var_after"], rtol=1e-8)
+dist.barrier(); dist.destroy_process_group()
+print("shard worker", sys.argv[3], "ok")
+'''
+
+
+@pytest.mark.parametrize("world_size", [2, 3])
+def test_acquisition_sharded_over_ranks_matches_the_reference(built_lib, tmp_path, world_size):
+    """Candidates sharded over ranks (gloo here, all ranks on cuda:0): global min / max for the normalisations and the
+    (value, index) gather reproduce the reference's losses and picks of the unsharded run."""
+    import socket
+    import subprocess
+    import sys
+
+    script = tmp_path / "shard_worker.py"
+    script.write_text(_SHARD_WORKER)
+    with socket.socket() as sock:
+        sock.bind(("127.0.0.1", 0))
+        port = str(sock.getsockname()[1])
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r), str(world_size)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(world_size)]
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and f"shard worker {r} ok" in o, o[-3000:]

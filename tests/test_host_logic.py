@@ -180,7 +180,7 @@ _WORKER = r'''
 import os, sys
 sys.path.insert(0, sys.argv[1])
 import numpy as np, torch.distributed as dist
-from profit_b200.distributed import gather_argmax, gather_argmin_rows, shard_bounds, world
+from profit_b200.distributed import gather_argmax, gather_argmin_rows, gather_concat, gather_minmax, shard_bounds, world
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + sys.argv[2], rank=int(sys.argv[3]), world_size=2)
 rank, ws = world()
 v = np.sin(np.arange(1001) * 0.37); v[[100, 900]] = 2.0           # a tie across the two shards
@@ -193,6 +193,19 @@ assert (idx, val) == (5, 1.0)
 rows = np.array([[r, 10.0 - (r % 3), 0.1 * r, 0.2] for r in range(rank, 5, ws)])   # restarts r -> rank r mod G
 best, table = gather_argmin_rows(rows)
 assert best[0] == 2 and best[1] == 8.0 and table.shape == (5, 4) and list(table[:, 0]) == [0, 1, 2, 3, 4]
+# np.argmax order across shards: the first NaN wins over any value
+w = v.copy(); w[[700, 650]] = np.nan
+lw = w[lo:hi]; li = int(np.argmax(lw))
+idx, val = gather_argmax(lw[li], lo + li)
+assert idx == int(np.argmax(w)) == 650 and np.isnan(val), (idx, val)
+# per-shard [min, max] -> global (the normalisations of the acquisition functions), empty shard = [+inf, -inf]
+cols = np.stack([v, -2.0 * v], axis=1)
+local = np.stack([cols[lo:hi].min(axis=0), cols[lo:hi].max(axis=0)], axis=1)
+g = gather_minmax(local)
+assert np.array_equal(g, np.stack([cols.min(axis=0), cols.max(axis=0)], axis=1))
+g1 = gather_minmax([[np.inf, -np.inf]] if rank == 1 else [[0.5, 0.7]])
+assert np.array_equal(g1, [[0.5, 0.7]])
+assert np.array_equal(gather_concat(v[lo:hi], len(v)), v)         # ragged last shard (1001 = 501 + 500)
 dist.barrier(); dist.destroy_process_group()
 print("worker", rank, "ok")
 '''
