@@ -45,6 +45,8 @@ SIGNATURES = {
     "gpb_solve_cholesky": (ctypes.c_int, [ctypes.c_void_p, _c_double_p, _ll, _c_double_p, ctypes.c_int, _c_double_p]),
     "gpb_stage_ms": (ctypes.c_int, [ctypes.c_void_p, _c_double_p]),
     "gpb_launch_count": (_ll, [ctypes.c_void_p]),
+    "gpb_debug_plan": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, _ll, ctypes.c_void_p, _ll,
+                                      ctypes.POINTER(_ll)]),
     "gpb_debug_gemm": (ctypes.c_int, [ctypes.c_void_p, _c_double_p, _c_double_p, _c_double_p, _ll, _ll, _ll,
                                       ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_int,
                                       ctypes.POINTER(ctypes.c_double)]),

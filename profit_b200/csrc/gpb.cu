@@ -1953,6 +1953,44 @@ int gpb_solve_cholesky(gpb_handle_t h, const double* L, long long n, const doubl
   return 0;
 }
 
+int gpb_debug_plan(int n_blocks, int which, int* tasks_out, long long task_cap, double* launches_out, long long launch_cap,
+                   long long* counts) {
+  if (n_blocks < 1 || !counts) return -1;
+  Workspace w;
+  w.Nb = n_blocks;
+  w.Np = (long long)n_blocks * 128;
+  w.N = w.Np;
+  build_potrf_plan(w);     // also fixes the phase cuts that build_trtri_plan splits by
+  build_trtri_plan(w);
+  build_syrk_plan(w);
+  const Plan* p = nullptr;
+  if (which == 0) p = &w.potrf;
+  else if (which == 1) p = &w.trtri;
+  else if (which == 2) p = &w.syrk;
+  else if (which == 20) p = &w.trtri_late;
+  else if (which >= 10 && which < 10 + w.n_phase) p = &w.trtri_phase[which - 10];
+  counts[0] = p ? (long long)p->tasks.size() : 0;
+  counts[1] = p ? (long long)p->launches.size() : 0;
+  counts[2] = w.n_phase;
+  for (int i = 0; i < Workspace::MAX_PHASE; ++i) counts[3 + i] = i < w.n_phase ? w.phase_cut[i] : -1;
+  if (!p) return which >= 10 && which < 10 + Workspace::MAX_PHASE ? 0 : -1;
+  if (tasks_out && task_cap >= counts[0])
+    for (size_t t = 0; t < p->tasks.size(); ++t) {
+      const GemmTask& k = p->tasks[t];
+      const int row[8] = {k.a_row, k.a_k, k.b_row, k.b_k, k.nk, k.c_row, k.c_col, k.aux};
+      memcpy(tasks_out + 8 * t, row, sizeof(row));
+    }
+  if (launches_out && launch_cap >= counts[1])
+    for (size_t l = 0; l < p->launches.size(); ++l) {
+      const Launch& L = p->launches[l];
+      const double row[16] = {(double)L.type, (double)L.k, (double)L.cfg, (double)L.matA, (double)L.matB, (double)L.matC,
+                              (double)L.matCt, L.alpha, L.beta, (double)L.task_off, (double)L.ntasks, (double)L.epi,
+                              (double)L.stream, (double)L.wait_ev, (double)L.wait_ev2, (double)L.rec_ev};
+      memcpy(launches_out + 16 * l, row, sizeof(row));
+    }
+  return 0;
+}
+
 int gpb_debug_gemm(gpb_handle_t h, const double* A, const double* B, double* C, long long M, long long N, long long K,
                    int cfg, double alpha, double beta, int reps, double* ms) {
   if (!h || !A || !B || !C || M % 128 || N % 128 || K % 128 || cfg < 0 || cfg >= NUM_CFG || reps < 1)
