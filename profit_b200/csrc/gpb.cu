@@ -1972,7 +1972,10 @@ int gpb_debug_plan(int n_blocks, int which, int* tasks_out, long long task_cap, 
   counts[0] = p ? (long long)p->tasks.size() : 0;
   counts[1] = p ? (long long)p->launches.size() : 0;
   counts[2] = w.n_phase;
-  for (int i = 0; i < Workspace::MAX_PHASE; ++i) counts[3 + i] = i < w.n_phase ? w.phase_cut[i] : -1;
+  for (int i = 0; i < Workspace::MAX_PHASE; ++i) {
+    counts[3 + i] = i < w.n_phase ? w.phase_cut[i] : -1;
+    counts[7 + i] = i < w.n_phase ? w.phase_ev[i] : -1;
+  }
   if (!p) return which >= 10 && which < 10 + Workspace::MAX_PHASE ? 0 : -1;
   if (tasks_out && task_cap >= counts[0])
     for (size_t t = 0; t < p->tasks.size(); ++t) {

@@ -22,7 +22,7 @@ def lib(built_lib):
 
 
 def get_plan(lib, nb, which):
-    counts = (ctypes.c_longlong * 8)()
+    counts = (ctypes.c_longlong * 11)()
     assert lib.gpb_debug_plan(nb, which, None, 0, None, 0, counts) == 0
     nt, nl = int(counts[0]), int(counts[1])
     tasks = np.zeros((max(nt, 1), 8), dtype=np.int32)
@@ -30,6 +30,7 @@ def get_plan(lib, nb, which):
     assert lib.gpb_debug_plan(nb, which, tasks.ctypes.data_as(ctypes.c_void_p), nt, launches.ctypes.data_as(ctypes.c_void_p),
                               nl, counts) == 0
     cuts = [int(c) for c in counts[3:3 + int(counts[2])]]
+    get_plan.phase_events = [int(c) for c in counts[7:7 + int(counts[2])]]
     return tasks[:nt], launches[:nl], cuts
 
 
@@ -157,3 +158,125 @@ def test_early_phases_partition_the_triangular_inverse(lib):
     Winv = np.linalg.inv(Lref)
     assert np.max(np.abs(np.tril(mats[M_W]) - Winv)) <= 1e-10 * np.abs(Winv).max()
     assert np.max(np.abs(np.triu(mats[M_U]) - Winv.T)) <= 1e-10 * np.abs(Winv).max()
+
+
+# ------------------------------------------------------------------------------------------ static race check
+def _footprints(tasks, launches, nb, extra_rows=1):
+    """Per launch: boolean read / write masks over 128x128 tiles of the four matrices (L has one extra block row)."""
+    shapes = {M_L: (nb + extra_rows, nb), M_U: (nb, nb), M_W: (nb, nb), M_DINV: (nb, 1)}
+    offs, tot = {}, 0
+    for m, (r, c) in shapes.items():
+        offs[m] = (tot, r, c)
+        tot += r * c
+
+    def mark(mask, m, r0, r1, c0, c1):
+        o, r, c = offs[m]
+        view = mask[o:o + r * c].reshape(r, c)
+        view[r0 // 128:(r1 + 127) // 128, c0 // 128:(c1 + 127) // 128] = True
+
+    R = np.zeros((len(launches), tot), dtype=bool)
+    W = np.zeros((len(launches), tot), dtype=bool)
+    for n, L in enumerate(launches):
+        typ, k, cfg, mA, mB, mC, mCt = (int(x) for x in L[:7])
+        beta, off, nt = L[8], int(L[9]), int(L[10])
+        if typ == 0:                                   # diagonal block: L_kk in place, inverse into Dinv
+            mark(R[n], M_L, k * 128, k * 128 + 128, k * 128, k * 128 + 128)
+            mark(W[n], M_L, k * 128, k * 128 + 128, k * 128, k * 128 + 128)
+            mark(W[n], M_DINV, k * 128, k * 128 + 128, 0, 128)
+            continue
+        if typ == 2:                                   # seed of the U / W diagonal tiles from Dinv, blocks [k, cfg)
+            for b in range(k, cfg):
+                mark(R[n], M_DINV, b * 128, b * 128 + 128, 0, 128)
+                mark(W[n], M_U, b * 128, b * 128 + 128, b * 128, b * 128 + 128)
+                mark(W[n], M_W, b * 128, b * 128 + 128, b * 128, b * 128 + 128)
+            continue
+        bm, bn = TILE[cfg]
+        for a_row, a_k, b_row, b_k, nk, c_row, c_col, _aux in tasks[off:off + nt]:
+            mark(R[n], mA, a_row, a_row + bm, a_k, a_k + 16 * nk)
+            mark(R[n], mB, b_row, b_row + bn, b_k, b_k + 16 * nk)
+            mark(W[n], mC, c_row, c_row + bm, c_col, c_col + bn)
+            if beta != 0.0:
+                mark(R[n], mC, c_row, c_row + bm, c_col, c_col + bn)
+            if mCt != M_NONE:
+                mark(W[n], mCt, c_col, c_col + bn, c_row, c_row + bm)
+    return R, W
+
+
+def _happens_before(launches):
+    """reach[j] = bitmask of launches ordered before j by stream order and event record -> wait pairs (run_plan)."""
+    last_on_stream, last_record, reach = {}, {}, []
+    for j, L in enumerate(launches):
+        stream, waits, rec = int(L[12]), [int(L[13]), int(L[14])], int(L[15])
+        preds = [last_on_stream[stream]] if stream in last_on_stream else []
+        preds += [last_record[e] for e in waits if e >= 0 and e in last_record]
+        bits = 1 << j
+        for p in preds:
+            bits |= reach[p]
+        reach.append(bits)
+        last_on_stream[stream] = j
+        if rec >= 0:
+            last_record[rec] = j
+    return reach
+
+
+def _assert_race_free(tasks, launches, nb):
+    R, W = _footprints(tasks, launches, nb)
+    reach = _happens_before(launches)
+    RW = R | W
+    for j in range(len(launches)):
+        if j == 0:
+            continue
+        conflict = (W[:j] & RW[j]).any(axis=1) | (R[:j] & W[j]).any(axis=1)
+        for i in np.nonzero(conflict)[0]:
+            assert (reach[j] >> int(i)) & 1, (
+                f"launches {int(i)} (stream {int(launches[i][12])}) and {j} (stream {int(launches[j][12])}) touch the same "
+                f"tiles without an ordering path")
+
+
+@pytest.mark.parametrize("nb", [3, 9, 24, 40, 70])
+def test_cholesky_plan_orders_every_conflicting_pair_of_launches(lib, nb):
+    """Static race check of the multi-stream Cholesky: any two launches whose tile footprints conflict (write/write or
+    read/write) must be ordered by stream order or by an event record -> wait pair."""
+    tasks, launches, _ = get_plan(lib, nb, 0)
+    _assert_race_free(tasks, launches, nb)
+    if nb >= 24:
+        assert {int(L[12]) for L in launches} == {0, 1, 2}
+
+
+def test_removing_an_event_is_detected(lib):
+    """The checker itself: dropping the wait of one trailing update on its panel's event must raise."""
+    tasks, launches, _ = get_plan(lib, 24, 0)
+    broken = launches.copy()
+    victim = next(n for n, L in enumerate(broken) if L[0] == 1 and int(L[12]) == 0 and int(L[13]) >= 0)
+    broken[victim, 13] = -1
+    with pytest.raises(AssertionError, match="without an ordering path"):
+        _assert_race_free(tasks, broken, 24)
+
+
+def test_early_inverse_phases_are_ordered_after_the_columns_they_read(lib):
+    """The early phases of the triangular inverse run on their own stream while the Cholesky continues: appended to
+    the Cholesky's launch list the way assemble_and_factor issues them (wait on the phase event, seed the diagonal
+    tiles, run the phase), the combined list must still be race free."""
+    nb = 48
+    tasks, launches, cuts = get_plan(lib, nb, 0)
+    events = list(get_plan.phase_events)               # the events assemble_and_factor makes stream3 wait for
+    all_tasks, all_launches = [tasks], [launches]
+    off = len(tasks)
+    k0 = 0
+    for i, cut in enumerate(cuts):
+        ev = events[i]
+        assert any(int(L[15]) == ev for L in launches)
+        seed = np.zeros((1, 16))
+        seed[0, :3] = [2, k0, cut]                      # pseudo launch: seed blocks [k0, cut)
+        seed[0, 3:7] = M_NONE
+        seed[0, 12:16] = [3, ev, -1, -1]
+        k0 = cut
+        pt, pl, _ = get_plan(lib, nb, 10 + i)
+        pl = pl.copy()
+        pl[:, 9] += off
+        pl[:, 12] = 3                                   # stream3
+        pl[:, 13:16] = -1
+        all_tasks.append(pt)
+        all_launches += [seed, pl]
+        off += len(pt)
+    _assert_race_free(np.vstack(all_tasks), np.vstack(all_launches), nb)
