@@ -14,6 +14,14 @@
 //   trtri : recursive  U12 = -U11 L21^T U22  evaluated level by level as two batched NT GEMMs.
 //   syrk  : K^-1 = U U^T (lower).                                          (invert_cholesky, gp_functions.py:304-322)
 //   predict variance : ||W k*||^2 as a tile GEMM with a column sum-of-squares epilogue.
+//   predict covariance: K** - Vt Vt^T, Vt = K*^T W^T (two tile GEMMs).
+//
+// Scheduling (build_potrf_plan / run_plan): one panel of look-ahead on a high-priority stream, large trailing updates
+// split over two streams by block-column parity, leading sub-trees of the triangular inverse started on a low-priority
+// stream while the Cholesky is still running.  tests/test_plans.py replays and race-checks these lists on the host.
+//
+// Active learning (acquisition.cuh): acquisition losses + masked arg-max on device-resident predictions, and the
+// O(N^2) extension of W, U, alpha, z, log|K| by one observed point (gpb_append_train).
 #include "../../include/gpb.h"
 
 #include <algorithm>
