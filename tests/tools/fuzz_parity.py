@@ -1,6 +1,6 @@
 """Randomised parity sweep against the oracle (developer tool; the fixed cases live in tests/)."""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import oracle
 from profit_b200 import GPBackend

@@ -1,6 +1,6 @@
 """Developer check on a GPU box: GEMM kernel vs torch, factorisation / NLL / predict vs the oracle, timings."""
 import sys, time, json, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 import oracle
 from profit_b200 import GPBackend, KIND_RBF, KIND_MATERN52

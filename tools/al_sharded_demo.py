@@ -14,7 +14,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-import oracle
+from _data import synthetic_problem
 from profit_b200 import B200GPSurrogate
 from profit_b200 import acquisition as acq
 
@@ -27,7 +27,7 @@ ws = dist.get_world_size() if dist.is_initialized() else 1
 M = 1 << (int(sys.argv[1]) if len(sys.argv) > 1 else 22)
 kind = sys.argv[2] if len(sys.argv) > 2 else "expected_improvement"
 N, D = 8192, 10
-X, y = oracle.synthetic_problem(N, D)
+X, y = synthetic_problem(N, D)
 theta = np.concatenate([np.linspace(0.6, 1.2, D), [1.5, 0.3]])
 Xpred = np.random.default_rng(2).random((M, D))
 s = B200GPSurrogate(local)

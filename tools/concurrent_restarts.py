@@ -2,11 +2,11 @@
 import sys, os, time, threading
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
-import oracle
+from _data import synthetic_problem
 from profit_b200 import GPBackend, KIND_MATERN52
 
 def run(N, D, streams, evals):
-    X, y = oracle.synthetic_problem(N, D)
+    X, y = synthetic_problem(N, D)
     th0 = np.concatenate([np.linspace(0.6, 1.2, D), [1.5, 0.3]])
     bes = [GPBackend(0) for _ in range(streams)]
     for be in bes:

@@ -4,7 +4,7 @@ import numpy as np, torch, oracle
 from profit_b200 import GPBackend, KIND_RBF
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
 be = GPBackend(0)
-X, y = oracle.synthetic_problem(N, 8)
+X, y = synthetic_problem(N, 8)
 theta = np.concatenate([np.linspace(0.6, 1.2, 8), [1.5, 0.3]])
 K = be.kernel_matrix(KIND_RBF, X, X, theta[:8], 1.5, 0.3)
 Lt = torch.linalg.cholesky(torch.from_numpy(K).cuda()).cpu().numpy()

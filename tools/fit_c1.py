@@ -8,11 +8,11 @@ import time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 
-import oracle
+from _data import synthetic_problem
 from profit_b200 import RBF, GPBackend, gp_functions as gpf
 
 N, D = 4096, 8
-X, y = oracle.synthetic_problem(N, D)
+X, y = synthetic_problem(N, D)
 theta_ref = np.concatenate([np.linspace(0.6, 1.2, D), [1.5, 0.3]])
 a0 = theta_ref * 10 ** (0.3 * (np.random.default_rng(5).random(D + 2) - 0.5))
 be = GPBackend(0)

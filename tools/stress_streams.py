@@ -16,13 +16,13 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     sys.path.insert(0, ROOT)
     import numpy as np
 
-    import oracle
+    from _data import synthetic_problem
     from profit_b200 import GPBackend
 
     be = GPBackend(0)
     out = {}
     for N, D in SIZES:
-        X, y = oracle.synthetic_problem(N, D)
+        X, y = synthetic_problem(N, D)
         theta = np.concatenate([np.linspace(0.6, 1.2, D), [1.5, 0.3]])
         be.set_train(X, y)
         res = []

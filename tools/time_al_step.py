@@ -10,7 +10,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 
-import oracle
+from _data import synthetic_problem
 from profit_b200 import GPBackend, KIND_MATERN52
 from profit_b200 import backend as B
 
@@ -30,7 +30,7 @@ def main():
     out = []
     D = 10
     for N, M in ((512, 1 << 20), (2048, 1 << 19), (8192, 1 << 17), (16384, 1 << 16)):
-        X, y = oracle.synthetic_problem(N + 8, D)
+        X, y = synthetic_problem(N + 8, D)
         theta = np.concatenate([np.linspace(0.6, 1.2, D), [1.5, 0.3]])
         Xc = np.random.default_rng(2).random((M, D))
         be = GPBackend(0)

@@ -2,11 +2,11 @@
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
-import oracle
+from _data import synthetic_problem
 from profit_b200 import GPBackend, KIND_RBF
 be = GPBackend(0)
 for (N, D) in ((8192, 16), (16384, 10)):
-    X, y = oracle.synthetic_problem(N, D)
+    X, y = synthetic_problem(N, D)
     theta = np.concatenate([np.linspace(0.6, 1.2, D), [1.5, 0.3]])
     be.set_train(X, y)
     be.nll(KIND_RBF, theta, want_grad=True)

@@ -6,13 +6,13 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 
-import oracle
+from _data import synthetic_problem
 from profit_b200 import GPBackend, KIND_MATERN52
 
 D = 10
 be = GPBackend(0)
 for N, M in ((256, 1 << 20), (512, 1 << 20), (1024, 1 << 19), (2048, 1 << 18), (4096, 1 << 17), (8192, 1 << 16)):
-    X, y = oracle.synthetic_problem(N, D)
+    X, y = synthetic_problem(N, D)
     theta = np.concatenate([np.linspace(0.6, 1.2, D), [1.5, 0.3]])
     be.set_train(X, y)
     be.factorize(KIND_MATERN52, theta)

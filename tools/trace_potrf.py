@@ -12,7 +12,7 @@ import torch
 from profit_b200 import _lib
 
 _lib.LIB_PATH = os.path.join(os.path.dirname(_lib.LIB_PATH), "libgpb_trace.so")
-import oracle
+from _data import synthetic_problem
 from profit_b200 import GPBackend, KIND_RBF
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
@@ -22,7 +22,7 @@ be = GPBackend(0)
 lib = be._lib
 lib.gpb_debug_trace.restype = ctypes.c_int
 lib.gpb_debug_trace.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint, ctypes.POINTER(ctypes.c_uint)]
-X, y = oracle.synthetic_problem(N, D)
+X, y = synthetic_problem(N, D)
 theta = np.concatenate([np.linspace(0.6, 1.2, D), [1.5, 0.3]])
 be.set_train(X, y)
 for _ in range(2):
