@@ -84,9 +84,26 @@ class GPBackend:
         self.factor_key = None
         _lib.check(self._lib.gpb_factorize(self._h, int(kind), _lib.ptr(theta), theta.size - 2), self._h, "factorize")
 
-    def predict(self, Xc, add_data_variance=True, out_mean=None, out_var=None, want_mean=True, want_var=True):
+    def _check_candidates(self, Xc):
         Xc = _lib.as_f64(Xc)
+        if Xc.ndim != 2 or int(Xc.shape[1]) != self.d:
+            raise ValueError(f"Xpred should have shape (n, {self.d}) but has shape {tuple(Xc.shape)}")
+        return Xc
+
+    @staticmethod
+    def _check_out(out, shape, name):
+        """A caller-provided output buffer must hold exactly the result (trailing unit axes are tolerated)."""
+        if out is None:
+            return
+        got = tuple(int(v) for v in out.shape)
+        if int(np.prod(got)) != int(np.prod(shape)) or (got[:1] != tuple(shape[:1])):
+            raise ValueError(f"{name} should have shape {tuple(shape)} but has shape {got}")
+
+    def predict(self, Xc, add_data_variance=True, out_mean=None, out_var=None, want_mean=True, want_var=True):
+        Xc = self._check_candidates(Xc)
         M = int(Xc.shape[0])
+        self._check_out(out_mean, (M, self.n_out), "out_mean")
+        self._check_out(out_var, (M,), "out_var")
         if want_mean and out_mean is None:
             out_mean = np.empty((M, self.n_out))
         if want_var and out_var is None:
@@ -98,8 +115,9 @@ class GPBackend:
 
     def predict_cov(self, Xc, noise_on_diagonal=True, want_mean=True, out_cov=None):
         """Full (M, M) predictive covariance [and the mean] -- predict_f(..., return_full_cov=True)."""
-        Xc = _lib.as_f64(Xc)
+        Xc = self._check_candidates(Xc)
         M = int(Xc.shape[0])
+        self._check_out(out_cov, (M, M), "out_cov")
         mean = np.empty((M, self.n_out)) if want_mean else None
         cov = np.empty((M, M)) if out_cov is None else out_cov
         st = self._lib.gpb_predict_cov(self._h, _lib.ptr(Xc), M, int(bool(noise_on_diagonal)), _lib.ptr(mean), _lib.ptr(cov))
@@ -108,7 +126,7 @@ class GPBackend:
 
     def marginal_variance(self, Xc, hess_inv, predictive_variance=None):
         """dm^T H^-1 dm + predictive variance per candidate (gp_functions.marginal_variance_BBQ) -> (M,) array."""
-        Xc = _lib.as_f64(Xc)
+        Xc = self._check_candidates(Xc)
         H = np.ascontiguousarray(hess_inv, dtype=np.float64)
         M = int(Xc.shape[0])
         pv = None if predictive_variance is None else np.ascontiguousarray(predictive_variance, dtype=np.float64).ravel()

@@ -568,6 +568,10 @@ def test_argument_errors_are_reported_not_crashed(backend):
         backend.nll(7, np.array([1.0, 1.0, 0.1]))                             # unknown kernel kind
     with pytest.raises(ValueError):
         RBF(X, X, np.array([1.0, 2.0]), 1.0, 0.0)                             # length_scale of the wrong size
+    with pytest.raises(ValueError):
+        backend.predict(np.zeros((4, X.shape[1] + 1)))                        # candidates of the wrong dimension
+    with pytest.raises(ValueError):
+        backend.predict(np.zeros((4, X.shape[1])), out_var=np.empty(3))       # output buffer of the wrong size
     fresh = GPBackend(0)
     with pytest.raises(RuntimeError):
         fresh.nll(0, np.array([1.0, 1.0, 0.1]))                               # no training set yet
