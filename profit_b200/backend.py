@@ -128,6 +128,8 @@ class GPBackend:
         """dm^T H^-1 dm + predictive variance per candidate (gp_functions.marginal_variance_BBQ) -> (M,) array."""
         Xc = self._check_candidates(Xc)
         H = np.ascontiguousarray(hess_inv, dtype=np.float64)
+        if H.ndim != 2 or H.shape[0] != H.shape[1]:
+            raise ValueError(f"hess_inv should be a square (P, P) matrix but has shape {H.shape}")
         M = int(Xc.shape[0])
         pv = None if predictive_variance is None else np.ascontiguousarray(predictive_variance, dtype=np.float64).ravel()
         out = np.empty(M)
@@ -196,6 +198,12 @@ class GPBackend:
         [min, max] of var (sqrt(var) for ACQ_EI) when ``var`` is one shard of the candidate set."""
         var = _lib.as_f64(var)
         M = int(var.shape[0])
+        self._check_out(var, (M,), "var")
+        if term is not None:
+            self._check_out(term, (M, int(n_out)), "term")
+        if extra is not None and int(extra.shape[0]) != M:
+            raise ValueError(f"extra should have {M} rows but has shape {tuple(extra.shape)}")
+        self._check_out(loss_out, (M,), "loss_out")
         params = np.ascontiguousarray(params, dtype=np.float64).ravel()
         vis = (ctypes.c_longlong * max(1, len(visited)))(*[int(v) for v in visited])
         idx = ctypes.c_longlong()
@@ -215,7 +223,11 @@ class GPBackend:
         Xa = _lib.as_f64(Xa)
         Xb = _lib.as_f64(Xb)
         ell = np.ascontiguousarray(ell, dtype=np.float64).ravel()
+        if Xa.ndim != 2 or Xb.ndim != 2 or int(Xa.shape[1]) != int(Xb.shape[1]):
+            raise ValueError(f"X and Y should have shapes (n, d) and (m, d) but have {tuple(Xa.shape)} and {tuple(Xb.shape)}")
         na, nb, d = int(Xa.shape[0]), int(Xb.shape[0]), int(Xa.shape[1])
+        if ell.size not in (1, d):
+            raise ValueError(f"length_scale must be a scalar or have {d} entries, got {ell.size}")
         K = np.empty((na, nb)) if out_K is None else out_K
         dK = (np.empty((na, nb, ell.size + 2)) if out_dK is None else out_dK) if eval_gradient else None
         st = self._lib.gpb_kernel_matrix(self._h, int(kind), _lib.ptr(Xa), na, _lib.ptr(Xb), nb, d, _lib.ptr(ell),
@@ -223,14 +235,21 @@ class GPBackend:
         _lib.check(st, self._h, "kernel_matrix")
         return (K, dK) if eval_gradient else K
 
+    @staticmethod
+    def _check_square(A, name):
+        if A.ndim != 2 or int(A.shape[0]) != int(A.shape[1]):
+            raise ValueError(f"{name} should be a square matrix but has shape {tuple(A.shape)}")
+
     def cholesky(self, A):
         A = _lib.as_f64(A)
+        self._check_square(A, "A")
         L = np.empty_like(A)
         _lib.check(self._lib.gpb_cholesky(self._h, _lib.ptr(A), int(A.shape[0]), _lib.ptr(L)), self._h, "cholesky")
         return L
 
     def invert_cholesky(self, L):
         L = _lib.as_f64(L)
+        self._check_square(L, "L")
         out = np.empty_like(L)
         _lib.check(self._lib.gpb_invert_cholesky(self._h, _lib.ptr(L), int(L.shape[0]), _lib.ptr(out)), self._h,
                    "invert_cholesky")
@@ -239,6 +258,9 @@ class GPBackend:
     def solve_cholesky(self, L, b):
         L = _lib.as_f64(L)
         b = _lib.as_f64(b)
+        self._check_square(L, "L")
+        if b.ndim not in (1, 2) or int(b.shape[0]) != int(L.shape[0]):
+            raise ValueError(f"b should have {int(L.shape[0])} rows but has shape {tuple(b.shape)}")
         nrhs = 1 if b.ndim == 1 else int(b.shape[1])
         x = np.empty_like(b)
         _lib.check(self._lib.gpb_solve_cholesky(self._h, _lib.ptr(L), int(L.shape[0]), _lib.ptr(b), nrhs, _lib.ptr(x)),
