@@ -228,6 +228,9 @@ class GPBackend:
         na, nb, d = int(Xa.shape[0]), int(Xb.shape[0]), int(Xa.shape[1])
         if ell.size not in (1, d):
             raise ValueError(f"length_scale must be a scalar or have {d} entries, got {ell.size}")
+        if na == 0 or nb == 0:     # nothing to evaluate: the reference returns empty arrays of these shapes
+            K0, dK0 = np.empty((na, nb)), np.empty((na, nb, ell.size + 2))
+            return (K0, dK0) if eval_gradient else K0
         K = np.empty((na, nb)) if out_K is None else out_K
         dK = (np.empty((na, nb, ell.size + 2)) if out_dK is None else out_dK) if eval_gradient else None
         st = self._lib.gpb_kernel_matrix(self._h, int(kind), _lib.ptr(Xa), na, _lib.ptr(Xb), nb, d, _lib.ptr(ell),

@@ -287,3 +287,16 @@ def test_acquisition_twins_mirror_the_reference_registry():
     alt.set_al_parameters(krun=0)
     with pytest.raises(TypeError, match="B200GPSurrogate"):      # no host path: a foreign surrogate is refused
         acq.SimpleExploration(Xp, object(), None).calculate_loss()
+
+
+def test_empty_kernel_matrix_needs_no_device():
+    """python_kernels.RBF on an empty operand returns empty arrays (n, 0) / (n, 0, P); so does the twin, without a call
+    into the library."""
+    from profit_b200.backend import GPBackend
+
+    be = GPBackend.__new__(GPBackend)              # no handle: the early return must not touch the device
+    K, dK = GPBackend.kernel_matrix(be, 0, np.zeros((5, 3)), np.zeros((0, 3)), [1.0, 2.0, 3.0], 1.0, 0.1, eval_gradient=True)
+    assert K.shape == (5, 0) and dK.shape == (5, 0, 5)
+    assert GPBackend.kernel_matrix(be, 1, np.zeros((0, 2)), np.zeros((4, 2)), [1.0], 1.0, 0.1).shape == (0, 4)
+    with pytest.raises(ValueError):
+        GPBackend.kernel_matrix(be, 0, np.zeros((5, 3)), np.zeros((4, 2)), [1.0], 1.0, 0.1)
