@@ -142,6 +142,10 @@ int gpb_kernel_matrix(gpb_handle_t h, int kind, const double* Xa, long long na, 
 int gpb_marginal_variance(gpb_handle_t h, const double* Xc, long long M, const double* hess_inv, const double* pred_var,
                           double* out);
 
+/* mean over all ordered pairs of |x_i - x_j| -- the data scale GaussianProcess.infer_hyperparameters derives the
+ * default length scale from (gaussian_process.py:124-136) without its (N, N, D) host tensor.  X: (n, d). */
+int gpb_mean_pairwise_distance(gpb_handle_t h, const double* X, long long n, int d, double* out);
+
 /* L = cholesky(A) (lower, upper zeroed) -- np.linalg.cholesky at gp_functions.py:143,341. A: (n, n). */
 int gpb_cholesky(gpb_handle_t h, const double* A, long long n, double* L);
 

@@ -238,6 +238,16 @@ class GPBackend:
         _lib.check(st, self._h, "kernel_matrix")
         return (K, dK) if eval_gradient else K
 
+    def mean_pairwise_distance(self, X):
+        """mean_ij |x_i - x_j| on the device (gaussian_process.py:126-128 without the (N, N, D) tensor)."""
+        X = _lib.as_f64(X)
+        if X.ndim != 2:
+            raise ValueError(f"X should have shape (n, d) but has shape {tuple(X.shape)}")
+        out = ctypes.c_double()
+        _lib.check(self._lib.gpb_mean_pairwise_distance(self._h, _lib.ptr(X), int(X.shape[0]), int(X.shape[1]),
+                                                        ctypes.byref(out)), self._h, "mean_pairwise_distance")
+        return float(out.value)
+
     @staticmethod
     def _check_square(A, name):
         if A.ndim != 2 or int(A.shape[0]) != int(A.shape[1]):

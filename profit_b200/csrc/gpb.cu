@@ -825,6 +825,41 @@ __global__ void cov_finish_kernel(const double* __restrict__ C, long long ldc, i
   out[e] = fmax(C[(long long)i * ldc + j], 1e-10);
 }
 
+// mean_ij |x_i - x_j| over all ordered pairs (GaussianProcess.infer_hyperparameters, gaussian_process.py:126-128):
+// one block per 64 rows, fixed-order reductions, partial sums per block.
+__global__ void __launch_bounds__(256) pairwise_distance_sum_kernel(const double* __restrict__ X, long long n, int d,
+                                                                   double* __restrict__ part) {
+  __shared__ double xi[64][MAX_D];
+  __shared__ double red[256];
+  const long long r0 = (long long)blockIdx.x * 64;
+  for (int e = threadIdx.x; e < 64 * d; e += 256) {
+    const long long r = r0 + e / d;
+    xi[e / d][e % d] = r < n ? X[r * d + e % d] : 0.0;
+  }
+  __syncthreads();
+  const int nrow = (n - r0 < 64) ? (int)(n - r0) : 64;
+  double s = 0.0;
+  for (long long j = threadIdx.x; j < n; j += 256) {
+    double xj[MAX_D];
+    for (int k = 0; k < d; ++k) xj[k] = X[j * d + k];
+    for (int r = 0; r < nrow; ++r) {
+      double a = 0.0;
+      for (int k = 0; k < d; ++k) {
+        const double u = xi[r][k] - xj[k];
+        a = fma(u, u, a);
+      }
+      s += sqrt(a);
+    }
+  }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) {
+    if ((int)threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) part[blockIdx.x] = red[0];
+}
+
 // ------------------------------------------------------------------------------------------------ helpers
 void stage_begin(H* h, int s) {
   cudaEventRecord(h->ev0[s], h->stream);
@@ -1893,6 +1928,26 @@ int gpb_acquire(gpb_handle_t h, int kind, const double* term, const double* var,
   CK(cudaStreamSynchronize(h->stream));
   if (val) *val = hv[0];
   memcpy(idx, &hv[1], sizeof(long long));
+  return 0;
+}
+
+int gpb_mean_pairwise_distance(gpb_handle_t h, const double* X, long long n, int d, double* out) {
+  if (!h || !X || !out || n < 1 || d < 1 || d > MAX_D) return fail(h, -1, "gpb_mean_pairwise_distance: bad argument");
+  CK(cudaSetDevice(h->device));
+  const long long nblk = (n + 63) / 64;
+  int rc = ensure_cap(h, &h->dstage, &h->dstage_cap, (size_t)n * d + (size_t)nblk + 8);
+  if (rc) return rc;
+  double* dX = h->dstage;
+  double* part = dX + (size_t)n * d;
+  CK(cudaMemcpyAsync(dX, X, (size_t)n * d * sizeof(double), cudaMemcpyDefault, h->stream));
+  pairwise_distance_sum_kernel<<<(unsigned)nblk, 256, 0, h->stream>>>(dX, n, d, part);
+  reduce_partials_kernel<<<1, 256, 0, h->stream>>>(part, (int)nblk, 1, part + nblk);
+  h->launches += 2;
+  CK(cudaGetLastError());
+  double sum = 0.0;
+  CK(cudaMemcpyAsync(&sum, part + nblk, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  *out = sum / ((double)n * (double)n);
   return 0;
 }
 

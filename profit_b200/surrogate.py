@@ -119,23 +119,6 @@ except Exception:  # profit not installed: stand-alone base with the same contra
             return self
 
 
-def _mean_pairwise_distance(X, block=2048):
-    """mean_ij |x_i - x_j| without the reference's (N, N, D) temporary (gaussian_process.py:126-128)."""
-    X = np.asarray(X, dtype=np.float64)
-    n = X.shape[0]
-    sq = np.einsum("ij,ij->i", X, X)
-    total = 0.0
-    for r0 in range(0, n, block):
-        r1 = min(n, r0 + block)
-        d2 = sq[r0:r1, None] + sq[None, :] - 2.0 * (X[r0:r1] @ X.T)
-        np.maximum(d2, 0.0, out=d2)
-        # exact zeros on the diagonal (the subtraction above leaves round-off there)
-        idx = np.arange(r0, r1)
-        d2[idx - r0, idx] = 0.0
-        total += np.sqrt(d2).sum()
-    return total / (float(n) * float(n))
-
-
 class B200GPSurrogate(_GPBase):
     """Custom GP on the B200: train / optimize / predict / add_training_data / set_ytrain, reference semantics.
 
@@ -183,10 +166,11 @@ class B200GPSurrogate(_GPBase):
 
     # -- reference API ----------------------------------------------------------------------------------
     def infer_hyperparameters(self):
-        """gaussian_process.py:124-136, with the pairwise mean evaluated block-wise (same value, O(N) memory)."""
+        """gaussian_process.py:124-136, with the pairwise mean distance evaluated on the device (same value, no
+        (N, N, D) tensor)."""
         std = np.std(self.ytrain, axis=0)
         spread = np.abs(self.ytrain.max(axis=0) - self.ytrain.min(axis=0))
-        dist = _mean_pairwise_distance(self.Xtrain)
+        dist = self.backend.mean_pairwise_distance(np.ascontiguousarray(self.Xtrain, dtype=np.float64))
         std, spread = np.mean(std), np.mean(spread)
         return {"length_scale": np.array([0.5 * dist]), "sigma_f": np.array([std]),
                 "sigma_n": 1e-2 * np.array([spread])}

@@ -753,3 +753,21 @@ def test_overlapped_schedule_is_bit_identical_to_the_serial_one(built_lib):
     out = subprocess.run([sys.executable, os.path.join(root, "tools", "stress_streams.py")], env=env, capture_output=True,
                          text=True, timeout=600)
     assert out.returncode == 0 and "stress ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_mean_pairwise_distance_and_inferred_defaults(backend):
+    """The data scale behind the default hyper-parameters (gaussian_process.py:124-136), computed on the device."""
+    from profit_b200 import B200GPSurrogate
+
+    rng = np.random.default_rng(4)
+    for n, d in ((1, 1), (5, 2), (64, 3), (65, 7), (700, 32)):
+        X = rng.random((n, d))
+        ref = np.linalg.norm(X[:, None, :] - X[None, :, :], axis=-1).mean()
+        got = backend.mean_pairwise_distance(X)
+        assert abs(got - ref) <= 1e-13 * max(ref, 1e-300) + 1e-300, (n, d, got, ref)
+    X, y = rng.random((300, 2)), rng.random(300)
+    s = B200GPSurrogate()
+    s.pre_train(X, y, kernel="RBF")
+    dist = np.linalg.norm(X[:, None, :] - X[None, :, :], axis=-1).mean()
+    assert np.allclose(s.hyperparameters["length_scale"], [0.5 * dist], rtol=1e-13)
+    assert np.allclose(s.hyperparameters["sigma_f"], [np.std(y)]) and np.allclose(s.hyperparameters["sigma_n"], [1e-2 * (y.max() - y.min())])
