@@ -771,3 +771,32 @@ def test_mean_pairwise_distance_and_inferred_defaults(backend):
     dist = np.linalg.norm(X[:, None, :] - X[None, :, :], axis=-1).mean()
     assert np.allclose(s.hyperparameters["length_scale"], [0.5 * dist], rtol=1e-13)
     assert np.allclose(s.hyperparameters["sigma_f"], [np.std(y)]) and np.allclose(s.hyperparameters["sigma_n"], [1e-2 * (y.max() - y.min())])
+
+
+def test_reference_fit_manual_and_optim_twins(backend, golden):
+    """tests/unit_tests/sur/test_kernels.py:143-194 with the device-backed functions: the manual fit on 128 Halton
+    points interpolates sin(2x0) + cos(3x1) to 1e-3 on a 20x20 grid (test_fit_manual), and the L-BFGS-B run of
+    test_optim (bounds of :188-194) goes through on the device objective and lowers the NLL."""
+    from scipy.optimize import minimize
+
+    from profit_b200 import RBF, gp_functions as gpf
+
+    h = golden["halton128"]
+    xtrain, ytrain = np.array(h["X"]), np.array(h["y"])
+    hyp = np.array([0.5, 0.5, 1.0, 1e-4])
+    Ky = RBF(xtrain, xtrain, hyp[:-2], *hyp[-2:])
+    L = gpf.cholesky(Ky) if hasattr(gpf, "cholesky") else backend.cholesky(Ky)
+    alpha = gpf.solve_cholesky(L, ytrain)
+    grid = np.mgrid[0:1:20j, 0:1:20j].reshape(2, 400).T
+    ymean = RBF(grid, xtrain, hyp[:2], 1, 0) @ alpha
+    yref = np.sin(2 * grid[:, 0]) + np.cos(3 * grid[:, 1])
+    assert np.allclose(ymean, yref, rtol=1e-3, atol=1e-3)
+
+    def cost(loghyp):
+        val, jac = gpf.negative_log_likelihood_cholesky(10**loghyp, xtrain, ytrain, RBF, eval_gradient=True,
+                                                        log_scale_hyp=True)
+        return val, jac                      # log_scale_hyp already applies the chain rule (gp_functions.py:184-186)
+
+    start = np.log10(np.array([0.3, 0.8, 2.0, 1e-2]))
+    res = minimize(cost, start, method="L-BFGS-B", jac=True, bounds=((-2, 2), (-2, 2), (-2, 2), (-4, 0)))
+    assert res.fun < cost(start)[0] - 10.0 and np.all(np.isfinite(res.x))
