@@ -82,6 +82,8 @@ except Exception:  # profit not installed: stand-alone base with the same contra
         def pre_predict(self, Xpred):                    # sur.py:187-221
             if not self.trained:
                 raise RuntimeError("Need to train() before predict()!")
+            if Xpred is None:                            # sur.py:200-201
+                Xpred = self.default_Xpred()
             Xpred = np.asarray(Xpred)
             if Xpred.ndim == 1:
                 Xpred = Xpred.reshape(-1, 1)
@@ -92,6 +94,13 @@ except Exception:  # profit not installed: stand-alone base with the same contra
             if Xpred.shape[1] != self.ndim:
                 raise ValueError(f"Xpred should have shape (n, {self.ndim}) but has shape {Xpred.shape}")
             return Xpred
+
+        def default_Xpred(self):                         # sur.py:399-420
+            if self.ndim > 3:
+                raise RuntimeError("Require x for prediction in > 3 dimensions!")
+            lo, hi = self.Xtrain.min(axis=0), self.Xtrain.max(axis=0)
+            axes = [np.linspace(a, b, 50) for a, b in zip(lo, hi)]
+            return np.hstack([g.flatten().reshape(-1, 1) for g in np.meshgrid(*axes)])
 
         def decode_training_data(self):
             pass

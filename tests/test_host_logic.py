@@ -304,3 +304,25 @@ def test_empty_kernel_matrix_needs_no_device():
     assert GPBackend.kernel_matrix(be, 1, np.zeros((0, 2)), np.zeros((4, 2)), [1.0], 1.0, 0.1).shape == (0, 4)
     with pytest.raises(ValueError):
         GPBackend.kernel_matrix(be, 0, np.zeros((5, 3)), np.zeros((4, 2)), [1.0], 1.0, 0.1)
+
+
+def test_reference_unit_tests_of_the_surrogate_plumbing():
+    """tests/unit_tests/sur/test_units.py: default hyper-parameters (:21-26), add_training_data (:29-46),
+    select_kernel (:49-53) and default_Xpred (:62-69) on the drop-in class."""
+    Xtrain = np.array([1, 2, 3, 4]).reshape(-1, 1)
+    ytrain = np.array([5, 6, 7, 8]).reshape(-1, 1)
+    sur = B200GPSurrogate()
+    sur._backend = OracleBackedFake()
+    sur.pre_train(Xtrain, ytrain)
+    assert np.allclose(sur.hyperparameters["length_scale"], [0.625], rtol=1e-15)
+    assert np.allclose(sur.hyperparameters["sigma_n"], [0.03], rtol=1e-15)
+    assert sur.hyperparameters["sigma_f"] == np.std(ytrain, axis=0)
+    Xadd, yadd = np.array([11, 12]).reshape(-1, 1), np.array([9, 10]).reshape(-1, 1)
+    sur = B200GPSurrogate()
+    sur.Xtrain, sur.ytrain = Xtrain, ytrain
+    sur.add_training_data(Xadd, yadd)
+    assert np.all(sur.Xtrain == np.concatenate([Xtrain, Xadd])) and np.all(sur.ytrain == np.concatenate([ytrain, yadd]))
+    assert sur.select_kernel("RBF") is kernels.RBF and sur.select_kernel("RBF").__name__ == "RBF"
+    sur = B200GPSurrogate()
+    sur.Xtrain, sur.ndim = Xtrain, 1
+    assert np.all(sur.default_Xpred() == np.linspace(Xtrain[0], Xtrain[-1], 50).reshape(-1, 1))
