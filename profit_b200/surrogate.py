@@ -2,7 +2,7 @@
 
 Same method set, argument meaning, attribute names and error behaviour; the numerics run in libgpb on the GPU.
 When ``profit`` is importable the class subclasses ``profit.sur.gp.GaussianProcess`` and registers itself as
-``Surrogate["B200"]`` (config: ``fit: {surrogate: B200}`` + ``include: <path to this file>``); call
+``Surrogate["B200"]`` (config: ``fit: {surrogate: B200}`` + ``include: <repo>/profit_b200_include.py``); call
 ``register_as_custom()`` to also take over the hard-coded ``Surrogate["Custom"]`` of McmcAL (mcmc_al.py:101-102).
 Without ``profit`` (e.g. on a bare GPU box) a minimal stand-in base class restates the checks of
 ``Surrogate.pre_train`` / ``pre_predict`` (sur.py:136-164,187-221) and ``GaussianProcess.pre_train``

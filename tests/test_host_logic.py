@@ -227,12 +227,42 @@ def test_world_size_2_gloo_gathers(tmp_path):
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/profit"), reason="reference tree not mounted")
-def test_registers_with_profit_when_available():
-    code = ("import profit_b200.surrogate as s; from profit.sur import Surrogate; from profit.sur.gp import GaussianProcess;"
-            "c = Surrogate['B200']; assert c is s.B200GPSurrogate and issubclass(c, GaussianProcess); print('registered')")
-    env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + "/root/reference", PYTHONDONTWRITEBYTECODE="1")
-    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
-    assert out.returncode == 0 and "registered" in out.stdout, out.stderr
+def _profit_path():
+    """The unmodified reference: the pip-installed copy that travels with the repo, else the mounted tree."""
+    for p in (os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
+        if os.path.isdir(os.path.join(p, "profit")):
+            return p
+    return None
+
+
+@pytest.mark.skipif(_profit_path() is None, reason="proFit itself is not available")
+def test_registers_with_profit_through_its_include_mechanism():
+    """`include: profit_b200_include.py` as proFit processes it (config.py:309-320 -> util.load_includes, which runs the
+    file as a stand-alone module): the surrogates and the acquisition twins land in proFit's registries."""
+    shim = os.path.join(ROOT, "profit_b200_include.py")
+    code = f"""
+from profit.util import load_includes
+load_includes([{shim!r}])
+from profit.sur import Surrogate
+from profit.sur.gp import GaussianProcess
+from profit.al.aquisition_functions import AcquisitionFunction
+import profit_b200.surrogate as s, profit_b200.acquisition as a
+assert Surrogate['B200'] is s.B200GPSurrogate and issubclass(Surrogate['B200'], GaussianProcess)
+assert Surrogate['B200MultiOutputGP'] is s.B200MultiOutputGPSurrogate
+assert AcquisitionFunction['b200_simple_exploration'] is a.SimpleExploration
+assert issubclass(a.ExpectedImprovement, AcquisitionFunction)
+assert Surrogate['Custom'] is not s.B200GPSurrogate          # the reference's own labels are untouched by default
+print('registered')
+"""
+    env = dict(os.environ, PYTHONPATH=_profit_path(), PYTHONDONTWRITEBYTECODE="1")
+    env.pop("PROFIT_B200_TAKE_OVER", None)
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300, cwd="/tmp")
+    assert out.returncode == 0 and "registered" in out.stdout, out.stderr[-3000:]
+    env["PROFIT_B200_TAKE_OVER"] = "1"
+    code2 = code.replace("assert Surrogate['Custom'] is not s.B200GPSurrogate", "assert Surrogate['Custom'] is s.B200GPSurrogate and "
+                         "AcquisitionFunction['simple_exploration'] is a.SimpleExploration")
+    out = subprocess.run([sys.executable, "-c", code2], env=env, capture_output=True, text=True, timeout=300, cwd="/tmp")
+    assert out.returncode == 0 and "registered" in out.stdout, out.stderr[-3000:]
 
 
 def test_add_training_data_extends_the_factor_only_when_it_is_current():

@@ -15,7 +15,9 @@ import numpy as np
 from profit.sur import Surrogate
 from profit.sur.gp import GaussianProcess
 from profit.al.aquisition_functions import SimpleExploration
-import profit_b200.surrogate as ps                      # self-registers as Surrogate["B200"]
+from profit.util import load_includes
+load_includes([SHIM])                                    # what `include: profit_b200_include.py` does (config.py:309-320)
+import profit_b200.surrogate as ps                      # registered as Surrogate["B200"] by the include
 
 assert Surrogate["B200"] is ps.B200GPSurrogate and issubclass(Surrogate["B200"], GaussianProcess)
 rng = np.random.default_rng(0)
@@ -84,7 +86,7 @@ print("profit integration ok", hg)
 @pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "profit")), reason="reference not installed in baseline/_ref")
 def test_profit_drives_the_b200_surrogate(built_lib, tmp_path):
     script = tmp_path / "integration.py"
-    script.write_text(_SCRIPT)
-    env = dict(os.environ, PYTHONPATH=REF + os.pathsep + ROOT, PYTHONDONTWRITEBYTECODE="1")
+    script.write_text(_SCRIPT.replace("SHIM", repr(os.path.join(ROOT, "profit_b200_include.py"))))
+    env = dict(os.environ, PYTHONPATH=REF, PYTHONDONTWRITEBYTECODE="1")     # the include shim adds the repository itself
     out = subprocess.run([sys.executable, str(script)], env=env, capture_output=True, text=True, timeout=900, cwd=str(tmp_path))
     assert out.returncode == 0 and "profit integration ok" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
