@@ -78,6 +78,38 @@ for label, kw, arg in pairs:
     assert int(np.argmax(rl)) == int(np.argmax(gl)), label
 pa.register_as_default()
 assert AcquisitionFunction["simple_exploration"] is pa.SimpleExploration
+
+# the configuration route: profit.yaml with `include:` + `fit: {surrogate: B200}` as proFit's own Config reads it
+# (config.py:309-320, :397-402), then from_config -> train -> save_model -> load_model -> predict
+open("profit.yaml", "w").write("""
+ntrain: 10
+include: %s
+variables:
+    u: Uniform(0, 1)
+    v: Uniform(0, 1)
+    f: Output
+run:
+    worker: {class: function, entry_point: f}
+fit:
+    surrogate: B200
+    kernel: Matern52
+    save: ./model_b200.npz
+active_learning:
+    algorithm:
+        class: simple
+        acquisition_function: {class: b200_expected_improvement, exploration_factor: 0.05}
+""" % SHIM)
+from profit.config import BaseConfig
+cfg = BaseConfig.from_file("profit.yaml")
+sur = Surrogate[cfg["fit"]["surrogate"]].from_config(cfg["fit"], cfg)
+assert type(sur) is ps.B200GPSurrogate and sur.kernel == "Matern52" and sur.hyperparameters["length_scale"] is None
+sur.train(X, y)
+assert sur.trained and sur.kernel.__name__ == "Matern52"
+sur.save_model(cfg["fit"]["save"])
+again = Surrogate["B200"].load_model(cfg["fit"]["save"])
+m1, v1 = sur.predict(Xc); m2, v2 = again.predict(Xc)
+assert np.array_equal(m1, m2) and np.array_equal(v1, v2)
+assert cfg["active_learning"]["algorithm"]["acquisition_function"]["class"] == "b200_expected_improvement"
 print("profit integration ok", hg)
 '''
 
