@@ -76,8 +76,6 @@ for label, kw, arg in pairs:
         rl, gl = ra.calculate_loss(), ga.calculate_loss()
     assert np.all(np.abs(rl - gl) <= 1e-8 * np.abs(rl) + 1e-10 * np.abs(rl).max()), (label, np.abs(rl - gl).max())
     assert int(np.argmax(rl)) == int(np.argmax(gl)), label
-pa.register_as_default()
-assert AcquisitionFunction["simple_exploration"] is pa.SimpleExploration
 
 # the configuration route: profit.yaml with `include:` + `fit: {surrogate: B200}` as proFit's own Config reads it
 # (config.py:309-320, :397-402), then from_config -> train -> save_model -> load_model -> predict
@@ -110,6 +108,77 @@ again = Surrogate["B200"].load_model(cfg["fit"]["save"])
 m1, v1 = sur.predict(Xc); m2, v2 = again.predict(Xc)
 assert np.array_equal(m1, m2) and np.array_equal(v1, v2)
 assert cfg["active_learning"]["algorithm"]["acquisition_function"]["class"] == "b200_expected_improvement"
+
+# proFit's own SimpleAL (al/simple_al.py: warmup -> learn -> find_next_candidates -> update_run -> set_ytrain ->
+# optimize) driven end to end, once with its own surrogate + acquisition function and once with the B200 twins; the
+# run system is replaced by an in-process runner that evaluates the test function
+from profit.al import ActiveLearning
+
+def run_al(surrogate_label, acq_label):
+    open("profit_al.yaml", "w").write("""
+ntrain: 12
+include: %s
+variables:
+    u: ActiveLearning(0, 1)
+    v: ActiveLearning(0, 1)
+    f: Output
+run:
+    worker: {class: function, entry_point: f}
+fit:
+    surrogate: %s
+    kernel: RBF
+active_learning:
+    nwarmup: 6
+    batch_size: 2
+    nsearch: 15
+    algorithm:
+        class: simple
+        acquisition_function: {class: %s}
+""" % (SHIM, surrogate_label, acq_label))
+    c = BaseConfig.from_file("profit_al.yaml")
+    n = c["ntrain"]
+    ins = [v.name for v in c.variable_group.input_list]
+    outs = [v.name for v in c.variable_group.output_list]
+
+    class Interface:
+        def __init__(self):
+            self.input = np.zeros(n, dtype=[(k, float) for k in ins])
+            self.output = np.full(n, np.nan, dtype=[(k, float) for k in outs])
+
+        def resize(self, m):
+            pass
+
+    class Runner:
+        def __init__(self):
+            self.interface, self.next = Interface(), 0
+        input_data = property(lambda self: self.interface.input)
+        output_data = property(lambda self: self.interface.output)
+
+        def spawn_array(self, params_array, wait=True, **kw):
+            for p in params_array:
+                for k, val in p.items():
+                    self.interface.input[k][self.next] = val
+                u, v = self.interface.input["u"][self.next], self.interface.input["v"][self.next]
+                self.interface.output["f"][self.next] = np.sin(3 * u) + np.cos(2 * v)
+                self.next += 1
+
+    al = ActiveLearning.from_config(Runner(), c.variable_group, c["active_learning"], c)
+    al.warmup(save_intermediate=None)
+    al.learn(save_intermediate=None)
+    return al
+
+al_ref = run_al("Custom", "simple_exploration")
+al_gpu = run_al("B200", "b200_simple_exploration")
+assert type(al_gpu.surrogate) is ps.B200GPSurrogate and type(al_gpu.acquisition_function) is pa.SimpleExploration
+assert al_gpu.surrogate.Xtrain.shape == al_ref.surrogate.Xtrain.shape == (12, 2)
+Xr, Xg = al_ref.variables.input, al_gpu.variables.input
+assert np.array_equal(Xr[:8], Xg[:8]), (Xr, Xg)            # warm-up points and the first learned batch are identical
+same = sum(bool(np.array_equal(a, b)) for a, b in zip(Xr, Xg))
+assert same >= 10, (same, Xr, Xg)                          # later picks may differ only through the 1e-4 spread of the optimiser
+assert np.all(np.isfinite(al_gpu.variables.output))
+
+pa.register_as_default()                                  # last: from here on the reference's labels select the twins
+assert AcquisitionFunction["simple_exploration"] is pa.SimpleExploration
 print("profit integration ok", hg)
 '''
 
