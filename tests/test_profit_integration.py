@@ -177,6 +177,27 @@ same = sum(bool(np.array_equal(a, b)) for a, b in zip(Xr, Xg))
 assert same >= 10, (same, Xr, Xg)                          # later picks may differ only through the 1e-4 spread of the optimiser
 assert np.all(np.isfinite(al_gpu.variables.output))
 
+# `profit fit` (main.py:172-193) step by step on the files SimpleAL's variables produce: Surrogate.from_config on the
+# base class (adds the configured encoders), FileHandler.load of the text files, train, save_model, and a second
+# configuration that loads the saved model instead of training (sur.py:265-266)
+from profit.util.file_handler import FileHandler
+FileHandler.save("input.txt", al_gpu.variables.named_input)
+FileHandler.save("output.txt", al_gpu.variables.formatted_output)
+c = BaseConfig.from_file("profit_al.yaml")
+fit_sur = Surrogate.from_config(c["fit"], c)
+assert type(fit_sur) is ps.B200GPSurrogate and not fit_sur.trained
+xin, yout = FileHandler.load("input.txt"), FileHandler.load("output.txt")
+xin = np.hstack([xin[k] for k in xin.dtype.names]); yout = np.hstack([yout[k] for k in yout.dtype.names])
+fit_sur.train(xin, yout)
+fit_sur.save_model("model_fit.npz")
+c.fit.load = "model_fit.npz"                             # c["fit"] hands out copies
+loaded = Surrogate.from_config(c["fit"], c)
+assert type(loaded) is ps.B200GPSurrogate and loaded.trained
+ma, va = fit_sur.predict(Xc[:20]); mb, vb = loaded.predict(Xc[:20])
+# fit_sur carries the configured input encoders (encode in pre_predict, decode in predict: an identity up to round-off,
+# custom_surrogate.py:96-99); the loaded model has none, exactly as with the reference's own save / load
+assert np.allclose(ma, mb, rtol=1e-10, atol=1e-12) and np.allclose(va, vb, rtol=1e-10)
+
 pa.register_as_default()                                  # last: from here on the reference's labels select the twins
 assert AcquisitionFunction["simple_exploration"] is pa.SimpleExploration
 print("profit integration ok", hg)
