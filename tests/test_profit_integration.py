@@ -198,6 +198,16 @@ ma, va = fit_sur.predict(Xc[:20]); mb, vb = loaded.predict(Xc[:20])
 # custom_surrogate.py:96-99); the loaded model has none, exactly as with the reference's own save / load
 assert np.allclose(ma, mb, rtol=1e-10, atol=1e-12) and np.allclose(va, vb, rtol=1e-10)
 
+# fixed_sigma_n (custom_surrogate.py:47-56,240-282; gp_functions.py:181-183,241-243): the noise level stays put and the
+# remaining hyper-parameters land where the reference's do
+hyp0 = {"length_scale": np.array([0.4]), "sigma_f": np.array([1.0]), "sigma_n": np.array([0.07])}
+rf, gf = Surrogate["Custom"](), Surrogate["B200"]()
+rf.train(X, y, hyperparameters={k: v.copy() for k, v in hyp0.items()}, fixed_sigma_n=True)
+gf.train(X, y, hyperparameters={k: v.copy() for k, v in hyp0.items()}, fixed_sigma_n=True)
+assert gf.hyperparameters["sigma_n"][0] == 0.07 == rf.hyperparameters["sigma_n"][0]
+for k in ("length_scale", "sigma_f"):
+    assert np.allclose(gf.hyperparameters[k], rf.hyperparameters[k], rtol=1e-3), (k, gf.hyperparameters[k], rf.hyperparameters[k])
+
 pa.register_as_default()                                  # last: from here on the reference's labels select the twins
 assert AcquisitionFunction["simple_exploration"] is pa.SimpleExploration
 print("profit integration ok", hg)
