@@ -208,6 +208,15 @@ assert gf.hyperparameters["sigma_n"][0] == 0.07 == rf.hyperparameters["sigma_n"]
 for k in ("length_scale", "sigma_f"):
     assert np.allclose(gf.hyperparameters[k], rf.hyperparameters[k], rtol=1e-3), (k, gf.hyperparameters[k], rf.hyperparameters[k])
 
+# marginal variance (custom_surrogate.py:144-163 -> gp_functions.marginal_variance_BBQ): both surrogates re-optimise
+# from the same hyper-parameters and add the hyper-parameter uncertainty of the mean
+for s3 in (ref, gpu):
+    s3.hyperparameters = {"length_scale": np.array([0.45]), "sigma_f": np.array([1.1]), "sigma_n": np.array([0.06])}
+mv_r = ref.get_marginal_variance(Xc[:64])
+mv_g = gpu.get_marginal_variance(Xc[:64])
+assert mv_g.shape == mv_r.shape == (64, 1)
+assert np.allclose(mv_g, mv_r, rtol=2e-2), np.max(np.abs(mv_g - mv_r) / mv_r)
+
 pa.register_as_default()                                  # last: from here on the reference's labels select the twins
 assert AcquisitionFunction["simple_exploration"] is pa.SimpleExploration
 print("profit integration ok", hg)
