@@ -52,6 +52,9 @@ SIGNATURES = {
     "gpb_debug_gemm": (ctypes.c_int, [ctypes.c_void_p, _c_double_p, _c_double_p, _c_double_p, _ll, _ll, _ll,
                                       ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_int,
                                       ctypes.POINTER(ctypes.c_double)]),
+    "gpb_debug_diag": (ctypes.c_int, [ctypes.c_void_p, _c_double_p, _c_double_p, _c_double_p,
+                                      ctypes.POINTER(ctypes.c_double), ctypes.c_int, ctypes.c_int,
+                                      ctypes.POINTER(ctypes.c_double)]),
 }
 
 NUM_STAGES = 8

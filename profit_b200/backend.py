@@ -298,6 +298,18 @@ class GPBackend:
         return ms.value
 
 
+    def debug_diag(self, A, mode=2, reps=1):
+        """Factor one 128x128 SPD block with the diagonal-block kernel `mode` -> (L, L^-1, sum log L_jj, ms)."""
+        A = _lib.as_f64(A)
+        if tuple(A.shape) != (128, 128):
+            raise ValueError("A should have shape (128, 128)")
+        L, W = np.empty((128, 128)), np.empty((128, 128))
+        ld, ms = ctypes.c_double(), ctypes.c_double()
+        _lib.check(self._lib.gpb_debug_diag(self._h, _lib.ptr(A), _lib.ptr(L), _lib.ptr(W), ctypes.byref(ld), int(mode),
+                                            int(reps), ctypes.byref(ms)), self._h, "debug_diag")
+        return L, W, ld.value, ms.value
+
+
 def _default_device():
     """LOCAL_RANK under torchrun (one process per GPU), else the current torch device, else 0."""
     import os

@@ -37,6 +37,7 @@
 #include "assemble.cuh"
 #include "dgemm_tasks.cuh"
 #include "potrf_diag.cuh"
+#include "potrf_diagr.cuh"
 
 using namespace gpb;
 
@@ -308,7 +309,8 @@ int launch_gemm(H* h, Workspace& w, int cfg, int epi, int matA, int matB, const 
 // ------------------------------------------------------------------------------------------------ plans
 int g_cfg_update = CFG_128x64;  // trailing updates / trtri / syrk / predict   (env GPB_CFG_UPDATE)
 int g_outer_blocks = 0;         // outer panel width of the Cholesky in 128-blocks; 0 = by size (env GPB_OUTER_BLOCKS)
-int g_diag4 = 1;                // rank-4 diagonal-block kernel (env GPB_DIAG4=0 selects the rank-1 one)
+int g_diag4 = 2;                // diagonal-block kernel: 2 = blocked DMMA kernel (potrf_diagr.cuh), 1 = rank-4 register
+                                // sweep, 0 = rank-1 register sweep (env GPB_DIAG4)
 int g_pdl = 1;                  // programmatic dependent launch along the panel chain (env GPB_PDL)
 int g_tail_blocks = 32;         // the last this-many block columns use single-block panels (env GPB_TAIL_BLOCKS)
 int g_lookahead = 1;            // overlap the next panel factorisation with the trailing update (env GPB_LOOKAHEAD)
@@ -595,38 +597,35 @@ int run_plan(H* h, Workspace& w, Plan& p, bool factor_diag, cudaStream_t only_st
     if (multi && L.wait_ev >= 0) CK(cudaStreamWaitEvent(st, h->events[L.wait_ev], 0));
     if (multi && L.wait_ev2 >= 0) CK(cudaStreamWaitEvent(st, h->events[L.wait_ev2], 0));
     if (L.type == 0) {
-      if (factor_diag && g_diag4) {
+      double* winv = w.Dinv + (long long)L.k * 128 * 128;
+      if (factor_diag) {
         cudaLaunchConfig_t lc{};
         lc.gridDim = dim3(1);
-        lc.blockDim = dim3(DIAG_THREADS);
-        lc.dynamicSmemBytes = DIAG4_SMEM;
         lc.stream = st;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = 1;
         lc.attrs = at;
         lc.numAttrs = (L.pdl && g_pdl) ? 1 : 0;
-        CK(cudaLaunchKernelEx(&lc, potrf_diag4_kernel, w.Lbuf, (long long)w.Np, L.k * 128,
-                              w.Dinv + (long long)L.k * 128 * 128, w.logdet + L.k, h->dinfo, (int)w.N));
-      } else if (factor_diag && L.pdl && g_pdl) {
-        cudaLaunchConfig_t lc{};
-        lc.gridDim = dim3(1);
-        lc.blockDim = dim3(DIAG_THREADS);
-        lc.dynamicSmemBytes = DIAG_SMEM;
-        lc.stream = st;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        at[0].val.programmaticStreamSerializationAllowed = 1;
-        lc.attrs = at;
-        lc.numAttrs = 1;
-        CK(cudaLaunchKernelEx(&lc, potrf_diag_kernel<true>, w.Lbuf, (long long)w.Np, L.k * 128,
-                              w.Dinv + (long long)L.k * 128 * 128, w.logdet + L.k, h->dinfo, (int)w.N));
-      } else if (factor_diag)
-        potrf_diag_kernel<true><<<1, DIAG_THREADS, DIAG_SMEM, st>>>(
-            w.Lbuf, w.Np, L.k * 128, w.Dinv + (long long)L.k * 128 * 128, w.logdet + L.k, h->dinfo, (int)w.N);
-      else
-        potrf_diag_kernel<false><<<1, DIAG_THREADS, DIAG_SMEM, st>>>(
-            w.Lbuf, w.Np, L.k * 128, w.Dinv + (long long)L.k * 128 * 128, w.logdet + L.k, h->dinfo, (int)w.N);
+        if (g_diag4 == 2) {
+          lc.blockDim = dim3(DR_THREADS);
+          lc.dynamicSmemBytes = DR_SMEM;
+          CK(cudaLaunchKernelEx(&lc, potrf_diagr_kernel, w.Lbuf, (long long)w.Np, L.k * 128, winv, w.logdet + L.k,
+                                h->dinfo, (int)w.N));
+        } else if (g_diag4 == 1) {
+          lc.blockDim = dim3(DIAG_THREADS);
+          lc.dynamicSmemBytes = DIAG4_SMEM;
+          CK(cudaLaunchKernelEx(&lc, potrf_diag4_kernel, w.Lbuf, (long long)w.Np, L.k * 128, winv, w.logdet + L.k,
+                                h->dinfo, (int)w.N));
+        } else {
+          lc.blockDim = dim3(DIAG_THREADS);
+          lc.dynamicSmemBytes = DIAG_SMEM;
+          CK(cudaLaunchKernelEx(&lc, potrf_diag_kernel<true>, w.Lbuf, (long long)w.Np, L.k * 128, winv, w.logdet + L.k,
+                                h->dinfo, (int)w.N));
+        }
+      } else
+        potrf_diag_kernel<false><<<1, DIAG_THREADS, DIAG_SMEM, st>>>(w.Lbuf, w.Np, L.k * 128, winv, w.logdet + L.k,
+                                                                     h->dinfo, (int)w.N);
       h->launches++;
       CK(cudaGetLastError());
     } else {
@@ -1242,7 +1241,8 @@ int gpb_create(int device, gpb_handle_t* out) {
     return -2;
   }
   h->encode = reinterpret_cast<EncodeTiledFn>(fn);
-  if (cudaFuncSetAttribute(potrf_diag4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG4_SMEM) != cudaSuccess ||
+  if (cudaFuncSetAttribute(potrf_diagr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DR_SMEM) != cudaSuccess ||
+      cudaFuncSetAttribute(potrf_diag4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG4_SMEM) != cudaSuccess ||
       cudaFuncSetAttribute(potrf_diag_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM) != cudaSuccess ||
       cudaFuncSetAttribute(potrf_diag_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM) != cudaSuccess) {
     delete h;
@@ -1266,7 +1266,7 @@ int gpb_create(int device, gpb_handle_t* out) {
   if (const char* e = getenv("GPB_FINE_BELOW")) g_fine_below = atoi(e);
   if (const char* e = getenv("GPB_PDL")) g_pdl = atoi(e) != 0;
   if (const char* e = getenv("GPB_TAIL_BLOCKS")) g_tail_blocks = std::max(0, atoi(e));
-  if (const char* e = getenv("GPB_DIAG4")) g_diag4 = atoi(e) != 0;
+  if (const char* e = getenv("GPB_DIAG4")) g_diag4 = std::max(0, std::min(2, atoi(e)));
   *out = h;
   return 0;
 }
@@ -2091,6 +2091,42 @@ int gpb_debug_gemm(gpb_handle_t h, const double* A, const double* B, double* C, 
   cudaEventElapsedTime(&t, e0, e1);
   if (ms) *ms = t / reps;
   return 0;
+}
+
+// Factor one 128x128 SPD block with the diagonal-block kernel selected by `mode` (0 / 1 / 2 as GPB_DIAG4), `reps`
+// times back to back on the handle's stream; returns L, L^-1, sum log L_jj and the mean kernel time.
+int gpb_debug_diag(gpb_handle_t h, const double* A, double* L, double* W, double* logdet, int mode, int reps, double* ms) {
+  if (!h || !A || !L || !W || reps < 1 || mode < 0 || mode > 2) return fail(h, -1, "gpb_debug_diag: bad argument");
+  CK(cudaSetDevice(h->device));
+  int rc = ensure_cap(h, &h->dstage, &h->dstage_cap, (size_t)3 * 128 * 128 + 8);
+  if (rc) return rc;
+  double* dA = h->dstage;
+  double* dB = dA + 128 * 128;
+  double* dW = dB + 128 * 128;
+  double* dl = dW + 128 * 128;
+  CK(cudaMemcpyAsync(dA, A, 128 * 128 * sizeof(double), cudaMemcpyDefault, h->stream));
+  CK(cudaMemsetAsync(h->dinfo, 0, sizeof(int), h->stream));
+  cudaEvent_t e0 = h->evx[0], e1 = h->evx[1];
+  float total = 0.f;
+  for (int r = 0; r < reps; ++r) {
+    CK(cudaMemcpyAsync(dB, dA, 128 * 128 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    cudaEventRecord(e0, h->stream);
+    if (mode == 2) potrf_diagr_kernel<<<1, DR_THREADS, DR_SMEM, h->stream>>>(dB, 128, 0, dW, dl, h->dinfo, 128);
+    else if (mode == 1) potrf_diag4_kernel<<<1, DIAG_THREADS, DIAG4_SMEM, h->stream>>>(dB, 128, 0, dW, dl, h->dinfo, 128);
+    else potrf_diag_kernel<true><<<1, DIAG_THREADS, DIAG_SMEM, h->stream>>>(dB, 128, 0, dW, dl, h->dinfo, 128);
+    cudaEventRecord(e1, h->stream);
+    h->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    float t = 0.f;
+    cudaEventElapsedTime(&t, e0, e1);
+    total += t;
+  }
+  CK(cudaMemcpyAsync(L, dB, 128 * 128 * sizeof(double), cudaMemcpyDefault, h->stream));
+  CK(cudaMemcpyAsync(W, dW, 128 * 128 * sizeof(double), cudaMemcpyDefault, h->stream));
+  if (logdet) CK(cudaMemcpyAsync(logdet, dl, sizeof(double), cudaMemcpyDefault, h->stream));
+  if (ms) *ms = total / reps;
+  return check_info(h);
 }
 
 #ifdef GPB_TRACE
