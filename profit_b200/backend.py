@@ -35,6 +35,7 @@ class GPBackend:
         # bookkeeping for callers that share one backend (set by B200GPSurrogate): what is resident / factorised
         self.resident_key = None
         self.factor_key = None
+        self.noise_override = None     # set by B200GPSurrogate when the resident factor carries the 1e-6 jitter retry
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
@@ -62,7 +63,7 @@ class GPBackend:
             raise ValueError(f"y should have shape (n,) or (n, D) but has shape {tuple(y.shape)}")
         if int(y.shape[0]) != n:
             raise ValueError(f"mismatched number of data points for X and y: {n} != {int(y.shape[0])}")
-        self.resident_key = self.factor_key = None
+        self.resident_key = self.factor_key = self.noise_override = None
         _lib.check(self._lib.gpb_set_train(self._h, _lib.ptr(X), _lib.ptr(y), n, d, n_out), self._h, "set_train")
         self.n, self.d, self.n_out = n, d, n_out
 
@@ -71,7 +72,7 @@ class GPBackend:
         """theta = [length_scale..., sigma_f, sigma_n] on the linear scale -> nll [, grad (P,)]."""
         theta = np.ascontiguousarray(theta, dtype=np.float64).ravel()
         n_ell = theta.size - 2
-        self.factor_key = None
+        self.factor_key = self.noise_override = None
         out = ctypes.c_double()
         grad = np.empty(theta.size) if want_grad else None
         st = self._lib.gpb_nll(self._h, int(kind), _lib.ptr(theta), n_ell, int(bool(want_grad)), ctypes.byref(out),
@@ -81,7 +82,7 @@ class GPBackend:
 
     def factorize(self, kind, theta):
         theta = np.ascontiguousarray(theta, dtype=np.float64).ravel()
-        self.factor_key = None
+        self.factor_key = self.noise_override = None
         _lib.check(self._lib.gpb_factorize(self._h, int(kind), _lib.ptr(theta), theta.size - 2), self._h, "factorize")
 
     def _check_candidates(self, Xc):

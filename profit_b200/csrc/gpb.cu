@@ -682,6 +682,8 @@ int resize_ws(H* h, Workspace& w, long long N) {
   w.Nb = Np / 128;
   CK(cudaMalloc(&w.Lbuf, (size_t)(Np + 128) * Np * sizeof(double)));
   CK(cudaMalloc(&w.Dinv, (size_t)Np * 128 * sizeof(double)));
+  // potrf_diagr_kernel only writes the lower block triangle of an inverted diagonal block
+  CK(cudaMemsetAsync(w.Dinv, 0, (size_t)Np * 128 * sizeof(double), h->stream));
   CK(cudaMalloc(&w.logdet, (size_t)w.Nb * sizeof(double)));
   CK(cudaMalloc(&w.alpha, (size_t)128 * Np * sizeof(double)));
   set_mat(w, M_L, w.Lbuf, Np + 128, Np, Np);
@@ -2106,6 +2108,7 @@ int gpb_debug_diag(gpb_handle_t h, const double* A, double* L, double* W, double
   double* dl = dW + 128 * 128;
   CK(cudaMemcpyAsync(dA, A, 128 * 128 * sizeof(double), cudaMemcpyDefault, h->stream));
   CK(cudaMemsetAsync(h->dinfo, 0, sizeof(int), h->stream));
+  CK(cudaMemsetAsync(dW, 0, 128 * 128 * sizeof(double), h->stream));   // mode 2 leaves the strict upper blocks alone
   cudaEvent_t e0 = h->evx[0], e1 = h->evx[1];
   float total = 0.f;
   for (int r = 0; r < reps; ++r) {
@@ -2122,7 +2125,10 @@ int gpb_debug_diag(gpb_handle_t h, const double* A, double* L, double* W, double
     cudaEventElapsedTime(&t, e0, e1);
     total += t;
   }
-  CK(cudaMemcpyAsync(L, dB, 128 * 128 * sizeof(double), cudaMemcpyDefault, h->stream));
+  // the factor as the library's consumers see it: lower triangle (mode 2 does not touch the strict upper one)
+  unpack_kernel<<<(128 * 128 + 255) / 256, 256, 0, h->stream>>>(dB, 128, 128, 0, dA);
+  h->launches++;
+  CK(cudaMemcpyAsync(L, dA, 128 * 128 * sizeof(double), cudaMemcpyDefault, h->stream));
   CK(cudaMemcpyAsync(W, dW, 128 * 128 * sizeof(double), cudaMemcpyDefault, h->stream));
   if (logdet) CK(cudaMemcpyAsync(logdet, dl, sizeof(double), cudaMemcpyDefault, h->stream));
   if (ms) *ms = total / reps;

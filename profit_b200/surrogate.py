@@ -114,8 +114,16 @@ except Exception:  # profit not installed: stand-alone base with the same contra
         def decode_predict_data(self, ym, yv):
             return ym, yv
 
-        def decode_hyperparameters(self):
-            pass
+        def decode_hyperparameters(self):                # gaussian_process.py:222-233 (no encoders stand-alone)
+            for key, value in self.hyperparameters.items():
+                self.hyperparameters[key] = self.special_hyperparameter_decoding(key, value)
+
+        def special_hyperparameter_decoding(self, key, value):
+            return np.atleast_1d(value)
+
+        def post_train(self):                            # sur.py:166-168
+            self.trained = True
+            self.decode_training_data()
 
         def print_hyperparameters(self, prefix):
             pass
@@ -224,23 +232,40 @@ class B200GPSurrogate(_GPBase):
         for enc in self.input_encoders[::-1]:
             Xpred = enc.decode(Xpred)
         self._ensure_factor()
+        jittered = self.backend.noise_override is not None
         mean, var = self.backend.predict(np.ascontiguousarray(Xpred, dtype=np.float64),
-                                         add_data_variance=1 if add_data_variance else 0)
+                                         add_data_variance=1 if (add_data_variance and not jittered) else 0)
+        if add_data_variance and jittered:
+            var += self.backend.noise_override   # the reported data variance stays the model's sigma_n^2
         return mean, var.reshape(-1, 1)
 
     def predict_into(self, Xpred, out_mean=None, out_var=None, add_data_variance=True):
         """``predict`` for callers that keep everything on the device: ``Xpred`` (M, d), ``out_mean`` (M, n_out) and
         ``out_var`` (M,) are torch CUDA tensors (or numpy arrays); either output may be None to skip it."""
         self._ensure_factor()
-        self.backend.predict(Xpred, add_data_variance=1 if add_data_variance else 0, out_mean=out_mean,
-                             out_var=out_var, want_mean=out_mean is not None, want_var=out_var is not None)
+        jittered = self.backend.noise_override is not None
+        self.backend.predict(Xpred, add_data_variance=1 if (add_data_variance and not jittered) else 0,
+                             out_mean=out_mean, out_var=out_var, want_mean=out_mean is not None,
+                             want_var=out_var is not None)
+        if add_data_variance and jittered and out_var is not None:
+            out_var += self.backend.noise_override
 
     def _ensure_factor(self):
+        """Factor of the current (data, hyper-parameters) on the device.  Like the reference's predict path, a
+        numerically non-SPD Ky is retried once with 1e-6 on the diagonal (gp_functions.invert, :343-346; alpha falls
+        back to lstsq there, custom_surrogate.py:42-45); the data variance reported by predict stays sigma_n^2."""
         self._upload()
         be = self.backend
         key = self._factor_key(be.resident_key)
         if be.resident_key is None or key != be.factor_key:
-            be.factorize(kernel_kind(self.kernel), self._theta())
+            theta = self._theta()
+            try:
+                be.factorize(kernel_kind(self.kernel), theta)
+            except np.linalg.LinAlgError:
+                jit = np.array(theta)
+                jit[-1] = np.sqrt(theta[-1] ** 2 + 1e-6)
+                be.factorize(kernel_kind(self.kernel), jit)
+                be.noise_override = float(theta[-1] ** 2)     # sigma_n^2 to report for this (jittered) factor
             be.factor_key = key
 
     def add_training_data(self, X, y):
@@ -261,7 +286,7 @@ class B200GPSurrogate(_GPBase):
             try:
                 be.append_train(X.reshape(-1, self.Xtrain.shape[1]), y.reshape(X.shape[0], -1))
             except np.linalg.LinAlgError:
-                return      # left to the next predict, which refactorises (and raises there like the reference)
+                return      # left to the next predict, which refactorises (with the jitter retry of _ensure_factor)
             be.resident_key = self._data_key(self.Xtrain, self.ytrain)
             be.factor_key = self._factor_key(be.resident_key)
 
@@ -275,7 +300,12 @@ class B200GPSurrogate(_GPBase):
         self.optimize(fixed_sigma_n=self.fixed_sigma_n, eval_gradient=True, return_hess_inv=True)
         assert self.hess_inv is not None
         _, fvar = self.predict(Xpred)          # leaves the factor of the optimised hyper-parameters on the device
-        return _gpf.marginal_variance_BBQ(self.Xtrain, self.ytrain, self.pre_predict(Xpred), self.kernel,
+        # the reference hands the raw Xpred on (custom_surrogate.py:152-163): the same points predict() evaluates
+        # after undoing the input encoding, NOT the encoded ones
+        Xraw = np.asarray(Xpred, dtype=np.float64)
+        if Xraw.ndim == 1:
+            Xraw = Xraw.reshape(-1, 1)
+        return _gpf.marginal_variance_BBQ(self.Xtrain, self.ytrain, Xraw, self.kernel,
                                           self.hyperparameters, self.hess_inv, self.fixed_sigma_n,
                                           predictive_variance=fvar, backend=self.backend)
 
