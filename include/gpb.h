@@ -135,6 +135,13 @@ int gpb_acquire(gpb_handle_t h, int kind, const double* term, const double* var,
 int gpb_kernel_matrix(gpb_handle_t h, int kind, const double* Xa, long long na, const double* Xb, long long nb, int d,
                       const double* ell, int n_ell, double sigma_f, double sigma_n, double* K, double* dK);
 
+/* Linear-embedding kernel -- python_kernels.LinearEmbedding (python_kernels.py:60-114):
+ * K = sf^2 exp(-1/2 |R (x - y)|^2) + sn^2 I with R (d, D) row-major; K: (na, nb); dK: (na, nb, d*D + 2) or NULL, ordered
+ * [R.ravel()..., sf, sn].  dK/dR_ab = -K_pure (R delta)_a delta_b is the analytic derivative (upstream's einsum at
+ * :108-110 is flagged "TODO: check" and only shape-consistent for d = 1). */
+int gpb_linear_embedding(gpb_handle_t h, const double* Xa, long long na, const double* Xb, long long nb, int D,
+                         const double* R, int d, double sigma_f, double sigma_n, double* K, double* dK);
+
 /* Marginal variance of Osborne (2012) -- gp_functions.marginal_variance_BBQ (gp_functions.py:376-454):
  * out[c] = dm_c^T Hinv dm_c + pred_var[c] with dm_c = d(mean_c)/d(theta), theta = [length_scale..., sigma_f, sigma_n]
  * of the factorised model (gpb_factorize).  hess_inv: (P, P) row-major, P = n_ell + 2 (already zero-padded if sigma_n was

@@ -39,6 +39,8 @@ SIGNATURES = {
     "gpb_kernel_matrix": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _c_double_p, _ll, _c_double_p, _ll,
                                          ctypes.c_int, _c_double_p, ctypes.c_int, ctypes.c_double, ctypes.c_double,
                                          _c_double_p, _c_double_p]),
+    "gpb_linear_embedding": (ctypes.c_int, [ctypes.c_void_p, _c_double_p, _ll, _c_double_p, _ll, ctypes.c_int, _c_double_p,
+                                            ctypes.c_int, ctypes.c_double, ctypes.c_double, _c_double_p, _c_double_p]),
     "gpb_marginal_variance": (ctypes.c_int, [ctypes.c_void_p, _c_double_p, _ll, _c_double_p, _c_double_p, _c_double_p]),
     "gpb_mean_pairwise_distance": (ctypes.c_int, [ctypes.c_void_p, _c_double_p, _ll, ctypes.c_int,
                                                   ctypes.POINTER(ctypes.c_double)]),

@@ -35,6 +35,7 @@ class GPBackend:
         # bookkeeping for callers that share one backend (set by B200GPSurrogate): what is resident / factorised
         self.resident_key = None
         self.factor_key = None
+        self.non_spd_events = []       # jitter retries of gp_functions.negative_log_likelihood since the last optimize()
         self.noise_override = None     # set by B200GPSurrogate when the resident factor carries the 1e-6 jitter retry
 
     def close(self):
@@ -237,6 +238,21 @@ class GPBackend:
         st = self._lib.gpb_kernel_matrix(self._h, int(kind), _lib.ptr(Xa), na, _lib.ptr(Xb), nb, d, _lib.ptr(ell),
                                          ell.size, float(sigma_f), float(sigma_n), _lib.ptr(K), _lib.ptr(dK))
         _lib.check(st, self._h, "kernel_matrix")
+        return (K, dK) if eval_gradient else K
+
+    def linear_embedding(self, Xa, Xb, R, sigma_f, sigma_n, eval_gradient=False):
+        """python_kernels.LinearEmbedding on the device: K (na, nb) [and dK (na, nb, R.size + 2)], R (d, D)."""
+        Xa, Xb, R = _lib.as_f64(Xa), _lib.as_f64(Xb), _lib.as_f64(R)
+        if Xa.ndim != 2 or Xb.ndim != 2 or R.ndim != 2 or not (Xa.shape[1] == Xb.shape[1] == R.shape[1]):
+            raise ValueError(f"X, Y and R should have shapes (n, D), (m, D) and (d, D) but have {tuple(Xa.shape)}, "
+                             f"{tuple(Xb.shape)} and {tuple(R.shape)}")
+        na, nb, D, d = int(Xa.shape[0]), int(Xb.shape[0]), int(Xa.shape[1]), int(R.shape[0])
+        K = np.empty((na, nb))
+        dK = np.empty((na, nb, d * D + 2)) if eval_gradient else None
+        if na and nb:
+            st = self._lib.gpb_linear_embedding(self._h, _lib.ptr(Xa), na, _lib.ptr(Xb), nb, D, _lib.ptr(R), d,
+                                                float(sigma_f), float(sigma_n), _lib.ptr(K), _lib.ptr(dK))
+            _lib.check(st, self._h, "linear_embedding")
         return (K, dK) if eval_gradient else K
 
     def mean_pairwise_distance(self, X):

@@ -401,4 +401,43 @@ __global__ void finish_variance_kernel(const double* __restrict__ part, long lon
   var[c] = v;
 }
 
+// Linear-embedding kernel of Garnett (2014) -- python_kernels.LinearEmbedding (python_kernels.py:60-114):
+//   K = sf^2 exp(-1/2 |R (x - y)|^2) + sn^2 I,  R (d, D) row-major.
+// One thread per element.  dK (na, nb, d*D + 2), ordered [R_00 .. R_(d-1)(D-1), sf, sn] like R.ravel():
+//   dK/dR_ab = -K_pure (R delta)_a delta_b   with delta = x - y   (the analytic derivative; the expression at
+//   python_kernels.py:108-110 is marked "TODO: check" upstream, only has consistent shapes for d = 1 and is not the
+//   derivative there -- see DESIGN.md section 6),   dK/dsf = 2/sf K_pure (:111),  dK/dsn = 2 sn I (:112).
+// Not a hot kernel (the embedding kernel is not on the NLL / predict path): plain coalesced K stores, strided dK.
+__global__ void __launch_bounds__(256) linear_embedding_kernel(const double* __restrict__ Xa, int na,
+                                                               const double* __restrict__ Xb, int nb, int D,
+                                                               const double* __restrict__ R, int d, double sf, double sn,
+                                                               double* __restrict__ K, double* __restrict__ dK) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long long)na * nb) return;
+  const int i = (int)(e / nb), j = (int)(e % nb);
+  double delta[MAX_D], proj[MAX_D];
+  for (int b = 0; b < D; ++b) delta[b] = Xa[(long long)i * D + b] - Xb[(long long)j * D + b];
+  double d2 = 0.0;
+  for (int a = 0; a < d; ++a) {
+    // (X R^T)_ia - (Y R^T)_ja evaluated like the reference: project first, then subtract
+    double pa = 0.0, pb = 0.0;
+    for (int b = 0; b < D; ++b) {
+      pa = fma(Xa[(long long)i * D + b], R[a * D + b], pa);
+      pb = fma(Xb[(long long)j * D + b], R[a * D + b], pb);
+    }
+    proj[a] = pa - pb;
+    d2 = fma(proj[a], proj[a], d2);
+  }
+  const double kp = sf * sf * exp(-0.5 * d2);
+  const double eye = (i == j) ? 1.0 : 0.0;
+  K[e] = kp + sn * sn * eye;
+  if (dK != nullptr) {
+    double* out = dK + e * (long long)(d * D + 2);
+    for (int a = 0; a < d; ++a)
+      for (int b = 0; b < D; ++b) out[a * D + b] = -kp * proj[a] * delta[b];
+    out[d * D] = 2.0 / sf * kp;
+    out[d * D + 1] = 2.0 * sn * eye;
+  }
+}
+
 }  // namespace gpb

@@ -1676,6 +1676,37 @@ int gpb_kernel_matrix(gpb_handle_t h, int kind, const double* Xa, long long na, 
   return 0;
 }
 
+// python_kernels.LinearEmbedding (python_kernels.py:60-114): K (na, nb) and, if dK != NULL, dK (na, nb, d*D + 2).
+int gpb_linear_embedding(gpb_handle_t h, const double* Xa, long long na, const double* Xb, long long nb, int D,
+                         const double* R, int d, double sigma_f, double sigma_n, double* K, double* dK) {
+  if (!h || !Xa || !Xb || !R || !K || na < 1 || nb < 1 || D < 1 || D > MAX_D || d < 1 || d > MAX_D)
+    return fail(h, -1, "gpb_linear_embedding: bad argument");
+  CK(cudaSetDevice(h->device));
+  const int P = d * D + 2;
+  const size_t nK = (size_t)na * nb, ndK = dK ? nK * P : 0;
+  int rc = ensure_cap(h, &h->dstage, &h->dstage_cap, (size_t)(na + nb) * D + (size_t)d * D);
+  if (rc) return rc;
+  const bool k_dev = is_device_ptr(K), dk_dev = dK ? is_device_ptr(dK) : true;
+  const size_t need_out = (k_dev ? 0 : nK) + (dk_dev ? 0 : ndK);
+  if (need_out && (rc = ensure_cap(h, &h->dstage2, &h->dstage2_cap, need_out))) return rc;
+  double* dXa = h->dstage;
+  double* dXb = dXa + (size_t)na * D;
+  double* dR = dXb + (size_t)nb * D;
+  CK(cudaMemcpyAsync(dXa, Xa, (size_t)na * D * sizeof(double), cudaMemcpyDefault, h->stream));
+  CK(cudaMemcpyAsync(dXb, Xb, (size_t)nb * D * sizeof(double), cudaMemcpyDefault, h->stream));
+  CK(cudaMemcpyAsync(dR, R, (size_t)d * D * sizeof(double), cudaMemcpyDefault, h->stream));
+  double* dKo = k_dev ? K : h->dstage2;
+  double* ddK = dK ? (dk_dev ? dK : h->dstage2 + (k_dev ? 0 : nK)) : nullptr;
+  linear_embedding_kernel<<<(unsigned)((nK + 255) / 256), 256, 0, h->stream>>>(dXa, (int)na, dXb, (int)nb, D, dR, d, sigma_f,
+                                                                            sigma_n, dKo, ddK);
+  h->launches++;
+  CK(cudaGetLastError());
+  if (!k_dev) CK(cudaMemcpyAsync(K, dKo, nK * sizeof(double), cudaMemcpyDefault, h->stream));
+  if (dK && !dk_dev) CK(cudaMemcpyAsync(dK, ddK, ndK * sizeof(double), cudaMemcpyDefault, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
 // Marginal (hyper-parameter-uncertainty) variance after Osborne 2012 -- gp_functions.marginal_variance_BBQ
 // (gp_functions.py:376-454):  out[c] = dm_c^T H^-1 dm_c + pred_var[c],
 //   dm_c[p] = dK*/dtheta_p[c,:] . alpha + K*[c,:] . dalpha/dtheta_p,   dalpha/dtheta_p = -K^-1 (dK/dtheta_p alpha).

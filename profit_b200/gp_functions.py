@@ -10,15 +10,33 @@ Same names, argument meaning and error behaviour as the reference:
 * ``marginal_variance_BBQ``             gp_functions.py:376-454
 * ``predict_f``                         gp_functions.py:457-491
 
-Note on ``negative_log_likelihood``: the reference first runs eigsh warm-up passes and only falls back to a
-truncated eigen-decomposition when the Cholesky factorisation fails (:254-301).  Whenever the Cholesky branch
-is reached its value is bit-identical to ``negative_log_likelihood_cholesky``.
-This backend implements the Cholesky branch only: a non-SPD matrix raises ``np.linalg.LinAlgError``.
+Non-SPD contract of ``negative_log_likelihood`` (the objective handed to SciPy).  The reference runs eigsh warm-up
+passes and leaves its loop on a TRUNCATED EIGEN-DECOMPOSITION either when the Cholesky factorisation fails or --
+without ever trying it -- when sigma_n^2 < 1e-3 min|l| and the spectrum decays inside the first 0.05 N eigenvalues
+(:254-301).  That value is not the Cholesky NLL (tests/golden/reference_nonspd.json: +19.37 against -2517.99 on a
+perfectly SPD 1000 x 1000 matrix) and is only reproducible to the eigsh tolerance 1e-3 min|l| from a random start
+vector, so it cannot be a parity target.  Here:
+
+* whenever the covariance matrix factorises, the value IS ``negative_log_likelihood_cholesky`` (north-star target a3);
+* when it does not, ``NON_SPD_POLICY`` decides: ``"jitter"`` (default) retries on the device with a growing diagonal
+  jitter (equivalently an inflated sigma_n), emits a ``NonSPDWarning`` and records the event on the backend
+  (``backend.non_spd_events``; ``optimize`` / ``B200GPSurrogate.optimize`` expose the count), so that a caller can see
+  that the optimiser visited this region; ``"raise"`` lets ``np.linalg.LinAlgError`` propagate.
 """
+import warnings
+
 import numpy as np
 
 from .backend import shared_backend
 from .kernels import kernel_kind
+
+
+class NonSPDWarning(RuntimeWarning):
+    """The covariance matrix of an NLL evaluation was not positive definite and a jittered one was used instead."""
+
+
+NON_SPD_POLICY = "jitter"        # "jitter" | "raise"; per call: negative_log_likelihood(..., on_non_spd=...)
+JITTER_LADDER = (1e-10, 1e-8, 1e-6, 1e-4, 1e-2)   # relative to sigma_f^2
 
 
 def _train_arrays(X, y):
@@ -46,7 +64,8 @@ def invert(K, neig=0, tol=1e-10, eps=1e-6, max_iter=1000):
     The eigen-decomposition branch (``neig > 0``, :350-373) is not part of the accelerated path.
     """
     if neig and 0 < neig <= 0.05 * len(K):
-        raise NotImplementedError("the truncated eigen-decomposition branch is not implemented on the GPU path")
+        raise NotImplementedError("invert(neig > 0): the truncated eigen-decomposition branch (gp_functions.py:350-373) has no "
+                                  "in-package caller and is not implemented on the GPU path; use neig=0")
     be = shared_backend()
     K = np.asarray(K, dtype=np.float64)
     try:
@@ -82,31 +101,38 @@ def negative_log_likelihood_cholesky(hyp, X, y, kernel, eval_gradient=False, log
 
 
 def negative_log_likelihood(hyp, X, y, kernel, eval_gradient=False, log_scale_hyp=False,
-                            fixed_sigma_n_value=None, neig=0, max_iter=1000, backend=None):
+                            fixed_sigma_n_value=None, neig=0, max_iter=1000, backend=None, on_non_spd=None):
     """Objective handed to the optimiser (gp_functions.py:190-270): ``hyp`` on the log10 scale if
-    ``log_scale_hyp``; a fixed sigma_n is appended before evaluation.
+    ``log_scale_hyp``; a fixed sigma_n is appended before evaluation.  ``neig`` / ``max_iter`` are accepted for
+    signature compatibility (they steer the reference's eigsh passes, which are not reproduced).
 
-    Non-SPD handling.  The reference catches ``LinAlgError`` here and switches to a truncated
-    eigen-decomposition with eigenvalues clipped at 1e-10 (:271-301), which returns a *different* number than
-    the Cholesky NLL.  This backend keeps the optimiser alive the same way but stays on the device: the
-    factorisation is retried with a growing diagonal jitter (equivalently an inflated sigma_n, since
-    K = K_pure + sigma_n^2 I), after printing a warning like the reference does.  If no jitter up to
-    1e-2 sigma_f^2 helps, ``LinAlgError`` propagates.
+    Returns ``negative_log_likelihood_cholesky`` whenever K factorises.  Otherwise see the module docstring:
+    ``on_non_spd`` (default ``NON_SPD_POLICY``) = ``"jitter"`` retries with K + j sigma_f^2 I for j in ``JITTER_LADDER``,
+    warns with ``NonSPDWarning``, appends ``{"jitter": j, "hyp": ...}`` to ``backend.non_spd_events`` and returns that
+    NLL (gradient by the chain rule through the inflated noise); ``"raise"`` propagates ``np.linalg.LinAlgError``.
     """
+    policy = on_non_spd or NON_SPD_POLICY
+    if policy not in ("jitter", "raise"):
+        raise ValueError(f"on_non_spd must be 'jitter' or 'raise', got {policy!r}")
     hyp = np.asarray(hyp, dtype=np.float64)
     if log_scale_hyp:
         hyp = 10**hyp                      # :239-240
     fixed_sigma_n = fixed_sigma_n_value is not None
     if fixed_sigma_n:
         hyp = np.append(hyp, fixed_sigma_n_value)   # :241-243
+    if backend is None:
+        backend = shared_backend()
+        Xc, yc = _train_arrays(X, y)
+        backend.set_train(Xc, yc)
     try:
         return negative_log_likelihood_cholesky(hyp, X, y, kernel, eval_gradient=eval_gradient,
                                                 log_scale_hyp=log_scale_hyp, fixed_sigma_n=fixed_sigma_n,
                                                 backend=backend)
     except np.linalg.LinAlgError:
-        print("Warning! Covariance matrix is not positive definite; retrying with diagonal jitter.")
+        if policy == "raise":
+            raise
     sigma_f, sigma_n = float(hyp[-2]), float(hyp[-1])
-    for jitter in (1e-10, 1e-8, 1e-6, 1e-4, 1e-2):
+    for jitter in JITTER_LADDER:
         inflated = np.array(hyp, dtype=np.float64)
         inflated[-1] = np.sqrt(sigma_n**2 + jitter * sigma_f**2)
         try:
@@ -114,6 +140,10 @@ def negative_log_likelihood(hyp, X, y, kernel, eval_gradient=False, log_scale_hy
                                                    log_scale_hyp=False, fixed_sigma_n=False, backend=backend)
         except np.linalg.LinAlgError:
             continue
+        backend.non_spd_events.append({"jitter": jitter, "hyp": hyp.copy()})
+        warnings.warn(NonSPDWarning(
+            f"covariance matrix not positive definite at hyp={hyp.tolist()}; NLL evaluated with diagonal jitter "
+            f"{jitter:g} * sigma_f^2 (the reference would switch to a truncated eigen-decomposition here)"), stacklevel=2)
         if not eval_gradient:
             return out
         nll, dnll = out
@@ -135,7 +165,8 @@ def optimize(xtrain, ytrain, a0, kernel, fixed_sigma_n=False, eval_gradient=Fals
 
     ``method`` / ``bounds`` / ``options`` (extensions, defaults = the reference's call at :59-66) select another SciPy
     driver, e.g. ``method="L-BFGS-B"`` with log10 bounds as in the reference's own test (test_kernels.py:188-194);
-    ``return_result`` returns the SciPy result object as the last element."""
+    ``return_result`` returns the SciPy result object as the last element (with ``non_spd_evaluations`` = how many
+    objective evaluations needed the jitter retry, see ``negative_log_likelihood``)."""
     from scipy.optimize import minimize
 
     a0 = np.asarray(a0, dtype=np.float64)
@@ -150,6 +181,7 @@ def optimize(xtrain, ytrain, a0, kernel, fixed_sigma_n=False, eval_gradient=Fals
         backend = shared_backend()
     Xc, yc = _train_arrays(xtrain, ytrain)
     backend.set_train(Xc, yc)
+    backend.non_spd_events = []          # what this optimisation run sees (read by B200GPSurrogate.optimize)
 
     def objective(h):
         return negative_log_likelihood(h, Xc, yc, kernel, eval_gradient, True, sigma_n, backend=backend)
@@ -162,6 +194,7 @@ def optimize(xtrain, ytrain, a0, kernel, fixed_sigma_n=False, eval_gradient=Fals
             hess_inv = np.asarray(hess_inv.todense())
         out += (hess_inv,)
     if return_result:
+        opt_result["non_spd_evaluations"] = len(backend.non_spd_events)
         out += (opt_result,)
     return out[0] if len(out) == 1 else out
 

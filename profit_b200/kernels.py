@@ -43,19 +43,21 @@ def Matern52(X, Y, length_scale=1, sigma_f=1, sigma_n=0, eval_gradient=False):
 
 def LinearEmbedding(X, Y, R, sigma_f=1e-6, sigma_n=0, eval_gradient=False):
     r"""Linear-embedding kernel of Garnett (2014), python_kernels.py:60-114:
-    K = sf^2 exp(-1/2 (x-y)^T R^T R (x-y)) + sn^2 I, i.e. the squared-exponential kernel with unit length scale on the
-    projected inputs X R^T.  ``R`` is a (d, D) matrix or its flattening.
+    K = sf^2 exp(-1/2 (x-y)^T R^T R (x-y)) + sn^2 I.  ``R`` is a (d, D) matrix or its flattening (reshaped like the
+    reference does, :99); ``Y=None`` means ``Y = X`` (:101).
 
-    Only the kernel matrix is provided: the reference's derivative w.r.t. R (:108-110) is marked "TODO: check"
-    upstream and only has consistent shapes for d = 1, so there is nothing to be faithful to.
+    ``eval_gradient=True`` returns dK of shape (n, m, R.size + 2), ordered ``[R.ravel()..., sigma_f, sigma_n]``.
+    The sigma_f / sigma_n planes are the reference's (:111-112).  The R planes are the ANALYTIC derivative
+    dK/dR_ab = -K_pure (R (x-y))_a (x-y)_b: the reference's ``einsum("ijk,kl", dX**2, R) * K_pure`` (:108-110) is marked
+    "TODO: check" upstream, is only shape-consistent for d = 1 and is not the derivative of K there (wrong sign and
+    (R delta)_a^2 R_ab in place of (R delta)_a delta_b); tests/test_gpu_parity.py checks this one by finite differences.
     """
-    if eval_gradient:
-        raise NotImplementedError("dK/dR of LinearEmbedding is unverified upstream (python_kernels.py:106) and not provided")
     X = np.atleast_2d(np.asarray(X, dtype=np.float64))
     R = np.asarray(R, dtype=np.float64)
-    R = R.reshape(R.size // X.shape[-1], X.shape[-1])
+    R = np.ascontiguousarray(R.reshape(R.size // X.shape[-1], X.shape[-1]))
     Yp = X if Y is None else np.atleast_2d(np.asarray(Y, dtype=np.float64))
-    return _evaluate(KIND_RBF, X @ R.T, Yp @ R.T, 1.0, sigma_f, sigma_n, False)
+    return shared_backend().linear_embedding(np.ascontiguousarray(X), np.ascontiguousarray(Yp), R, _scalar(sigma_f),
+                                             _scalar(sigma_n), eval_gradient)
 
 
 RBF.gpb_kind = KIND_RBF

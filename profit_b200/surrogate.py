@@ -148,6 +148,7 @@ class B200GPSurrogate(_GPBase):
     def __init__(self, device=None):
         super().__init__()
         self.hess_inv = None
+        self.non_spd_evaluations = 0
         self._device = device
         self._backend = None      # may be shared between surrogates (multi-output children): residency is tracked on it
 
@@ -324,6 +325,8 @@ class B200GPSurrogate(_GPBase):
         if return_hess_inv:
             self.hess_inv = opt[1]
             opt = opt[0]
+        # how many objective evaluations of this fit hit a non-SPD covariance matrix (gp_functions.NonSPDWarning)
+        self.non_spd_evaluations = len(self.backend.non_spd_events)
         self._set_hyperparameters_from_model(opt, fixed)
         self.print_hyperparameters("Optimized")
 
@@ -385,7 +388,9 @@ class B200GPSurrogate(_GPBase):
 
 class B200MultiOutputGPSurrogate(_GPBase):
     """Independent GP per output column -- mirror of ``MultiOutputGPSurrogate`` ("CustomMultiOutputGP",
-    custom_surrogate.py:285-451) with ``B200GPSurrogate`` children.
+    custom_surrogate.py:285-451) with ``B200GPSurrogate`` children, including its encoder handling: the parent
+    encodes the training data (``Surrogate.pre_train``), the children are trained on the ENCODED arrays and carry no
+    encoders of their own, hyper-parameters and predictions are decoded by the parent (:292-350).
 
     Every child owns a device handle, so its training set and factor stay resident (a prediction over all outputs
     does not refactorise) and the children are fitted ``concurrent`` at a time on host threads -- a single
@@ -410,21 +415,45 @@ class B200MultiOutputGPSurrogate(_GPBase):
             m._backend = self._shared_backend
         return m
 
-    def pre_train(self, X, y, *args, **kwargs):
+    def infer_hyperparameters(self):
+        """gaussian_process.py:124-136 on the (encoded) training data, pairwise mean distance on the device."""
+        std = np.mean(np.std(self.ytrain, axis=0))
+        spread = np.mean(np.abs(self.ytrain.max(axis=0) - self.ytrain.min(axis=0)))
+        be = self._shared_backend or GPBackend(self._device)
+        dist = be.mean_pairwise_distance(np.ascontiguousarray(self.Xtrain, dtype=np.float64))
+        if be is not self._shared_backend:
+            be.close()
+        return {"length_scale": np.array([0.5 * dist]), "sigma_f": np.array([std]), "sigma_n": 1e-2 * np.array([spread])}
+
+    def pre_train(self, X, y, kernel=_gp_defaults["kernel"], hyperparameters=_gp_defaults["hyperparameters"],
+                  fixed_sigma_n=_base_defaults["fixed_sigma_n"]):
+        """GaussianProcess.pre_train (gaussian_process.py:74-114): check + ENCODE the training data, take kernel /
+        hyper-parameters / fixed_sigma_n from the config, the arguments or the defaults, infer what is missing.  Only
+        difference: the inference runs when a value is actually missing (the reference always builds an (N, N, D)
+        tensor on the host)."""
         if HAVE_PROFIT:
-            _Surrogate.pre_train(self, X, y)
+            _Surrogate.pre_train(self, X, y)          # sur.py:136-164, encodes
         else:
             self._check_training_data(X, y)
         self.output_ndim = self.ytrain.shape[-1]
+        self.set_attributes(fixed_sigma_n=fixed_sigma_n, kernel=kernel, hyperparameters=hyperparameters)
+        inferred = None
+        for key, value in self.hyperparameters.items():
+            if value is None:
+                if inferred is None:
+                    inferred = self.infer_hyperparameters()
+                value = inferred[key]
+            self.hyperparameters[key] = np.atleast_1d(value)
+        self.print_hyperparameters("Initial")
+        if isinstance(self.kernel, str):
+            self.kernel = self.select_kernel(self.kernel)
 
     def train(self, X, y, kernel=_gp_defaults["kernel"], hyperparameters=_gp_defaults["hyperparameters"],
               fixed_sigma_n=_base_defaults["fixed_sigma_n"], return_hess_inv=False):
         """custom_surrogate.py:292-315.  Like the reference, the children are trained with eval_gradient=False
-        (the positional ``False`` at :309), i.e. SciPy finite-differences the device NLL."""
-        self.pre_train(X, y)
-        self.kernel = kernel if self.kernel is None else self.kernel
-        self.hyperparameters = dict(hyperparameters) if not self.hyperparameters else self.hyperparameters
-        self.fixed_sigma_n = fixed_sigma_n or self.fixed_sigma_n
+        (the positional ``False`` at :309), i.e. SciPy finite-differences the device NLL, on the encoded data; then the
+        hyper-parameters are merged and decoded and ``post_train`` decodes the parent's training arrays."""
+        self.pre_train(X, y, kernel, hyperparameters, fixed_sigma_n)
         self.models = [self._new_child() for _ in range(self.output_ndim)]
 
         def fit(dim):
@@ -441,29 +470,38 @@ class B200MultiOutputGPSurrogate(_GPBase):
             with ThreadPoolExecutor(max_workers=workers) as pool:     # the C calls release the GIL
                 list(pool.map(fit, range(self.output_ndim)))
         self._set_hyperparameters_from_model()
-        self.trained = True
+        self.post_train()                                             # sur.py:166-168: trained, decode training data
 
     def _set_hyperparameters_from_model(self):
-        # custom_surrogate.py:317-328: children concatenated, then reduced to norm / max
-        merged = {k: np.concatenate([np.atleast_1d(m.hyperparameters[k]) for m in self.models])
-                  for k in ("length_scale", "sigma_f", "sigma_n")}
-        self.hyperparameters = {"length_scale": np.atleast_1d(np.linalg.norm(merged["length_scale"])),
-                                "sigma_f": np.atleast_1d(np.max(merged["sigma_f"])),
-                                "sigma_n": np.atleast_1d(np.max(merged["sigma_n"]))}
+        # custom_surrogate.py:317-330 verbatim in effect: the children's values are appended to the parent's own
+        # (initial) ones, then reduced to norm / max, then decoded
+        for m in self.models:
+            for k, v in m.hyperparameters.items():
+                self.hyperparameters[k] = np.concatenate([np.atleast_1d(self.hyperparameters[k]), np.atleast_1d(v)])
+        self.hyperparameters["length_scale"] = np.atleast_1d(np.linalg.norm(self.hyperparameters["length_scale"]))
+        self.hyperparameters["sigma_f"] = np.atleast_1d(np.max(self.hyperparameters["sigma_f"]))
+        self.hyperparameters["sigma_n"] = np.atleast_1d(np.max(self.hyperparameters["sigma_n"]))
+        self.decode_hyperparameters()
 
     def predict(self, Xpred, add_data_variance=True):
+        """custom_surrogate.py:332-340: encode Xpred (pre_predict), children on encoded points, decode the outputs."""
         Xpred = self.pre_predict(Xpred)
         ypred = np.empty((Xpred.shape[0], self.output_ndim))
         yvar = np.empty_like(ypred)
         for dim, m in enumerate(self.models):
             ypred[:, [dim]], yvar[:, [dim]] = m.predict(Xpred, add_data_variance)
-        return ypred, yvar
+        return self.decode_predict_data(ypred, yvar)
 
     def add_training_data(self, X, y):
+        """custom_surrogate.py:342-350: append raw rows, encode everything, hand the encoded new rows to the children,
+        decode the parent's copy again."""
+        start = self.Xtrain.shape[0]
         self.Xtrain = np.concatenate([self.Xtrain, X], axis=0)
         self.ytrain = np.concatenate([self.ytrain, y], axis=0)
+        self.encode_training_data()
         for dim, m in enumerate(self.models):
-            m.add_training_data(X, y[:, [dim]])
+            m.add_training_data(self.Xtrain[start:], self.ytrain[start:, [dim]])
+        self.decode_training_data()
 
     def set_ytrain(self, y):
         for dim, m in enumerate(self.models):
@@ -477,12 +515,106 @@ class B200MultiOutputGPSurrogate(_GPBase):
     def select_kernel(self, kernel):
         return select_kernel(kernel)
 
+    def special_hyperparameter_decoding(self, key, value):
+        """custom_surrogate.py:437-444."""
+        if len(value) > 1:
+            return np.atleast_1d(np.linalg.norm(value)) if key == "length_scale" else np.atleast_1d(np.max(value))
+        return value
+
+    def get_marginal_variance(self, Xpred):
+        """custom_surrogate.py:446-451: sum of the children's marginal variances at the encoded points."""
+        Xpred = self.encode_predict_data(Xpred)
+        v = np.zeros((Xpred.shape[0], 1))
+        for m in self.models:
+            v += m.get_marginal_variance(Xpred)
+        return v
+
+    _PARENT_ATTRS = ("Xtrain", "ytrain", "trained", "output_ndim", "hyperparameters")
+    _CHILD_ATTRS = ("trained", "fixed_sigma_n", "Xtrain", "ytrain", "ndim", "output_ndim", "kernel", "hyperparameters")
+
+    def _save_dict(self):
+        """The dictionary custom_surrogate.py:357-390 hands to FileHandler.save."""
+        save_dict = {attr: getattr(self, attr) for attr in self._PARENT_ATTRS}
+        save_dict["input_encoders"] = str([enc.repr for enc in self.input_encoders])
+        save_dict["output_encoders"] = str([enc.repr for enc in self.output_encoders])
+        for i, m in enumerate(self.models):
+            save_dict[i] = {attr: getattr(m, attr) for attr in self._CHILD_ATTRS}
+            if not isinstance(save_dict[i]["kernel"], str):
+                save_dict[i]["kernel"] = m.kernel.__name__
+        return save_dict
+
     def save_model(self, path):
-        raise NotImplementedError("use the children's save_model (custom_surrogate.py:356-390 needs proFit's HDF5 handler)")
+        """custom_surrogate.py:352-390: the same nested dictionary (parent arrays, encoder reprs, one group per child).
+        ``.hdf5`` goes through proFit's FileHandler (needs h5py); ``.npz`` is the h5py-free container of the same keys
+        ("<child>/<attr>", "hyperparameters/<name>")."""
+        save_dict = self._save_dict()
+        if str(path).endswith(".npz"):
+            flat = {}
+            for k, v in save_dict.items():
+                if isinstance(v, dict):
+                    for kk, vv in v.items():
+                        if isinstance(vv, dict):
+                            for k3, v3 in vv.items():
+                                flat[f"{k}/{kk}/{k3}"] = v3
+                        else:
+                            flat[f"{k}/{kk}"] = vv
+                else:
+                    flat[str(k)] = v
+            np.savez(path, **flat)
+            return
+        from profit.util.file_handler import FileHandler
+
+        FileHandler.save(path, save_dict)
 
     @classmethod
     def load_model(cls, path):
-        raise NotImplementedError("use the children's load_model")
+        """custom_surrogate.py:392-431: restore the parent, rebuild its encoders (and initialise them by one encode /
+        decode round trip), then the children."""
+        if str(path).endswith(".npz"):
+            data = np.load(path, allow_pickle=False)
+            load_dict = {}
+            for key in data.files:
+                parts = key.split("/")
+                node = load_dict
+                for part in parts[:-1]:
+                    node = node.setdefault(part, {})
+                val = data[key]
+                node[parts[-1]] = val.item() if val.ndim == 0 else val
+        else:
+            from profit.util.file_handler import FileHandler
+
+            load_dict = FileHandler.load(path, as_type="dict")
+        self = cls()
+        self.trained = bool(load_dict["trained"])
+        self.output_ndim = int(load_dict["output_ndim"])
+        self.Xtrain, self.ytrain = load_dict["Xtrain"], load_dict["ytrain"]
+        self.hyperparameters = dict(load_dict["hyperparameters"])
+        self.ndim = self.Xtrain.shape[-1]
+        if HAVE_PROFIT:
+            from numpy import array  # noqa: F401  (needed by eval of the encoder reprs, as upstream)
+            from profit.sur.encoders import Encoder
+
+            for enc in eval(str(load_dict["input_encoders"])):
+                self.add_input_encoder(Encoder[enc["class"]](enc["columns"], enc["parameters"]))
+            for enc in eval(str(load_dict["output_encoders"])):
+                self.add_output_encoder(Encoder[enc["class"]](enc["columns"], enc["parameters"]))
+            self.encode_training_data()
+            self.decode_training_data()
+        self.models = [self._new_child() for _ in range(self.output_ndim)]
+        for i, m in enumerate(self.models):
+            for attr, value in load_dict[str(i)].items():
+                if attr in ("trained", "fixed_sigma_n"):
+                    value = bool(value)
+                elif attr in ("ndim", "output_ndim"):
+                    value = int(value)
+                elif attr == "kernel":
+                    value = str(value)
+                elif attr == "hyperparameters":
+                    value = dict(value)
+                setattr(m, attr, value)
+            m.kernel = m.select_kernel(m.kernel)
+            m.print_hyperparameters("Loaded")
+        return self
 
 
 def register(label="B200"):

@@ -76,7 +76,7 @@ def test_product_code_never_imports_the_oracle():
                     text = open(os.path.join(dirpath, f)).read()
                     assert not re.search(r"^\s*(import|from)\s+oracle\b", text, flags=re.M), f"{sub}/{f} imports the oracle"
     # bench.py: only inside the CPU-baseline / reference-arm functions; __graft_entry__: only inside smoke()
-    for name, allowed in (("bench.py", ("cpu_nll_grad_sample", "cpu_predict_sample", "reference_arm", "run_reference")),
+    for name, allowed in (("bench.py", ("cpu_nll_grad_eval", "cpu_nll_grad_sample", "cpu_predict_sample", "run_reference")),
                           ("__graft_entry__.py", ("smoke",))):
         text = open(os.path.join(ROOT, name)).read()
         assert not re.search(r"^(import|from)\s+oracle\b", text, flags=re.M), f"{name} imports the oracle at module level"

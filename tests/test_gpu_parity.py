@@ -1,6 +1,8 @@
 """Parity of the CUDA path against the oracle and the reference's golden vectors, through the C ABI
 (ctypes -> libgpb.so).  Tolerances are the north-star's: NLL and gradient 1e-9 relative, predictive mean and
 variance 1e-8 relative (fp64)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -587,26 +589,84 @@ def test_linear_embedding_kernel_matrix(backend, golden):
     X, Y, R = rng.random((c["n"], c["D"])), rng.random((c["m"], c["D"])), rng.standard_normal((c["d"], c["D"]))
     K = LinearEmbedding(X, Y, R.ravel(), c["sigma_f"], c["sigma_n"])
     assert np.allclose(K, c["K"], rtol=1e-12, atol=1e-15)
-    with pytest.raises(NotImplementedError):
-        LinearEmbedding(X, Y, R, eval_gradient=True)
+    # derivative planes: sigma_f / sigma_n as the reference (python_kernels.py:111-112), R planes = analytic derivative,
+    # checked by central finite differences of the kernel itself (upstream's own expression is an unverified TODO)
+    K2, dK = LinearEmbedding(X, Y, R, c["sigma_f"], c["sigma_n"], eval_gradient=True)
+    assert np.array_equal(K2, K) and dK.shape == (c["n"], c["m"], R.size + 2)
+    Kp = K - c["sigma_n"] ** 2 * np.eye(c["n"], c["m"])
+    assert np.allclose(dK[..., -2], 2 / c["sigma_f"] * Kp, rtol=1e-13)
+    assert np.allclose(dK[..., -1], 2 * c["sigma_n"] * np.eye(c["n"], c["m"]), rtol=1e-15)
+    eps = 1e-6
+    for p in range(R.size):
+        Rp, Rm = R.ravel().copy(), R.ravel().copy()
+        Rp[p] += eps
+        Rm[p] -= eps
+        fd = (LinearEmbedding(X, Y, Rp, c["sigma_f"], c["sigma_n"]) - LinearEmbedding(X, Y, Rm, c["sigma_f"], c["sigma_n"])) / (2 * eps)
+        assert np.allclose(dK[..., p], fd, rtol=1e-6, atol=1e-9), (p, np.abs(dK[..., p] - fd).max())
+    # Y = None means Y = X (python_kernels.py:101); a d = 1 embedding along e_0 is the isotropic RBF in x_0
+    from profit_b200 import RBF
+    assert np.allclose(LinearEmbedding(X, None, R, 1.0, 0.1), LinearEmbedding(X, X, R, 1.0, 0.1), rtol=0, atol=0)
+    e0 = np.zeros((1, c["D"])); e0[0, 0] = 1 / 0.7
+    assert np.allclose(LinearEmbedding(X, Y, e0, 1.2, 0.0), RBF(X[:, :1], Y[:, :1], 0.7, 1.2, 0.0), rtol=1e-13)
 
 
-def test_objective_survives_a_singular_covariance(backend, capsys):
-    """gp_functions.negative_log_likelihood keeps the optimiser alive when the Cholesky factorisation fails
-    (the reference falls back to an eigen-decomposition, gp_functions.py:271-301; here: on-device jitter retry),
-    while negative_log_likelihood_cholesky itself raises like the reference's does."""
-    from profit_b200 import RBF, gp_functions as gpf
+def test_non_spd_contract(backend):
+    """The non-SPD contract of gp_functions.negative_log_likelihood (module docstring): Cholesky value whenever K
+    factorises; otherwise jitter retry + NonSPDWarning + a recorded event, or LinAlgError with on_non_spd="raise".
+    Pinned against tests/golden/reference_nonspd.json (generated from the unmodified reference)."""
+    import json
+    import warnings
 
-    X = np.repeat(np.random.default_rng(0).random((10, 2)), 3, axis=0)      # every point three times
-    y = np.sin(X[:, 0])
-    hyp = np.array([0.5, 1.0, 0.0])                                          # no noise: exactly singular
+    from profit_b200 import RBF, B200GPSurrogate, gp_functions as gpf
+
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_nonspd.json")))
+    # (1) the survey's quirk case: the reference leaves on the eig branch (+19.37) although K is SPD; the drop-in
+    # returns the Cholesky NLL -- the reference's own negative_log_likelihood_cholesky value -- without any warning
+    q = gold["quirk"]
+    X = np.linspace(0.0, 1.0, q["N"]).reshape(-1, 1)
+    y = np.sin(3 * X[:, 0]) + 0.02 * np.random.default_rng(q["noise_seed"]).standard_normal(q["N"])
+    hyp = np.array(q["hyp"])
+    with warnings.catch_warnings():
+        warnings.simplefilter("error", gpf.NonSPDWarning)
+        nll, g = gpf.negative_log_likelihood(np.log10(hyp), X, y, RBF, eval_gradient=True, log_scale_hyp=True)
+    assert abs(nll - q["a3_nll"]) <= 1e-9 * abs(q["a3_nll"])
+    assert np.all(np.abs(g / (hyp * np.log(10)) - q["a3_grad"]) <= 2e-7 * np.abs(q["a3_grad"]))   # cond(K) ~ 1e7
+    assert all(abs(r["nll"] - 19.37) < 0.01 for r in q["a4_eig_branch_runs"])     # what upstream returns instead
+
+    # (2) exactly singular K (every point three times, no noise): the Cholesky twin raises like the reference's
+    s = gold["singular"]
+    Xs = np.repeat(np.random.default_rng(0).random((10, 2)), 3, axis=0)
+    ys = np.sin(Xs[:, 0])
+    hs = np.array(s["hyp"])
+    assert s["a3"] == "LinAlgError"
     with pytest.raises(np.linalg.LinAlgError):
-        gpf.negative_log_likelihood_cholesky(hyp, X, y, RBF, eval_gradient=True)
-    with np.errstate(divide="ignore"):
-        nll, g = gpf.negative_log_likelihood(np.log10(np.array([0.5, 1.0, 1e-12])), X, y, RBF, eval_gradient=True,
-                                             log_scale_hyp=True)
+        gpf.negative_log_likelihood_cholesky(np.array([0.5, 1.0, 0.0]), Xs, ys, RBF, eval_gradient=True)
+    with pytest.raises(np.linalg.LinAlgError):
+        gpf.negative_log_likelihood(np.log10(hs), Xs, ys, RBF, log_scale_hyp=True, on_non_spd="raise")
+    # default policy: warning + event + the Cholesky NLL of K + j sf^2 I for the first j of the ladder that factorises
+    be = gpf.shared_backend()
+    be.non_spd_events = []
+    with pytest.warns(gpf.NonSPDWarning, match="diagonal jitter"):
+        nll, g = gpf.negative_log_likelihood(np.log10(hs), Xs, ys, RBF, eval_gradient=True, log_scale_hyp=True)
     assert np.isfinite(nll) and np.all(np.isfinite(g)) and g.shape == (3,)
-    assert "retrying with diagonal jitter" in capsys.readouterr().out
+    assert len(be.non_spd_events) == 1 and be.non_spd_events[0]["jitter"] in gpf.JITTER_LADDER
+    j = be.non_spd_events[0]["jitter"]
+    ref = oracle.nll_cholesky(np.array([hs[0], hs[1], np.sqrt(hs[2] ** 2 + j * hs[1] ** 2)]), Xs, ys, oracle.rbf)
+    assert abs(nll - ref) <= 1e-6 * abs(ref)            # K is singular up to the jitter: cond ~ 1 / j
+    # the reference returns its truncated-eig number here (-47.04); recorded so that the difference is documented
+    assert abs(s["a4_eig_branch_nll"] + 47.04) < 0.01 and abs(nll - s["a4_eig_branch_nll"]) > 1.0
+
+    # (3) a fit that visits the region reports it
+    sur = B200GPSurrogate()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", gpf.NonSPDWarning)
+        sur.train(Xs, ys.reshape(-1, 1), hyperparameters={"length_scale": np.array([0.5]), "sigma_f": np.array([1.0]),
+                                                           "sigma_n": np.array([1e-9])})
+    assert sur.non_spd_evaluations == len(sur.backend.non_spd_events) and sur.non_spd_evaluations >= 1
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", gpf.NonSPDWarning)
+        m, v = sur.predict(Xs[:5])                      # predict tolerates it too (1e-6 retry of gp_functions.invert)
+    assert np.all(np.isfinite(m)) and np.all(v > 0)
 
 
 def test_predict_f_full_covariance(backend, golden):

@@ -23,9 +23,11 @@ class OracleBackedFake:
 
     def __init__(self):
         self.calls = 0
-        self.resident_key = self.factor_key = None
+        self.resident_key = self.factor_key = self.noise_override = None
+        self.non_spd_events = []
 
     def set_train(self, X, y):
+        self.noise_override = None
         self.X, self.y = np.array(X), np.array(y)
         self.n_out = 1 if self.y.ndim == 1 else self.y.shape[1]
 
@@ -41,7 +43,10 @@ class OracleBackedFake:
     # -- what the predict / add_training_data plumbing touches
     def factorize(self, kind, theta):
         self.factorizations = getattr(self, "factorizations", 0) + 1
+        self.noise_override = None
         self.kind, self.theta = kind, np.array(theta)
+        if getattr(self, "fail_below_sn", None) is not None and self.theta[-1] < self.fail_below_sn:
+            raise np.linalg.LinAlgError("not positive definite (test double)")
 
     def append_train(self, X, y):
         self.appends = getattr(self, "appends", 0) + 1
@@ -159,15 +164,43 @@ def test_multi_output_wrapper_trains_one_child_per_column(golden):
     s.train(X, Y)
     assert s.trained and s.output_ndim == 2 and len(s.models) == 2
     assert all(m._backend is s._shared_backend for m in s.models)
-    ls = np.concatenate([m.hyperparameters["length_scale"] for m in s.models])
+    # custom_surrogate.py:317-330 appends the children's values to the PARENT's own initial (inferred) ones before the
+    # norm / max reduction -- mirrored, quirk included
+    dist = s._shared_backend.mean_pairwise_distance(X)
+    ls = np.concatenate([[0.5 * dist]] + [m.hyperparameters["length_scale"] for m in s.models])
     assert np.allclose(s.hyperparameters["length_scale"], [np.linalg.norm(ls)])
-    assert np.allclose(s.hyperparameters["sigma_f"], [max(m.hyperparameters["sigma_f"][0] for m in s.models)])
+    sf0 = np.mean(np.std(Y, axis=0))
+    assert np.allclose(s.hyperparameters["sigma_f"], [max([sf0] + [m.hyperparameters["sigma_f"][0] for m in s.models])])
     # the second output is an affine image of the first: same length scale, doubled signal scale
     assert np.allclose(s.models[1].hyperparameters["length_scale"], s.models[0].hyperparameters["length_scale"], rtol=5e-2)
     s.add_training_data(np.array([[0.3, 0.3]]), np.array([[0.5, 1.1]]))
     assert s.models[1].ytrain.shape == (61, 1) and s.models[1].ytrain[-1, 0] == 1.1
     s.set_ytrain(np.zeros((61, 2)))
     assert s.models[0].ytrain.shape == (61, 1)
+
+
+def test_predict_retries_a_failed_factorisation_with_jitter(golden):
+    """_ensure_factor retries a non-SPD Ky once with 1e-6 on the diagonal (gp_functions.invert, :343-346) and
+    predict keeps reporting the model's own sigma_n^2 as data variance."""
+    from profit_b200 import B200GPSurrogate
+
+    c = golden["c0_train"]
+    X, y = np.array(c["X"])[:40], np.array(c["y"])[:40]
+    s = B200GPSurrogate()
+    fake = s._backend = OracleBackedFake()
+    s.Xtrain, s.ytrain, s.ndim, s.trained = X, y, 2, True
+    s.kernel = s.select_kernel("RBF")
+    s.hyperparameters = {"length_scale": np.array([0.4]), "sigma_f": np.array([1.0]), "sigma_n": np.array([1e-5])}
+    fake.fail_below_sn = 5e-4                       # Ky(sigma_n = 1e-5) "fails", Ky + 1e-6 I (sigma_n' = 1.0000e-3) works
+    Xq = np.random.default_rng(3).random((7, 2))
+    m, v = s.predict(Xq)
+    assert fake.factorizations == 2 and abs(fake.theta[-1] - np.sqrt(1e-10 + 1e-6)) < 1e-15
+    assert abs(fake.noise_override - 1e-10) < 1e-24
+    m0, v0 = s.predict(Xq, add_data_variance=False)
+    assert fake.factorizations == 2                  # cached
+    assert np.allclose(v - v0, 1e-10, rtol=0, atol=1e-15) and np.array_equal(m, m0)
+    ref_m, ref_v = oracle.predict(X, y, Xq, oracle.rbf, np.array([0.4]), 1.0, np.sqrt(1e-10 + 1e-6), add_data_variance=False)
+    assert np.allclose(m, ref_m) and np.allclose(v0, ref_v)
 
 
 def test_shard_bounds_cover_everything_once():

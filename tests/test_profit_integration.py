@@ -217,6 +217,78 @@ mv_g = gpu.get_marginal_variance(Xc[:64])
 assert mv_g.shape == mv_r.shape == (64, 1)
 assert np.allclose(mv_g, mv_r, rtol=2e-2), np.max(np.abs(mv_g - mv_r) / mv_r)
 
+# multi-output surrogate THROUGH Surrogate.from_config, i.e. with the default encoders attached (sur.py:262-284:
+# Normalization on inputs and outputs): parent encodes, children are trained on encoded data, predictions and
+# training arrays come back decoded (custom_surrogate.py:292-350) -- next to the reference's CustomMultiOutputGP
+def mo_config(label):
+    open("profit_mo.yaml", "w").write("""
+ntrain: 10
+include: %s
+variables:
+    u: Uniform(0, 2)
+    v: Uniform(-1, 3)
+    f: Output
+    g: Output
+run:
+    worker: {class: function, entry_point: f}
+fit:
+    surrogate: %s
+    kernel: RBF
+""" % (SHIM, label))
+    return BaseConfig.from_file("profit_mo.yaml")
+
+Xm = np.column_stack([2 * X[:, 0], 4 * X[:, 1] - 1])                      # raw inputs away from the unit cube
+Ym = np.column_stack([30 + 5 * np.sin(3 * X[:, 0]) + 2 * np.cos(2 * X[:, 1]), -200 + 40 * X[:, 0] * X[:, 1]])
+Ym = Ym + np.array([0.25, 1.0]) * rng.standard_normal(Ym.shape)          # noisy: both sides stay on the Cholesky branch
+Xq = np.column_stack([2 * Xc[:50, 0], 4 * Xc[:50, 1] - 1])
+mos = {}
+for label in ("CustomMultiOutputGP", "B200MultiOutputGP"):
+    cm = mo_config(label)
+    mo = Surrogate.from_config(cm["fit"], cm)
+    assert len(mo.input_encoders) >= 1 and len(mo.output_encoders) >= 1, "default encoders expected"
+    mo.train(Xm, Ym)
+    mos[label] = mo
+mo_r, mo_g = mos["CustomMultiOutputGP"], mos["B200MultiOutputGP"]
+assert type(mo_g) is ps.B200MultiOutputGPSurrogate and mo_g.trained
+assert np.allclose(mo_g.Xtrain, Xm) and np.allclose(mo_g.ytrain, Ym), "parent training arrays must be decoded after train"
+pr, vr2 = mo_r.predict(Xq); pg, vg2 = mo_g.predict(Xq)
+assert pg.shape == pr.shape == (50, 2) and vg2.shape == vr2.shape
+assert np.abs(pg[:, 0] - 30).max() < 15 and np.abs(pg[:, 1] + 180).max() < 60, "predictions must be in the raw output scale"
+assert np.allclose(pg, pr, rtol=2e-2, atol=0.2), np.abs(pg - pr).max()     # finite-difference BFGS on both sides
+# identical child hyper-parameters -> identical numbers, to the north-star tolerance, through the encoders
+for cr, cg in zip(mo_r.models, mo_g.models):
+    cg.hyperparameters = {k: np.array(v, dtype=float).copy() for k, v in cr.hyperparameters.items()}
+pr, vr2 = mo_r.predict(Xq); pg, vg2 = mo_g.predict(Xq)
+assert np.max(np.abs(pg - pr) / np.abs(pr)) <= 1e-8 and np.max(np.abs(vg2 - vr2) / vr2) <= 1e-7, (np.abs(pg - pr).max(), np.max(np.abs(vg2 - vr2) / vr2))
+# add_training_data: raw rows in, parent arrays stay raw, children receive the encoded rows
+for mo in (mo_r, mo_g):
+    mo.add_training_data(Xq[:3], np.column_stack([pr[:3, 0], pr[:3, 1]]))
+assert mo_g.Xtrain.shape == (153, 2) and np.allclose(mo_g.Xtrain, mo_r.Xtrain) and np.allclose(mo_g.ytrain, mo_r.ytrain)
+assert np.allclose(mo_g.models[0].Xtrain, mo_r.models[0].Xtrain) and np.allclose(mo_g.models[1].ytrain, mo_r.models[1].ytrain)
+pr, vr2 = mo_r.predict(Xq); pg, vg2 = mo_g.predict(Xq)
+assert np.max(np.abs(pg - pr) / np.abs(pr)) <= 1e-8 and np.max(np.abs(vg2 - vr2) / vr2) <= 1e-6
+# save / load (.npz container of the reference's dictionary) keeps encoders, children and predictions
+mo_g.save_model("model_mo.npz")
+mo_l = ps.B200MultiOutputGPSurrogate.load_model("model_mo.npz")
+assert len(mo_l.input_encoders) == len(mo_g.input_encoders) and len(mo_l.models) == 2
+pl, vl = mo_l.predict(Xq)
+assert np.allclose(pl, pg, rtol=1e-10) and np.allclose(vl, vg2, rtol=1e-8)
+mvr, mvg = mo_r.get_marginal_variance(Xq[:16]), mo_g.get_marginal_variance(Xq[:16])
+assert mvg.shape == mvr.shape == (16, 1) and np.all(np.isfinite(mvg))
+assert mo_g.special_hyperparameter_decoding("length_scale", np.array([3.0, 4.0]))[0] == 5.0
+
+# single-output surrogate with input encoders attached: get_marginal_variance must evaluate at the points predict()
+# uses (the reference passes the raw Xpred on, custom_surrogate.py:152-163)
+cs = mo_config("B200"); cs_ref = mo_config("Custom")
+ge, re_ = Surrogate.from_config(cs["fit"], cs), Surrogate.from_config(cs_ref["fit"], cs_ref)
+for s4 in (ge, re_):
+    s4.output_ndim = 1
+    s4.train(Xm, Ym[:, [0]])
+    s4.hyperparameters = {"length_scale": np.array([0.9]), "sigma_f": np.array([4.0]), "sigma_n": np.array([0.4])}
+assert len(ge.input_encoders) >= 1
+mve, mvr1 = ge.get_marginal_variance(Xq[:32]), re_.get_marginal_variance(Xq[:32])
+assert np.allclose(mve, mvr1, rtol=5e-2), np.max(np.abs(mve - mvr1) / mvr1)
+
 pa.register_as_default()                                  # last: from here on the reference's labels select the twins
 assert AcquisitionFunction["simple_exploration"] is pa.SimpleExploration
 print("profit integration ok", hg)
