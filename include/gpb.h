@@ -15,9 +15,11 @@
  *     < 0 = bad argument (-1), CUDA failure (-2), not ready (-3).  gpb_error_string() describes the last error.
  *   - One handle = one device + one stream; calls on a handle must be serialised by the caller.
  *   - Stream semantics for device pointers: the handle's stream is a blocking stream, i.e. it is ordered after work
- *     already queued on the legacy default stream (the one torch uses unless told otherwise); producers on other
- *     streams must synchronise before the call.  Every entry point is host-synchronous: when it returns, its
- *     outputs (host or device) are complete.
+ *     already queued on the legacy default stream (the one torch uses unless told otherwise).  A caller that
+ *     produces device buffers on another stream names it with gpb_set_stream(); every later call is then ordered
+ *     after the work queued on that stream at call time (event record + wait, no host synchronisation), which is
+ *     what the Python layer does with torch.cuda.current_stream().  Every entry point is host-synchronous: when it
+ *     returns, its outputs (host or device) are complete.
  *   - There is no CPU fallback anywhere behind this interface.
  */
 #ifndef GPB_H_
@@ -49,6 +51,11 @@ int gpb_version(void);
 int gpb_create(int device, gpb_handle_t* out);
 int gpb_destroy(gpb_handle_t h);
 const char* gpb_error_string(gpb_handle_t h);
+
+/* Name the CUDA stream (a cudaStream_t, passed as void*) on which the caller produces the device buffers it hands to
+ * this handle; NULL (the default) = the legacy default stream.  See "Stream semantics" above.  The stream is
+ * borrowed, never destroyed, and must stay alive while it is set. */
+int gpb_set_stream(gpb_handle_t h, void* cuda_stream);
 
 /* Upload the training set once; it stays resident across optimiser iterations.
  * Replaces the (X, y) arguments threaded through gp_functions.optimize (gp_functions.py:8-69) and the

@@ -21,6 +21,7 @@ SIGNATURES = {
     "gpb_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
     "gpb_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "gpb_error_string": (ctypes.c_char_p, [ctypes.c_void_p]),
+    "gpb_set_stream": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "gpb_set_train": (ctypes.c_int, [ctypes.c_void_p, _c_double_p, _c_double_p, _ll, ctypes.c_int, ctypes.c_int]),
     "gpb_nll": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _c_double_p, ctypes.c_int, ctypes.c_int,
                                ctypes.POINTER(ctypes.c_double), _c_double_p]),
@@ -99,6 +100,10 @@ def ptr(x):
             raise ValueError("expected a contiguous float64 tensor")
         return ctypes.c_void_p(x.data_ptr())
     raise TypeError(f"cannot take the address of {type(x)!r}")
+
+
+def is_cuda_tensor(x):
+    return x is not None and not isinstance(x, np.ndarray) and hasattr(x, "data_ptr") and getattr(x, "is_cuda", False)
 
 
 def as_f64(a):

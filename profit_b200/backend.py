@@ -35,8 +35,22 @@ class GPBackend:
         # bookkeeping for callers that share one backend (set by B200GPSurrogate): what is resident / factorised
         self.resident_key = None
         self.factor_key = None
+        self._caller_stream = 0        # cudaStream_t last passed to gpb_set_stream (0 = legacy default stream)
         self.non_spd_events = []       # jitter retries of gp_functions.negative_log_likelihood since the last optimize()
         self.noise_override = None     # set by B200GPSurrogate when the resident factor carries the 1e-6 jitter retry
+
+    def _order(self, *arrays):
+        """Stream ordering for device arguments (include/gpb.h, "Stream semantics"): when any argument is a torch CUDA
+        tensor, tell the library which torch stream is current so that the call is ordered after the work queued on
+        it -- a producer on a non-default stream needs no manual synchronisation."""
+        if not any(_lib.is_cuda_tensor(a) for a in arrays):
+            return
+        import torch
+
+        stream = int(torch.cuda.current_stream(self.device).cuda_stream)
+        if stream != self._caller_stream:
+            _lib.check(self._lib.gpb_set_stream(self._h, ctypes.c_void_p(stream)), self._h, "set_stream")
+            self._caller_stream = stream
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
@@ -65,6 +79,7 @@ class GPBackend:
         if int(y.shape[0]) != n:
             raise ValueError(f"mismatched number of data points for X and y: {n} != {int(y.shape[0])}")
         self.resident_key = self.factor_key = self.noise_override = None
+        self._order(X, y)
         _lib.check(self._lib.gpb_set_train(self._h, _lib.ptr(X), _lib.ptr(y), n, d, n_out), self._h, "set_train")
         self.n, self.d, self.n_out = n, d, n_out
 
@@ -110,6 +125,7 @@ class GPBackend:
             out_mean = np.empty((M, self.n_out))
         if want_var and out_var is None:
             out_var = np.empty(M)
+        self._order(Xc, out_mean, out_var)
         st = self._lib.gpb_predict(self._h, _lib.ptr(Xc), M, int(add_data_variance),
                                    _lib.ptr(out_mean) if want_mean else None, _lib.ptr(out_var) if want_var else None)
         _lib.check(st, self._h, "predict")
@@ -122,6 +138,7 @@ class GPBackend:
         self._check_out(out_cov, (M, M), "out_cov")
         mean = np.empty((M, self.n_out)) if want_mean else None
         cov = np.empty((M, M)) if out_cov is None else out_cov
+        self._order(Xc, cov)
         st = self._lib.gpb_predict_cov(self._h, _lib.ptr(Xc), M, int(bool(noise_on_diagonal)), _lib.ptr(mean), _lib.ptr(cov))
         _lib.check(st, self._h, "predict_cov")
         return mean, cov
@@ -135,6 +152,7 @@ class GPBackend:
         M = int(Xc.shape[0])
         pv = None if predictive_variance is None else np.ascontiguousarray(predictive_variance, dtype=np.float64).ravel()
         out = np.empty(M)
+        self._order(Xc)
         st = self._lib.gpb_marginal_variance(self._h, _lib.ptr(Xc), M, _lib.ptr(H), _lib.ptr(pv), _lib.ptr(out))
         _lib.check(st, self._h, "marginal_variance")
         return out
@@ -143,6 +161,7 @@ class GPBackend:
         v = _lib.as_f64(v)
         idx = ctypes.c_longlong()
         val = ctypes.c_double()
+        self._order(v)
         _lib.check(self._lib.gpb_argmax(self._h, _lib.ptr(v), int(v.shape[0]), ctypes.byref(idx), ctypes.byref(val)),
                    self._h, "argmax")
         return int(idx.value), float(val.value)
@@ -162,6 +181,7 @@ class GPBackend:
         if m == 0:
             return
         self.resident_key = self.factor_key = None
+        self._order(X_new, y_new)
         _lib.check(self._lib.gpb_append_train(self._h, _lib.ptr(X_new), _lib.ptr(y_new), m), self._h, "append_train")
         self.n += m
 
@@ -178,6 +198,7 @@ class GPBackend:
             out = np.empty((M, n_out))
         sin = None if stats_in is None else np.ascontiguousarray(stats_in, dtype=np.float64).reshape(n_out, 2)
         sout = np.empty((n_out, 2)) if return_stats else None
+        self._order(mean, out)
         st = self._lib.gpb_acq_prepare(self._h, int(kind), _lib.ptr(mean), M, n_out,
                                        _lib.ptr(params) if params.size else None, int(params.size), _lib.ptr(out),
                                        _lib.ptr(sin), _lib.ptr(sout))
@@ -190,6 +211,7 @@ class GPBackend:
         M = int(v.shape[0])
         ncol = 1 if v.ndim == 1 else int(v.shape[1])
         out = np.empty((ncol, 2))
+        self._order(v)
         _lib.check(self._lib.gpb_acq_stats(self._h, _lib.ptr(v), M, ncol, int(transform), _lib.ptr(out)), self._h, "acq_stats")
         return out
 
@@ -211,6 +233,7 @@ class GPBackend:
         idx = ctypes.c_longlong()
         val = ctypes.c_double()
         sin = None if stats is None else np.ascontiguousarray(stats, dtype=np.float64).ravel()[:2].copy()
+        self._order(var, term, extra, loss_out)
         st = self._lib.gpb_acquire(self._h, int(kind), _lib.ptr(None if term is None else _lib.as_f64(term)),
                                    _lib.ptr(var), _lib.ptr(None if extra is None else _lib.as_f64(extra)), M, int(n_out),
                                    _lib.ptr(params) if params.size else None, int(params.size), vis, len(visited),
@@ -235,6 +258,7 @@ class GPBackend:
             return (K0, dK0) if eval_gradient else K0
         K = np.empty((na, nb)) if out_K is None else out_K
         dK = (np.empty((na, nb, ell.size + 2)) if out_dK is None else out_dK) if eval_gradient else None
+        self._order(Xa, Xb, K, dK)
         st = self._lib.gpb_kernel_matrix(self._h, int(kind), _lib.ptr(Xa), na, _lib.ptr(Xb), nb, d, _lib.ptr(ell),
                                          ell.size, float(sigma_f), float(sigma_n), _lib.ptr(K), _lib.ptr(dK))
         _lib.check(st, self._h, "kernel_matrix")
@@ -310,6 +334,7 @@ class GPBackend:
         M, K = int(A.shape[0]), int(A.shape[1])
         N = int(B.shape[0])
         ms = ctypes.c_double()
+        self._order(A, B, C)
         _lib.check(self._lib.gpb_debug_gemm(self._h, _lib.ptr(A), _lib.ptr(B), _lib.ptr(C), M, N, K, int(cfg), float(alpha), float(beta),
                                             int(reps), ctypes.byref(ms)), self._h, "debug_gemm")
         return ms.value

@@ -117,6 +117,8 @@ struct gpb_handle_s {
   cudaStream_t stream3 = nullptr;   // low-priority stream of the early triangular inverse
   cudaStream_t stream4 = nullptr;   // second trailing-update stream (same priority as the main stream)
   cudaEvent_t ev_early = nullptr;   // recorded on stream3 after the last early phase
+  cudaStream_t caller = nullptr;    // gpb_set_stream: producer stream of the caller's device buffers (nullptr = legacy default)
+  cudaEvent_t ev_caller = nullptr;
   std::vector<cudaEvent_t> events;
   std::string err;
   EncodeTiledFn encode = nullptr;
@@ -177,6 +179,15 @@ int fail(H* h, int code, const std::string& msg) {
   } while (0)
 
 long long round_up(long long x, long long m) { return (x + m - 1) / m * m; }
+
+// Order the handle's stream after everything the caller has queued on its own stream so far (gpb_set_stream): device
+// buffers produced there are complete before any kernel of this call reads them.
+int order_after_caller(H* h) {
+  if (!h->caller) return 0;
+  CK(cudaEventRecord(h->ev_caller, h->caller));
+  CK(cudaStreamWaitEvent(h->stream, h->ev_caller, 0));
+  return 0;
+}
 
 bool is_device_ptr(const void* p) {
   cudaPointerAttributes a;
@@ -1231,7 +1242,8 @@ int gpb_create(int device, gpb_handle_t* out) {
         cudaStreamCreateWithPriority(&h->stream2, cudaStreamDefault, hi) != cudaSuccess ||
         cudaStreamCreateWithPriority(&h->stream3, cudaStreamNonBlocking, lo) != cudaSuccess ||
         cudaStreamCreateWithPriority(&h->stream4, cudaStreamNonBlocking, mid) != cudaSuccess ||
-        cudaEventCreateWithFlags(&h->ev_early, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&h->ev_early, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_caller, cudaEventDisableTiming) != cudaSuccess) {
       delete h;
       return -2;
     }
@@ -1308,8 +1320,15 @@ int gpb_destroy(gpb_handle_t h) {
   cudaStreamDestroy(h->stream3);
   cudaStreamDestroy(h->stream4);
   cudaEventDestroy(h->ev_early);
+  cudaEventDestroy(h->ev_caller);
   cudaStreamDestroy(h->stream);
   delete h;
+  return 0;
+}
+
+int gpb_set_stream(gpb_handle_t h, void* cuda_stream) {
+  if (!h) return -1;
+  h->caller = reinterpret_cast<cudaStream_t>(cuda_stream);
   return 0;
 }
 
@@ -1328,6 +1347,7 @@ int gpb_set_train(gpb_handle_t h, const double* X, const double* y, long long n,
   if (d > MAX_D) return fail(h, -1, "gpb_set_train: input dimension above 32 is not supported");
   if (n_out > 128) return fail(h, -1, "gpb_set_train: more than 128 outputs are not supported");
   CK(cudaSetDevice(h->device));
+  if (int rc_order = order_after_caller(h)) return rc_order;
   const long long oldNp = h->ws.Np;
   const int oldDP = h->DP;
   int rc = resize_ws(h, h->ws, n);
@@ -1359,6 +1379,7 @@ int gpb_nll(gpb_handle_t h, int kind, const double* theta, int n_ell, int want_g
   if (rc) return rc;
   if (!theta || !nll || (want_grad && !grad)) return fail(h, -1, "gpb_nll: null argument");
   CK(cudaSetDevice(h->device));
+  if (int rc_order = order_after_caller(h)) return rc_order;
   if ((rc = set_hyp(h, kind, theta, n_ell))) return rc;
   Workspace& w = h->ws;
   h->factor_ready = false;
@@ -1427,6 +1448,7 @@ int gpb_factorize(gpb_handle_t h, int kind, const double* theta, int n_ell) {
   if (rc) return rc;
   if (!theta) return fail(h, -1, "gpb_factorize: null argument");
   CK(cudaSetDevice(h->device));
+  if (int rc_order = order_after_caller(h)) return rc_order;
   if ((rc = set_hyp(h, kind, theta, n_ell))) return rc;
   Workspace& w = h->ws;
   h->factor_ready = false;
@@ -1454,6 +1476,7 @@ int gpb_predict(gpb_handle_t h, const double* Xc, long long M, int add_data_vari
   if (!Xc || M < 0) return fail(h, -1, "gpb_predict: bad argument");
   if (M == 0) return 0;
   CK(cudaSetDevice(h->device));
+  if (int rc_order = order_after_caller(h)) return rc_order;
   Workspace& w = h->ws;
   const int cfg = g_cfg_update;
   int bm, bn;
@@ -1556,6 +1579,7 @@ int gpb_predict_cov(gpb_handle_t h, const double* Xc, long long M, int noise_on_
   if (!Xc || !cov || M < 1) return fail(h, -1, "gpb_predict_cov: bad argument");
   if (M > 16384) return fail(h, -1, "gpb_predict_cov: at most 16384 test points (the covariance is M x M)");
   CK(cudaSetDevice(h->device));
+  if (int rc_order = order_after_caller(h)) return rc_order;
   Workspace& w = h->ws;
   const long long Np = w.Np, Mp = round_up(M, 128);
   const int D = h->D, cfg = cfg_for_blocks(g_cfg_update, (int)((Mp / 128) * w.Nb));
@@ -1647,6 +1671,7 @@ int gpb_kernel_matrix(gpb_handle_t h, int kind, const double* Xa, long long na, 
   if (!(n_ell == 1 || n_ell == d)) return fail(h, -1, "gpb_kernel_matrix: n_ell must be 1 or d");
   if (kind != GPB_KERNEL_RBF && kind != GPB_KERNEL_MATERN52) return fail(h, -1, "unknown kernel kind");
   CK(cudaSetDevice(h->device));
+  if (int rc_order = order_after_caller(h)) return rc_order;
   KernelHyp hy{};
   hy.kind = kind;
   hy.D = d;
@@ -1682,6 +1707,7 @@ int gpb_linear_embedding(gpb_handle_t h, const double* Xa, long long na, const d
   if (!h || !Xa || !Xb || !R || !K || na < 1 || nb < 1 || D < 1 || D > MAX_D || d < 1 || d > MAX_D)
     return fail(h, -1, "gpb_linear_embedding: bad argument");
   CK(cudaSetDevice(h->device));
+  if (int rc_order = order_after_caller(h)) return rc_order;
   const int P = d * D + 2;
   const size_t nK = (size_t)na * nb, ndK = dK ? nK * P : 0;
   int rc = ensure_cap(h, &h->dstage, &h->dstage_cap, (size_t)(na + nb) * D + (size_t)d * D);
@@ -1719,6 +1745,7 @@ int gpb_marginal_variance(gpb_handle_t h, const double* Xc, long long M, const d
   if (!Xc || !hess_inv || !out || M < 1) return fail(h, -1, "gpb_marginal_variance: bad argument");
   if (h->n_out != 1) return fail(h, -1, "gpb_marginal_variance: single-output models only");
   CK(cudaSetDevice(h->device));
+  if (int rc_order = order_after_caller(h)) return rc_order;
   Workspace& w = h->ws;
   const long long N = w.N, Np = w.Np;
   const int P = h->hyp.n_ell + 2, D = h->D;
@@ -1774,6 +1801,7 @@ int gpb_append_train(gpb_handle_t h, const double* Xnew, const double* ynew, lon
   if (!h->factor_ready) return fail(h, -3, "gpb_append_train: call gpb_factorize first");
   if (!Xnew || !ynew || m < 1) return fail(h, -1, "gpb_append_train: bad argument");
   CK(cudaSetDevice(h->device));
+  if (int rc_order = order_after_caller(h)) return rc_order;
   const int D = h->D, n_out = h->n_out;
   for (long long p = 0; p < m; ++p) {
     Workspace& w = h->ws;
@@ -1850,6 +1878,7 @@ int gpb_acq_stats(gpb_handle_t h, const double* v, long long M, int ncol, int tr
   if (!h || !v || !out || M < 1 || ncol < 1 || ncol > ACQ_MAX_OUT || (transform != 0 && transform != 1))
     return fail(h, -1, "gpb_acq_stats: bad argument");
   CK(cudaSetDevice(h->device));
+  if (int rc_order = order_after_caller(h)) return rc_order;
   const size_t tot = (size_t)M * ncol;
   const int nblk = acq_grid(M);
   int rc = ensure_cap(h, &h->dacq, &h->dacq_cap, tot + (size_t)2 * nblk * ncol + 2 * ACQ_MAX_OUT + 64);
@@ -1870,6 +1899,7 @@ int gpb_acq_prepare(gpb_handle_t h, int kind, const double* mean, long long M, i
   if (!h || !mean || !out || M < 1 || n_out < 1 || n_out > ACQ_MAX_OUT) return fail(h, -1, "gpb_acq_prepare: bad argument");
   if (kind != ACQ_WEIGHTED && kind != ACQ_EI) return fail(h, -1, "gpb_acq_prepare: kind has no prepare step");
   CK(cudaSetDevice(h->device));
+  if (int rc_order = order_after_caller(h)) return rc_order;
   AcqArgs a;
   int rc = 0;
   if (kind == ACQ_EI) {
@@ -1915,6 +1945,7 @@ int gpb_acquire(gpb_handle_t h, int kind, const double* term, const double* var,
   if (!h || !var || !idx || M < 1 || n_out < 1 || n_out > ACQ_MAX_OUT || n_visited < 0 || (n_visited > 0 && !visited))
     return fail(h, -1, "gpb_acquire: bad argument");
   CK(cudaSetDevice(h->device));
+  if (int rc_order = order_after_caller(h)) return rc_order;
   AcqArgs a;
   int rc = fill_acq_args(h, a, kind, M, n_out, params, n_params);
   if (rc) return rc;
@@ -1967,6 +1998,7 @@ int gpb_acquire(gpb_handle_t h, int kind, const double* term, const double* var,
 int gpb_mean_pairwise_distance(gpb_handle_t h, const double* X, long long n, int d, double* out) {
   if (!h || !X || !out || n < 1 || d < 1 || d > MAX_D) return fail(h, -1, "gpb_mean_pairwise_distance: bad argument");
   CK(cudaSetDevice(h->device));
+  if (int rc_order = order_after_caller(h)) return rc_order;
   const long long nblk = (n + 63) / 64;
   int rc = ensure_cap(h, &h->dstage, &h->dstage_cap, (size_t)n * d + (size_t)nblk + 8);
   if (rc) return rc;
@@ -1987,6 +2019,7 @@ int gpb_mean_pairwise_distance(gpb_handle_t h, const double* X, long long n, int
 int gpb_cholesky(gpb_handle_t h, const double* A, long long n, double* L) {
   if (!h || !A || !L || n < 1) return fail(h, -1, "gpb_cholesky: bad argument");
   CK(cudaSetDevice(h->device));
+  if (int rc_order = order_after_caller(h)) return rc_order;
   Workspace& w = h->tmp;
   int rc = resize_ws(h, w, n);
   if (rc) return rc;
@@ -2006,6 +2039,7 @@ int gpb_cholesky(gpb_handle_t h, const double* A, long long n, double* L) {
 int gpb_invert_cholesky(gpb_handle_t h, const double* L, long long n, double* Kinv) {
   if (!h || !L || !Kinv || n < 1) return fail(h, -1, "gpb_invert_cholesky: bad argument");
   CK(cudaSetDevice(h->device));
+  if (int rc_order = order_after_caller(h)) return rc_order;
   Workspace& w = h->tmp;
   int rc = resize_ws(h, w, n);
   if (rc) return rc;
@@ -2026,6 +2060,7 @@ int gpb_invert_cholesky(gpb_handle_t h, const double* L, long long n, double* Ki
 int gpb_solve_cholesky(gpb_handle_t h, const double* L, long long n, const double* b, int nrhs, double* x) {
   if (!h || !L || !b || !x || n < 1 || nrhs < 1 || nrhs > 128) return fail(h, -1, "gpb_solve_cholesky: bad argument");
   CK(cudaSetDevice(h->device));
+  if (int rc_order = order_after_caller(h)) return rc_order;
   Workspace& w = h->tmp;
   int rc = resize_ws(h, w, n);
   if (rc) return rc;
@@ -2095,6 +2130,7 @@ int gpb_debug_gemm(gpb_handle_t h, const double* A, const double* B, double* C, 
   if (!h || !A || !B || !C || M % 128 || N % 128 || K % 128 || cfg < 0 || cfg >= NUM_CFG || reps < 1)
     return fail(h, -1, "gpb_debug_gemm: bad argument");
   CK(cudaSetDevice(h->device));
+  if (int rc_order = order_after_caller(h)) return rc_order;
   Workspace& w = h->tmp;
   set_mat(w, M_DBG_A, const_cast<double*>(A), M, K, K);
   set_mat(w, M_DBG_B, const_cast<double*>(B), N, K, K);
@@ -2131,6 +2167,7 @@ int gpb_debug_gemm(gpb_handle_t h, const double* A, const double* B, double* C, 
 int gpb_debug_diag(gpb_handle_t h, const double* A, double* L, double* W, double* logdet, int mode, int reps, double* ms) {
   if (!h || !A || !L || !W || reps < 1 || mode < 0 || mode > 2) return fail(h, -1, "gpb_debug_diag: bad argument");
   CK(cudaSetDevice(h->device));
+  if (int rc_order = order_after_caller(h)) return rc_order;
   int rc = ensure_cap(h, &h->dstage, &h->dstage_cap, (size_t)3 * 128 * 128 + 8);
   if (rc) return rc;
   double* dA = h->dstage;
@@ -2172,6 +2209,7 @@ int gpb_debug_diag(gpb_handle_t h, const double* A, double* L, double* W, double
 int gpb_debug_trace(gpb_handle_t h, unsigned long long* buf, unsigned int cap, unsigned int* count) {
   if (!h) return -1;
   CK(cudaSetDevice(h->device));
+  if (int rc_order = order_after_caller(h)) return rc_order;
   CK(cudaDeviceSynchronize());
   if (count) CK(cudaMemcpyFromSymbol(count, g_trace_count, sizeof(unsigned int)));
   unsigned int zero = 0;

@@ -860,3 +860,41 @@ def test_reference_fit_manual_and_optim_twins(backend, golden):
     start = np.log10(np.array([0.3, 0.8, 2.0, 1e-2]))
     res = minimize(cost, start, method="L-BFGS-B", jac=True, bounds=((-2, 2), (-2, 2), (-2, 2), (-4, 0)))
     assert res.fun < cost(start)[0] - 10.0 and np.all(np.isfinite(res.x))
+
+
+def test_candidates_produced_on_a_non_default_torch_stream(backend):
+    """Stream semantics of include/gpb.h: a caller that produces its device buffers on a non-default torch stream needs no
+    manual synchronisation -- GPBackend names torch's current stream (gpb_set_stream) and the library orders its own
+    stream behind it.  The producer is made slow on purpose (a long matmul chain ahead of the final write)."""
+    import torch
+
+    N, D, M = 700, 6, 4096
+    X, y = oracle.synthetic_problem(N, D)
+    theta = np.concatenate([np.linspace(0.6, 1.2, D), [1.5, 0.3]])
+    backend.set_train(X, y)
+    backend.factorize(1, theta)
+    Xc_host = np.random.default_rng(5).random((M, D))
+    ref_m, ref_v = backend.predict(Xc_host)
+    dev = torch.device("cuda", backend.device)
+    src = torch.from_numpy(Xc_host).to(dev)
+    big = torch.randn(4096, 4096, device=dev)
+    side = torch.cuda.Stream(device=dev)
+    torch.cuda.synchronize()
+    for _ in range(3):
+        Xc = torch.zeros(M, D, dtype=torch.float64, device=dev)     # wrong values until the producer has run
+        out_m = torch.empty(M, 1, dtype=torch.float64, device=dev)
+        out_v = torch.empty(M, dtype=torch.float64, device=dev)
+        torch.cuda.synchronize()
+        with torch.cuda.stream(side):
+            acc = big
+            for _ in range(20):                                     # ~tens of ms of work queued ahead of the copy
+                acc = acc @ big * 1e-2
+            Xc.copy_(src + 0.0 * acc[0, 0].double())
+            backend.predict(Xc, out_mean=out_m, out_var=out_v)      # no synchronisation in between
+        assert np.array_equal(out_m.cpu().numpy(), ref_m) and np.array_equal(out_v.cpu().numpy(), ref_v)
+    assert backend._caller_stream == int(side.cuda_stream)
+    # back on the default stream the handle follows
+    Xd = torch.from_numpy(Xc_host).to(dev)
+    m2, v2 = backend.predict(Xd)
+    assert backend._caller_stream == int(torch.cuda.current_stream(dev).cuda_stream)
+    assert np.array_equal(m2, ref_m)
