@@ -199,6 +199,8 @@ class DeviceAcquisitionFunction(_RefBase):
             visited.append(idx)                      # mask[idx] = 0
             candidates[n] = Xp[idx]
             mu_candidate, _ = self.surrogate.predict(candidates[n].reshape(1, -1))
+            # B200GPSurrogate extends the device-resident factor and training set in place (O(N^2)), so the optimize()
+            # that follows finds the data resident and uploads nothing (gp_functions.optimize, resident_key)
             self.surrogate.add_training_data(candidates[n].reshape(1, -1), mu_candidate)
             self.surrogate.optimize()
         return candidates

@@ -240,11 +240,13 @@ grad_contract_kernel(const double* __restrict__ Xs, const double* __restrict__ X
 #pragma unroll
   for (int p = 0; p < DP + 2; ++p) acc[p] = 0.0;
   __shared__ double xi[AS_TM][DP];
+  __shared__ double ar[AS_TM];                       // alpha of the tile rows (single-output fast path)
   __shared__ double red[AS_THREADS / 32][DP + 2];
   const bool active = !(col0 > row0 + AS_TM - 1) && row0 < n && col0 < n;
   if (active) {
     for (int e = threadIdx.x; e < AS_TM * DP; e += AS_THREADS)
       xi[e / DP][e % DP] = Xs[(long long)(row0 + e / DP) * DP + e % DP];
+    if (threadIdx.x < AS_TM) ar[threadIdx.x] = alpha[row0 + threadIdx.x];
     // thread owns ONE column (128 column lanes) and every second row of the tile: half the registers of a
     // two-column layout, two CTAs per SM
     const int cl = threadIdx.x & 127, rg = threadIdx.x >> 7;
@@ -252,31 +254,48 @@ grad_contract_kernel(const double* __restrict__ Xs, const double* __restrict__ X
     double xj[DP];
 #pragma unroll
     for (int d = 0; d < DP; ++d) xj[d] = XsT[(long long)d * ldt + c];
+    const double ac = alpha[c];
     __syncthreads();
     if (c < n) {
-      for (int rr = rg; rr < AS_TM; rr += 2) {
-        const int r = row0 + rr;
-        if (r >= n || c > r) continue;
-        const double kin = Kinv[(long long)r * ldk + c];
-        double aa = 0.0;
-        for (int o = 0; o < n_out; ++o) aa = fma(alpha[(long long)o * lda + r], alpha[(long long)o * lda + c], aa);
-        double w = n_out * kin - aa;
-        w = (c == r) ? w : 2.0 * w;
-        double u2[DP];
-        double d2 = 0.0;
+      // Rows in batches of GB: the K^-1 entries of a batch are all requested before the first one is used, so the
+      // FP64 work of one row covers the memory latency of the next ones.
+      constexpr int GB = 8;
+      for (int rb = rg; rb < AS_TM; rb += 2 * GB) {
+        double kin[GB];
 #pragma unroll
-        for (int d = 0; d < DP; ++d) {
-          const double v = xi[rr][d] - xj[d];
-          u2[d] = v * v;
-          d2 += u2[d];
+        for (int q = 0; q < GB; ++q) {
+          const int r = row0 + rb + 2 * q;
+          kin[q] = (r < n && c <= r) ? Kinv[(long long)r * ldk + c] : 0.0;
         }
-        double k0, g0;
-        kern_eval<KIND>(d2, sf2, k0, g0);
-        const double wg = w * g0;
 #pragma unroll
-        for (int d = 0; d < DP; ++d) acc[d] = fma(wg, u2[d], acc[d]);
-        acc[DP] = fma(w, k0, acc[DP]);
-        if (c == r) acc[DP + 1] += w;
+        for (int q = 0; q < GB; ++q) {
+          const int rr = rb + 2 * q, r = row0 + rr;
+          if (r >= n || c > r) continue;
+          double aa;
+          if (n_out == 1) {
+            aa = ar[rr] * ac;
+          } else {
+            aa = 0.0;
+            for (int o = 0; o < n_out; ++o) aa = fma(alpha[(long long)o * lda + r], alpha[(long long)o * lda + c], aa);
+          }
+          double w = n_out * kin[q] - aa;
+          w = (c == r) ? w : 2.0 * w;
+          double u2[DP];
+          double d2 = 0.0;
+#pragma unroll
+          for (int d = 0; d < DP; ++d) {
+            const double v = xi[rr][d] - xj[d];
+            u2[d] = v * v;
+            d2 += u2[d];
+          }
+          double k0, g0;
+          kern_eval<KIND>(d2, sf2, k0, g0);
+          const double wg = w * g0;
+#pragma unroll
+          for (int d = 0; d < DP; ++d) acc[d] = fma(wg, u2[d], acc[d]);
+          acc[DP] = fma(w, k0, acc[DP]);
+          if (c == r) acc[DP + 1] += w;
+        }
       }
     }
   }

@@ -332,6 +332,7 @@ int g_early_mask = 0xF;         // which of the cut points {1/4, 1/2, 3/4, 7/8} 
 
 // Small launches are latency-bound (one CTA takes ~15 us for a 128x64x128 tile on its own SM): cut the tiles finer
 // so the same work spreads over more SMs.  `coarse` is the configuration used for large launches.
+int g_super = 12;                // super-tile edge in 128-blocks, ~sqrt(148) (env GPB_SUPER; 0 = row-major task order)
 int g_fine_below = 148;          // launches with fewer 128-blocks than this use the fine tiles (env GPB_FINE_BELOW)
 int cfg_for_blocks(int coarse, int nblocks) {
   if (nblocks >= g_fine_below) return coarse;
@@ -341,9 +342,16 @@ int cfg_for_blocks(int coarse, int nblocks) {
 struct TaskSink {
   Plan& p;
   size_t begin;
+  std::vector<int> keys;   // optional sort key per task (finish(..., sort_heavy) orders by key, else by nk)
+  int key = -1;            // key given to the tasks emitted next (-1: none)
   explicit TaskSink(Plan& pl) : p(pl), begin(pl.tasks.size()) {}
   // emit the tile(s) covering the 128x128 block (c_row, c_col) for the given config
   void block(int cfg, int a_row, int a_k, int b_row, int b_k, int nk, int c_row, int c_col, int aux = 0) {
+    const size_t before = p.tasks.size();
+    block_(cfg, a_row, a_k, b_row, b_k, nk, c_row, c_col, aux);
+    if (key >= 0) keys.resize(keys.size() + (p.tasks.size() - before), key);
+  }
+  void block_(int cfg, int a_row, int a_k, int b_row, int b_k, int nk, int c_row, int c_col, int aux) {
     if (cfg == CFG_128x128) {
       p.tasks.push_back({a_row, a_k, b_row, b_k, nk, c_row, c_col, aux});
     } else if (cfg == CFG_128x64) {
@@ -363,9 +371,18 @@ struct TaskSink {
   void finish(int cfg, int epi, int matA, int matB, int matC, int matCt, double alpha, double beta, bool sort_heavy) {
     const int n = (int)(p.tasks.size() - begin);
     if (n == 0) return;
-    if (sort_heavy)
+    if (sort_heavy && (int)keys.size() == n) {
+      // stable sort by group key (descending): super-tiles stay contiguous, heavy groups first
+      std::vector<int> order(n);
+      for (int t = 0; t < n; ++t) order[t] = t;
+      std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return keys[a] > keys[b]; });
+      std::vector<GemmTask> sorted(n);
+      for (int t = 0; t < n; ++t) sorted[t] = p.tasks[begin + order[t]];
+      std::copy(sorted.begin(), sorted.end(), p.tasks.begin() + begin);
+    } else if (sort_heavy) {
       std::stable_sort(p.tasks.begin() + begin, p.tasks.end(),
                        [](const GemmTask& a, const GemmTask& b) { return a.nk > b.nk; });
+    }
     p.launches.push_back({1, 0, cfg, matA, matB, matC, matCt, alpha, beta, begin, n, epi});
     last = (int)p.launches.size() - 1;
   }
@@ -528,22 +545,33 @@ void emit_trtri_nodes(Plan& p, const std::vector<Node>& nodes, int top, int cfg,
       if (nd.height == hgt && pick(nd)) nblk += (nd.mid - nd.a) * (nd.b - nd.mid);
     if (nblk == 0) continue;
     const int hc = force_cfg >= 0 ? force_cfg : cfg_for_blocks(cfg, nblk);
+    // Tiles of a node are emitted super-tile by super-tile (see build_syrk_plan) and the launch is ordered by the
+    // heaviest tile of each super-tile, so that resident CTAs share operand panels and heavy groups still go first.
+    const int S = g_super > 0 ? g_super : (1 << 20);
     {  // T = U11 L21^T  -> scratch in the strict upper triangle of Lbuf
       TaskSink s(p);
       for (const Node& nd : nodes)
         if (nd.height == hgt && pick(nd))
-          for (int m = nd.a; m < nd.mid; ++m)
-            for (int n = nd.mid; n < nd.b; ++n)
-              s.block(hc, m * 128, m * 128, n * 128, m * 128, 8 * (nd.mid - m), m * 128, n * 128);
+          for (int M0 = nd.a; M0 < nd.mid; M0 += S)
+            for (int N0 = nd.mid; N0 < nd.b; N0 += S) {
+              s.key = g_super > 0 ? 8 * (nd.mid - M0) : -1;
+              for (int m = M0; m < std::min(nd.mid, M0 + S); ++m)
+                for (int n = N0; n < std::min(nd.b, N0 + S); ++n)
+                  s.block(hc, m * 128, m * 128, n * 128, m * 128, 8 * (nd.mid - m), m * 128, n * 128);
+            }
       s.finish(hc, EPI_STORE, M_U, M_L, M_L, M_NONE, 1.0, 0.0, true);
     }
     {  // U12 = -T W22^T, mirrored into W21
       TaskSink s(p);
       for (const Node& nd : nodes)
         if (nd.height == hgt && pick(nd))
-          for (int m = nd.a; m < nd.mid; ++m)
-            for (int n = nd.mid; n < nd.b; ++n)
-              s.block(hc, m * 128, nd.mid * 128, n * 128, nd.mid * 128, 8 * (n - nd.mid + 1), m * 128, n * 128);
+          for (int M0 = nd.a; M0 < nd.mid; M0 += S)
+            for (int N0 = nd.mid; N0 < nd.b; N0 += S) {
+              s.key = g_super > 0 ? 8 * (std::min(nd.b, N0 + S) - nd.mid) : -1;
+              for (int m = M0; m < std::min(nd.mid, M0 + S); ++m)
+                for (int n = N0; n < std::min(nd.b, N0 + S); ++n)
+                  s.block(hc, m * 128, nd.mid * 128, n * 128, nd.mid * 128, 8 * (n - nd.mid + 1), m * 128, n * 128);
+            }
       s.finish(hc, EPI_STORE, M_L, M_W, M_U, M_W, -1.0, 0.0, true);
     }
   }
@@ -567,14 +595,28 @@ void build_trtri_plan(Workspace& w) {
   emit_trtri_nodes(w.trtri_late, nodes, top, cfg, [&](const Node& nd) { return phase_of(nd) == w.n_phase; });
 }
 
+// Super-tile rasterisation (L2 reuse).  A tile (i, j) of an NT product streams the row panels i and j of its operands
+// through the k range; CTAs are dispatched in task order, so the ~296 resident CTAs of a launch should form a compact
+// g_super x g_super block of tiles: they then share 2 g_super row panels instead of reading one or two each, and
+// because they walk k in step the shared slabs are still in L2 when the next CTA asks for them.
 void build_syrk_plan(Workspace& w) {
   Plan& p = w.syrk;
   p.clear();
   const int Nb = (int)w.Nb, cfg = cfg_for_blocks(g_cfg_update, (int)(w.Nb * (w.Nb + 1) / 2));
   TaskSink s(p);
-  for (int i = 0; i < Nb; ++i)
-    for (int j = 0; j <= i; ++j) s.block(cfg, i * 128, i * 128, j * 128, i * 128, 8 * (Nb - i), i * 128, j * 128);
-  s.finish(cfg, EPI_STORE, M_U, M_U, M_L, M_NONE, 1.0, 0.0, true);
+  auto tile = [&](int i, int j) { s.block(cfg, i * 128, i * 128, j * 128, i * 128, 8 * (Nb - i), i * 128, j * 128); };
+  if (g_super <= 0) {
+    for (int i = 0; i < Nb; ++i)
+      for (int j = 0; j <= i; ++j) tile(i, j);
+    s.finish(cfg, EPI_STORE, M_U, M_U, M_L, M_NONE, 1.0, 0.0, true);
+    return;
+  }
+  // rows ascending = longest k first; the super-tiles of one block row run left to right
+  for (int I = 0; I < Nb; I += g_super)
+    for (int J = 0; J <= I; J += g_super)
+      for (int i = I; i < std::min(Nb, I + g_super); ++i)
+        for (int j = J; j < std::min(J + g_super, i + 1); ++j) tile(i, j);
+  s.finish(cfg, EPI_STORE, M_U, M_U, M_L, M_NONE, 1.0, 0.0, false);
 }
 
 int upload_plan(H* h, Plan& p) {
@@ -1280,6 +1322,7 @@ int gpb_create(int device, gpb_handle_t* out) {
   if (const char* e = getenv("GPB_FINE_BELOW")) g_fine_below = atoi(e);
   if (const char* e = getenv("GPB_PDL")) g_pdl = atoi(e) != 0;
   if (const char* e = getenv("GPB_TAIL_BLOCKS")) g_tail_blocks = std::max(0, atoi(e));
+  if (const char* e = getenv("GPB_SUPER")) g_super = std::max(0, std::min(64, atoi(e)));
   if (const char* e = getenv("GPB_DIAG4")) g_diag4 = std::max(0, std::min(2, atoi(e)));
   *out = h;
   return 0;

@@ -41,7 +41,13 @@ def _all_gather_rows(row):
         return row[None, :]
     import torch
 
-    dev = torch.device("cuda", torch.cuda.current_device()) if d.get_backend() == "nccl" else torch.device("cpu")
+    if d.get_backend() == "nccl":
+        # the rank's own GPU (the one GPBackend picks: LOCAL_RANK under torchrun), whatever torch's current device is
+        from .backend import _default_device
+
+        dev = torch.device("cuda", _default_device())
+    else:
+        dev = torch.device("cpu")
     mine = torch.from_numpy(row.copy()).to(dev)
     out = [torch.empty_like(mine) for _ in range(d.get_world_size())]
     d.all_gather(out, mine)
@@ -146,6 +152,8 @@ def multistart_optimize(xtrain, ytrain, starts, kernel, fixed_sigma_n=False, eva
 
     rank, ws = world()
     starts = np.atleast_2d(np.asarray(starts, dtype=np.float64))
+    if starts.size == 0:
+        raise ValueError("multistart_optimize needs at least one start point")
     mine = list(range(rank, starts.shape[0], ws))
     streams = max(1, min(int(streams), len(mine) or 1))
     first = backend or shared_backend()

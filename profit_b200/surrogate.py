@@ -269,16 +269,18 @@ class B200GPSurrogate(_GPBase):
                 be.noise_override = float(theta[-1] ** 2)     # sigma_n^2 to report for this (jittered) factor
             be.factor_key = key
 
-    def add_training_data(self, X, y):
+    def add_training_data(self, X, y, extend_factor=True):
         """custom_surrogate.py:122-134: append rows; hyper-parameters are not re-optimised here.
 
         The reference leaves "Update Ky" as a TODO (:132) and refactorises on the next predict.  Here, when the
-        device holds the factor of exactly this model, the factor is extended in place (O(N^2) per row)."""
+        device holds the factor of exactly this model, the factor is extended in place (O(N^2) per row) -- unless the
+        caller says ``extend_factor=False`` because a re-optimisation follows at once (the acquisition loop,
+        aquisition_functions.py:70-72), which would discard the extended factor anyway."""
         X = np.asarray(X, dtype=np.float64)
         y = np.asarray(y, dtype=np.float64)
         be = self._backend
         extend = False
-        if be is not None and self.trained and be.resident_key is not None and callable(self.kernel):
+        if extend_factor and be is not None and self.trained and be.resident_key is not None and callable(self.kernel):
             old_key = self._data_key(self.Xtrain, self.ytrain)
             extend = old_key == be.resident_key and be.factor_key == self._factor_key(old_key)
         self.Xtrain = np.concatenate([self.Xtrain, X], axis=0)
@@ -321,7 +323,8 @@ class B200GPSurrogate(_GPBase):
         self.kernel = self.select_kernel(self.kernel)
         fixed = bool(self.fixed_sigma_n or fixed_sigma_n)
         opt = _gpf.optimize(self.Xtrain, self.ytrain, a0, self.kernel, fixed_sigma_n=fixed,
-                            eval_gradient=eval_gradient, return_hess_inv=return_hess_inv, backend=self.backend)
+                            eval_gradient=eval_gradient, return_hess_inv=return_hess_inv, backend=self.backend,
+                            resident_key=self._data_key(self.Xtrain, self.ytrain))
         if return_hess_inv:
             self.hess_inv = opt[1]
             opt = opt[0]
