@@ -194,8 +194,9 @@ int gpb_debug_gemm(gpb_handle_t h, const double* A, const double* B, double* C, 
                    int cfg, double alpha, double beta, int reps, double* ms);
 
 /* Test/benchmark hook for the serial stage of the Cholesky (np.linalg.cholesky, gp_functions.py:143): factor ONE
- * 128x128 SPD block A (row-major, host or device) with the diagonal-block kernel `mode` (2 = blocked DMMA kernel,
- * 1 = rank-4 register sweep, 0 = rank-1 register sweep; the same numbering as the GPB_DIAG4 switch), `reps` times.
+ * 128x128 SPD block A (row-major, host or device) with the diagonal-block kernel `mode` (3 = blocked DMMA kernel as it
+ * runs on the panel chain: factor + 32x32 diagonal inverses, completed by complete_inverse_kernel after the timing;
+ * 2 = blocked DMMA kernel with the full inverse; 1 = rank-4 register sweep, 0 = rank-1 register sweep), `reps` times.
  * L <- lower factor, W <- L^-1 (both 128x128 row-major, strict upper zero), *logdet <- sum_j log L_jj,
  * *ms <- mean device time of one factorisation.  Returns the LAPACK-style info like gpb_nll. */
 int gpb_debug_diag(gpb_handle_t h, const double* A, double* L, double* W, double* logdet, int mode, int reps, double* ms);

@@ -341,7 +341,7 @@ class GPBackend:
 
 
     def debug_diag(self, A, mode=2, reps=1):
-        """Factor one 128x128 SPD block with the diagonal-block kernel `mode` -> (L, L^-1, sum log L_jj, ms)."""
+        """Factor one 128x128 SPD block with the diagonal-block kernel `mode` (include/gpb.h) -> (L, L^-1, sum log L_jj, ms)."""
         A = _lib.as_f64(A)
         if tuple(A.shape) != (128, 128):
             raise ValueError("A should have shape (128, 128)")

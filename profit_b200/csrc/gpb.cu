@@ -38,6 +38,7 @@
 #include "dgemm_tasks.cuh"
 #include "potrf_diag.cuh"
 #include "potrf_diagr.cuh"
+#include "trsm_panel.cuh"
 
 using namespace gpb;
 
@@ -59,6 +60,7 @@ struct Launch {
   int wait_ev2 = -1; // optional second event
   int rec_ev = -1;   // event recorded after the launch
   int pdl = 0;       // launch with programmatic stream serialization (overlaps the launch with the previous kernel)
+  int trsm = 0;      // diag block: factor-only variant (32x32 diagonal inverses);  panel solve: blocked triangular solve
 };
 
 struct Plan {
@@ -106,6 +108,7 @@ struct Workspace {
   int phase_ev[MAX_PHASE] = {};  // potrf-plan event after which L[0:cut, 0:cut] is final
   Plan trtri_late;               // the remaining nodes
   std::map<std::pair<int, int>, CUtensorMap> maps;
+  int dinv_partial_from = 1 << 30;   // first diagonal block of which Dinv only holds the 32x32 diagonal blocks of the inverse
 };
 
 }  // namespace
@@ -322,6 +325,13 @@ int g_cfg_update = CFG_128x64;  // trailing updates / trtri / syrk / predict   (
 int g_outer_blocks = 0;         // outer panel width of the Cholesky in 128-blocks; 0 = by size (env GPB_OUTER_BLOCKS)
 int g_diag4 = 2;                // diagonal-block kernel: 2 = blocked DMMA kernel (potrf_diagr.cuh), 1 = rank-4 register
                                 // sweep, 0 = rank-1 register sweep (env GPB_DIAG4)
+int g_trsm = 1;                 // panel solve as a blocked triangular solve; the diagonal-block kernel then skips the 128x128
+                                // inverse, which complete_inverse_kernel supplies off the chain (env GPB_TRSM; needs GPB_DIAG4=2)
+int g_trsm_below = 40;          // ... for the block columns with at most this many block rows left (env GPB_TRSM_BELOW): while the
+                                // panel is taller the chain is hidden behind the trailing update and the 64-row GEMM solve with
+                                // the full inverse has the better throughput (N=16384: 130.8 vs 131.2 ms per evaluation)
+int g_early_min_blocks = 16;    // smallest matrix (in 128-blocks) whose triangular inverse starts during the Cholesky (env GPB_EARLY_MIN_BLOCKS)
+int g_super_min_blocks = 48;    // smallest matrix for the super-tile order of K^-1 = U U^T (below, the plain order is 5 % faster)
 int g_pdl = 1;                  // programmatic dependent launch along the panel chain (env GPB_PDL)
 int g_tail_blocks = 32;         // the last this-many block columns use single-block panels (env GPB_TAIL_BLOCKS)
 int g_lookahead = 1;            // overlap the next panel factorisation with the trailing update (env GPB_LOOKAHEAD)
@@ -332,7 +342,9 @@ int g_early_mask = 0xF;         // which of the cut points {1/4, 1/2, 3/4, 7/8} 
 
 // Small launches are latency-bound (one CTA takes ~15 us for a 128x64x128 tile on its own SM): cut the tiles finer
 // so the same work spreads over more SMs.  `coarse` is the configuration used for large launches.
-int g_super = 12;                // super-tile edge in 128-blocks, ~sqrt(148) (env GPB_SUPER; 0 = row-major task order)
+int g_super = 12;                // super-tile edge of the K^-1 = U U^T launch in 128-blocks, ~sqrt(148) (env GPB_SUPER; 0 = off)
+int g_super_trtri = 0;           // the same for the triangular-inverse launches (env GPB_SUPER_TRTRI): measured +7 % time at
+                                 // N=16384 (the heaviest-first order matters more there than the L2 hit rate), so off
 int g_fine_below = 148;          // launches with fewer 128-blocks than this use the fine tiles (env GPB_FINE_BELOW)
 int cfg_for_blocks(int coarse, int nblocks) {
   if (nblocks >= g_fine_below) return coarse;
@@ -424,7 +436,7 @@ void build_potrf_plan(Workspace& w) {
   // Cut points of the early triangular inverse: L[0:c, 0:c] is final once the panel that contains block column
   // c - 1 has been factored and solved (event evP of that panel).
   w.n_phase = 0;
-  if (la && g_early_trtri && Nb >= 48) {   // below ~6k rows the whole factorisation is chain-bound: nothing to gain
+  if (la && g_early_trtri && Nb >= g_early_min_blocks) {   // below ~6k rows the whole factorisation is chain-bound: nothing to gain
     const int cuts[Workspace::MAX_PHASE] = {Nb / 4, Nb / 2, 3 * Nb / 4, 7 * Nb / 8};
     for (int ci = 0; ci < Workspace::MAX_PHASE; ++ci) {
       if (!((g_early_mask >> ci) & 1)) continue;
@@ -443,18 +455,21 @@ void build_potrf_plan(Workspace& w) {
   auto emit_panel = [&](int J) {
     const int J0 = pb[J], Je = pb[J + 1];
     for (int k = J0; k < Je; ++k) {
+      const bool trsm = g_trsm && g_diag4 == 2 && (Nb - k) <= g_trsm_below;
       Launch dg{0, k, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
       dg.stream = ps;
       dg.pdl = pdl;
+      dg.trsm = trsm;
       p.launches.push_back(dg);
       {  // panel solve: L_ik = A_ik W_kk^T, in place (64-row tiles own all the columns they read)
         TaskSink s(p);
-        const int tc = cfg_for_blocks(CFG_64x128, aug - k);
+        const int tc = trsm ? CFG_32x128 : cfg_for_blocks(CFG_64x128, aug - k);
         for (int i = k + 1; i <= aug; ++i) s.block(tc, i * 128, k * 128, k * 128, 0, 8, i * 128, k * 128);
         s.finish(tc, EPI_STORE, M_L, M_DINV, M_L, M_NONE, 1.0, 0.0, false);
         if (s.last >= 0) {
           p.launches[s.last].stream = ps;
           p.launches[s.last].pdl = pdl;
+          p.launches[s.last].trsm = trsm;
         }
       }
       {  // update the remaining columns of the current outer panel with block column k
@@ -547,14 +562,14 @@ void emit_trtri_nodes(Plan& p, const std::vector<Node>& nodes, int top, int cfg,
     const int hc = force_cfg >= 0 ? force_cfg : cfg_for_blocks(cfg, nblk);
     // Tiles of a node are emitted super-tile by super-tile (see build_syrk_plan) and the launch is ordered by the
     // heaviest tile of each super-tile, so that resident CTAs share operand panels and heavy groups still go first.
-    const int S = g_super > 0 ? g_super : (1 << 20);
+    const int S = g_super_trtri > 0 ? g_super_trtri : (1 << 20);
     {  // T = U11 L21^T  -> scratch in the strict upper triangle of Lbuf
       TaskSink s(p);
       for (const Node& nd : nodes)
         if (nd.height == hgt && pick(nd))
           for (int M0 = nd.a; M0 < nd.mid; M0 += S)
             for (int N0 = nd.mid; N0 < nd.b; N0 += S) {
-              s.key = g_super > 0 ? 8 * (nd.mid - M0) : -1;
+              s.key = g_super_trtri > 0 ? 8 * (nd.mid - M0) : -1;
               for (int m = M0; m < std::min(nd.mid, M0 + S); ++m)
                 for (int n = N0; n < std::min(nd.b, N0 + S); ++n)
                   s.block(hc, m * 128, m * 128, n * 128, m * 128, 8 * (nd.mid - m), m * 128, n * 128);
@@ -567,7 +582,7 @@ void emit_trtri_nodes(Plan& p, const std::vector<Node>& nodes, int top, int cfg,
         if (nd.height == hgt && pick(nd))
           for (int M0 = nd.a; M0 < nd.mid; M0 += S)
             for (int N0 = nd.mid; N0 < nd.b; N0 += S) {
-              s.key = g_super > 0 ? 8 * (std::min(nd.b, N0 + S) - nd.mid) : -1;
+              s.key = g_super_trtri > 0 ? 8 * (std::min(nd.b, N0 + S) - nd.mid) : -1;
               for (int m = M0; m < std::min(nd.mid, M0 + S); ++m)
                 for (int n = N0; n < std::min(nd.b, N0 + S); ++n)
                   s.block(hc, m * 128, nd.mid * 128, n * 128, nd.mid * 128, 8 * (n - nd.mid + 1), m * 128, n * 128);
@@ -605,7 +620,7 @@ void build_syrk_plan(Workspace& w) {
   const int Nb = (int)w.Nb, cfg = cfg_for_blocks(g_cfg_update, (int)(w.Nb * (w.Nb + 1) / 2));
   TaskSink s(p);
   auto tile = [&](int i, int j) { s.block(cfg, i * 128, i * 128, j * 128, i * 128, 8 * (Nb - i), i * 128, j * 128); };
-  if (g_super <= 0) {
+  if (g_super <= 0 || Nb < g_super_min_blocks) {
     for (int i = 0; i < Nb; ++i)
       for (int j = 0; j <= i; ++j) tile(i, j);
     s.finish(cfg, EPI_STORE, M_U, M_U, M_L, M_NONE, 1.0, 0.0, true);
@@ -633,6 +648,7 @@ int upload_plan(H* h, Plan& p) {
 
 int run_plan(H* h, Workspace& w, Plan& p, bool factor_diag, cudaStream_t only_stream = nullptr) {
   const bool multi = p.num_events > 0 && !only_stream;
+  if (factor_diag) w.dinv_partial_from = 1 << 30;   // set again below by the factor-only diagonal blocks of this plan
   if (multi) {
     while ((int)h->events.size() < p.num_events + 3) {
       cudaEvent_t e;
@@ -663,8 +679,13 @@ int run_plan(H* h, Workspace& w, Plan& p, bool factor_diag, cudaStream_t only_st
         if (g_diag4 == 2) {
           lc.blockDim = dim3(DR_THREADS);
           lc.dynamicSmemBytes = DR_SMEM;
-          CK(cudaLaunchKernelEx(&lc, potrf_diagr_kernel, w.Lbuf, (long long)w.Np, L.k * 128, winv, w.logdet + L.k,
-                                h->dinfo, (int)w.N));
+          if (L.trsm) w.dinv_partial_from = std::min(w.dinv_partial_from, L.k);
+          if (L.trsm)
+            CK(cudaLaunchKernelEx(&lc, potrf_diagr_kernel<false>, w.Lbuf, (long long)w.Np, L.k * 128, winv,
+                                  w.logdet + L.k, h->dinfo, (int)w.N));
+          else
+            CK(cudaLaunchKernelEx(&lc, potrf_diagr_kernel<true>, w.Lbuf, (long long)w.Np, L.k * 128, winv,
+                                  w.logdet + L.k, h->dinfo, (int)w.N));
         } else if (g_diag4 == 1) {
           lc.blockDim = dim3(DIAG_THREADS);
           lc.dynamicSmemBytes = DIAG4_SMEM;
@@ -679,6 +700,22 @@ int run_plan(H* h, Workspace& w, Plan& p, bool factor_diag, cudaStream_t only_st
       } else
         potrf_diag_kernel<false><<<1, DIAG_THREADS, DIAG_SMEM, st>>>(w.Lbuf, w.Np, L.k * 128, winv, w.logdet + L.k,
                                                                      h->dinfo, (int)w.N);
+      h->launches++;
+      CK(cudaGetLastError());
+    } else if (factor_diag && L.trsm) {
+      // panel solve L_ik = A_ik W_kk^T, executed as a blocked triangular solve on the same stripe tasks
+      cudaLaunchConfig_t lc{};
+      lc.gridDim = dim3((unsigned)L.ntasks);
+      lc.blockDim = dim3(TP_THREADS);
+      lc.dynamicSmemBytes = TP_SMEM;
+      lc.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[0].val.programmaticStreamSerializationAllowed = 1;
+      lc.attrs = at;
+      lc.numAttrs = (L.pdl && g_pdl && !(multi && L.wait_ev >= 0)) ? 1 : 0;
+      CK(cudaLaunchKernelEx(&lc, trsm_panel_kernel, w.Lbuf, (long long)w.Np, (const double*)w.Dinv,
+                            (const GemmTask*)(p.d_tasks + L.task_off)));
       h->launches++;
       CK(cudaGetLastError());
     } else {
@@ -1033,6 +1070,11 @@ int assemble_and_factor(H* h, bool early_inverse = false) {
     for (int i = 0; i < w.n_phase; ++i) {
       CK(cudaStreamWaitEvent(h->stream3, h->events[w.phase_ev[i]], 0));
       if (w.phase_cut[i] > k0) {
+        const int c0 = std::max(k0, w.dinv_partial_from);
+        if (c0 < w.phase_cut[i]) {
+          complete_inverse_kernel<<<(unsigned)(w.phase_cut[i] - c0), TP_THREADS, 0, h->stream3>>>(w.Lbuf, w.Np, c0, w.Dinv);
+          h->launches++;
+        }
         seed_diag_kernel<<<(unsigned)(w.phase_cut[i] - k0), 256, 0, h->stream3>>>(w.Dinv, w.Ubuf, w.Wbuf, w.Np, k0);
         h->launches++;
         CK(cudaGetLastError());
@@ -1053,6 +1095,11 @@ int triangular_inverse(H* h, Workspace& w, bool early_done = false) {
   if (rc) return rc;
   const bool early = early_done && w.n_phase > 0;
   const int k0 = early ? w.phase_cut[w.n_phase - 1] : 0;
+  const int c0 = std::max(k0, w.dinv_partial_from);
+  if (c0 < (int)w.Nb) {   // the chain only left the 32x32 diagonal blocks of these inverted diagonal blocks
+    complete_inverse_kernel<<<(unsigned)(w.Nb - c0), TP_THREADS, 0, h->stream>>>(w.Lbuf, w.Np, c0, w.Dinv);
+    h->launches++;
+  }
   seed_diag_kernel<<<(unsigned)(w.Nb - k0), 256, 0, h->stream>>>(w.Dinv, w.Ubuf, w.Wbuf, w.Np, k0);
   h->launches++;
   CK(cudaGetLastError());
@@ -1101,6 +1148,7 @@ int load_matrix_into_L(H* h, Workspace& w, const double* A, long long n) {
 }
 
 int invert_diag_blocks(H* h, Workspace& w) {
+  w.dinv_partial_from = 1 << 30;
   potrf_diag_kernel<false><<<(unsigned)w.Nb, DIAG_THREADS, DIAG_SMEM, h->stream>>>(w.Lbuf, w.Np, 0, w.Dinv, w.logdet,
                                                                                    h->dinfo, (int)w.N);
   h->launches++;
@@ -1297,7 +1345,9 @@ int gpb_create(int device, gpb_handle_t* out) {
     return -2;
   }
   h->encode = reinterpret_cast<EncodeTiledFn>(fn);
-  if (cudaFuncSetAttribute(potrf_diagr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DR_SMEM) != cudaSuccess ||
+  if (cudaFuncSetAttribute(potrf_diagr_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DR_SMEM) != cudaSuccess ||
+      cudaFuncSetAttribute(potrf_diagr_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DR_SMEM) != cudaSuccess ||
+      cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TP_SMEM) != cudaSuccess ||
       cudaFuncSetAttribute(potrf_diag4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG4_SMEM) != cudaSuccess ||
       cudaFuncSetAttribute(potrf_diag_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM) != cudaSuccess ||
       cudaFuncSetAttribute(potrf_diag_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM) != cudaSuccess) {
@@ -1321,8 +1371,12 @@ int gpb_create(int device, gpb_handle_t* out) {
   if (const char* e = getenv("GPB_EARLY_MASK")) g_early_mask = atoi(e);
   if (const char* e = getenv("GPB_FINE_BELOW")) g_fine_below = atoi(e);
   if (const char* e = getenv("GPB_PDL")) g_pdl = atoi(e) != 0;
+  if (const char* e = getenv("GPB_TRSM")) g_trsm = atoi(e) != 0;
+  if (const char* e = getenv("GPB_TRSM_BELOW")) g_trsm_below = std::max(0, atoi(e));
+  if (const char* e = getenv("GPB_EARLY_MIN_BLOCKS")) g_early_min_blocks = std::max(8, atoi(e));
   if (const char* e = getenv("GPB_TAIL_BLOCKS")) g_tail_blocks = std::max(0, atoi(e));
   if (const char* e = getenv("GPB_SUPER")) g_super = std::max(0, std::min(64, atoi(e)));
+  if (const char* e = getenv("GPB_SUPER_TRTRI")) g_super_trtri = std::max(0, std::min(64, atoi(e)));
   if (const char* e = getenv("GPB_DIAG4")) g_diag4 = std::max(0, std::min(2, atoi(e)));
   *out = h;
   return 0;
@@ -2208,7 +2262,7 @@ int gpb_debug_gemm(gpb_handle_t h, const double* A, const double* B, double* C, 
 // Factor one 128x128 SPD block with the diagonal-block kernel selected by `mode` (0 / 1 / 2 as GPB_DIAG4), `reps`
 // times back to back on the handle's stream; returns L, L^-1, sum log L_jj and the mean kernel time.
 int gpb_debug_diag(gpb_handle_t h, const double* A, double* L, double* W, double* logdet, int mode, int reps, double* ms) {
-  if (!h || !A || !L || !W || reps < 1 || mode < 0 || mode > 2) return fail(h, -1, "gpb_debug_diag: bad argument");
+  if (!h || !A || !L || !W || reps < 1 || mode < 0 || mode > 3) return fail(h, -1, "gpb_debug_diag: bad argument");
   CK(cudaSetDevice(h->device));
   if (int rc_order = order_after_caller(h)) return rc_order;
   int rc = ensure_cap(h, &h->dstage, &h->dstage_cap, (size_t)3 * 128 * 128 + 8);
@@ -2225,7 +2279,8 @@ int gpb_debug_diag(gpb_handle_t h, const double* A, double* L, double* W, double
   for (int r = 0; r < reps; ++r) {
     CK(cudaMemcpyAsync(dB, dA, 128 * 128 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     cudaEventRecord(e0, h->stream);
-    if (mode == 2) potrf_diagr_kernel<<<1, DR_THREADS, DR_SMEM, h->stream>>>(dB, 128, 0, dW, dl, h->dinfo, 128);
+    if (mode == 2) potrf_diagr_kernel<true><<<1, DR_THREADS, DR_SMEM, h->stream>>>(dB, 128, 0, dW, dl, h->dinfo, 128);
+    else if (mode == 3) potrf_diagr_kernel<false><<<1, DR_THREADS, DR_SMEM, h->stream>>>(dB, 128, 0, dW, dl, h->dinfo, 128);
     else if (mode == 1) potrf_diag4_kernel<<<1, DIAG_THREADS, DIAG4_SMEM, h->stream>>>(dB, 128, 0, dW, dl, h->dinfo, 128);
     else potrf_diag_kernel<true><<<1, DIAG_THREADS, DIAG_SMEM, h->stream>>>(dB, 128, 0, dW, dl, h->dinfo, 128);
     cudaEventRecord(e1, h->stream);
@@ -2235,6 +2290,11 @@ int gpb_debug_diag(gpb_handle_t h, const double* A, double* L, double* W, double
     float t = 0.f;
     cudaEventElapsedTime(&t, e0, e1);
     total += t;
+  }
+  if (mode == 3) {   // what the library does off the chain: the blocks of L^-1 below the block diagonal
+    complete_inverse_kernel<<<1, TP_THREADS, 0, h->stream>>>(dB, 128, 0, dW);
+    h->launches++;
+    CK(cudaGetLastError());
   }
   // the factor as the library's consumers see it: lower triangle (mode 2 does not touch the strict upper one)
   unpack_kernel<<<(128 * 128 + 255) / 256, 256, 0, h->stream>>>(dB, 128, 128, 0, dA);

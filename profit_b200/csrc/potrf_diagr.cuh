@@ -232,6 +232,27 @@ __device__ __forceinline__ void dr_solve_row(int p, int lr, bool inverse, bool w
   }
 }
 
+// ---- workers (256 threads), factor-only variant: columns 32p..32p+31 of L = Z diag(sqrt d), rows 32p..127, to global
+// memory while the serial warp sweeps the next panel (the workers have nothing else to do then, and no DMMA stream
+// competes with the scaling multiplications).  Only the lower triangle is written.
+__device__ __forceinline__ void dr_store_panel(int p, int wt, double* __restrict__ Ablk, long long lda) {
+  const DrSmem sm = dr_smem();
+  const int cl = (wt & 15) * 2;                     // column pair inside the panel
+  const double sd0 = sqrt(sm.dvec[32 * p + cl]), sd1 = sqrt(sm.dvec[32 * p + cl + 1]);
+  const double* zcol = sm.Zs + dr_zrow0(p) * DR_S + cl;
+  double* out = Ablk + (long long)(32 * p) * lda + 32 * p + cl;
+#pragma unroll 4
+  for (int lr = wt >> 4; lr < 128 - 32 * p; lr += 16) {
+    if (cl <= lr) {
+      const double2 z = *reinterpret_cast<const double2*>(zcol + lr * DR_S);
+      double2 l;
+      l.x = (cl < lr) ? z.x * sd0 : sd0;
+      l.y = (cl + 1 < lr) ? z.y * sd1 : ((cl + 1 == lr) ? sd1 : 0.0);
+      *reinterpret_cast<double2*>(out + (long long)lr * lda) = l;
+    }
+  }
+}
+
 // ---- workers: C fragments of column-block P of the trailing matrix -> Pb (local rows 32 (i - P) ..)
 template <int P>
 __device__ __forceinline__ void dr_dump(const DrSmem& sm, double (&accA)[10][2][2], int tr, int tcb, int g, int t) {
@@ -340,10 +361,15 @@ __device__ __forceinline__ void dr_inverse(const DrSmem& sm, double (&accT)[6][2
   }
 }
 
-// In / out exactly as potrf_diag4_kernel:
-//   A (row-major, lda): lower triangle of the SPD block at rows/cols [k0, k0+128)  ->  L (strict upper zeroed)
-//   Winv <- L^-1 (128x128 row-major, strict upper zeroed);  logdet[0] <- sum_j log L_jj over rows < n_valid;
+// In / out as potrf_diag4_kernel:
+//   A (row-major, lda): lower triangle of the SPD block at rows/cols [k0, k0+128)  ->  L (lower triangle)
+//   Winv <- L^-1 (128x128 row-major, lower block triangle);  logdet[0] <- sum_j log L_jj over rows < n_valid;
 //   info <- first non-positive pivot (global 1-based index), untouched otherwise.
+// FULL_INV == false (the blocked Cholesky's panel chain): only the four 32x32 diagonal blocks of L^-1 are produced
+// -- the panel solve is a blocked triangular solve (trsm_panel_kernel) that needs nothing else, and
+// complete_inverse_kernel fills the rest of L^-1 off the chain when the triangular inverse asks for it.  The workers
+// then have no inverse work and write the finished panel of L while the next one is being swept.
+template <bool FULL_INV>
 __global__ void __launch_bounds__(DR_THREADS, 1)
 potrf_diagr_kernel(double* __restrict__ A, long long lda, int k0, double* __restrict__ Winv, double* __restrict__ logdet,
                    int* __restrict__ info, int n_valid) {
@@ -396,7 +422,8 @@ potrf_diagr_kernel(double* __restrict__ A, long long lda, int k0, double* __rest
     dr_dump<P>(sm, accA, tr, tcb, g, t);                                                \
     dr_bar_all(); /* S1(P) */                                                           \
     if (warp == 0) DR_STAMP(0, 8 * P + 1);                                              \
-    dr_inverse<(P > 0 ? P - 1 : 0)>(sm, accT, tr, tcb, g, t, Winv);                     \
+    if (FULL_INV) dr_inverse<(P > 0 ? P - 1 : 0)>(sm, accT, tr, tcb, g, t, Winv);       \
+    else dr_store_panel((P > 0 ? P - 1 : 0), tid, Ablk, lda);                           \
     if (warp == 0) DR_STAMP(0, 8 * P + 2);                                              \
   }                                                                                     \
   dr_bar_all(); /* S2(P) */                                                             \
@@ -408,7 +435,8 @@ potrf_diagr_kernel(double* __restrict__ A, long long lda, int k0, double* __rest
   }
     GPB_DR_PANEL(0) GPB_DR_PANEL(1) GPB_DR_PANEL(2) GPB_DR_PANEL(3)
 #undef GPB_DR_PANEL
-    dr_inverse<3>(sm, accT, tr, tcb, g, t, Winv);
+    if (FULL_INV) dr_inverse<3>(sm, accT, tr, tcb, g, t, Winv);
+    else dr_store_panel(3, tid, Ablk, lda);
     if (warp == 0) DR_STAMP(0, 41);
   } else if (warp == DR_SERIAL) {
 #pragma unroll 1
@@ -442,7 +470,7 @@ potrf_diagr_kernel(double* __restrict__ A, long long lda, int k0, double* __rest
   // triangle of the block nor the part of Winv above the block diagonal is written: nothing reads the former (every
   // consumer of a diagonal block of L masks k <= i) and the caller provides a zero-initialised Winv.  (Storing the
   // panels earlier, behind S2(p), was measured slower: the scaling DMULs then queue behind the update's DMMAs.)
-  {
+  if (FULL_INV) {
     const int c = (tid & 63) * 2, pc = c >> 5;   // 384 = 6 x 64: a thread keeps its column pair, rows r0, r0 + 6, ..
     const double2 sd = *reinterpret_cast<const double2*>(sm.sdv + c);
     const double* zcol = sm.Zs + (dr_zrow0(pc) - 32 * pc) * DR_S + (c & 31);

@@ -1,5 +1,6 @@
 """Diagonal-block kernels of the Cholesky on one 128x128 SPD block: correctness against numpy and device time of
-mode 2 (blocked DMMA kernel, potrf_diagr.cuh), 1 (rank-4 register sweep) and 0 (rank-1 register sweep)."""
+mode 3 (blocked DMMA kernel as on the panel chain: factor + 32x32 diagonal inverses, completed off the chain), 2 (the
+same with the full inverse), 1 (rank-4 register sweep) and 0 (rank-1 register sweep)."""
 import json
 import os
 import sys
@@ -24,7 +25,7 @@ for case in ("wishart", "kernel", "identity"):
         A = np.eye(128)
     Lref = np.linalg.cholesky(A)
     Wref = np.linalg.inv(Lref)
-    for mode in (2, 1, 0):
+    for mode in (3, 2, 1, 0):
         L, W, ld, ms = be.debug_diag(np.tril(A), mode=mode, reps=20)
         rec = {"case": case, "mode": mode, "us": round(ms * 1e3, 2),
                "L_err": float(np.abs(L - Lref).max() / np.abs(Lref).max()),
