@@ -12,7 +12,7 @@
  *     which.  Caller owns all buffers passed in; the library owns its device workspaces inside the handle.
  *   - Return value: 0 = ok; > 0 = LAPACK-style info (1-based index of the first non-positive pivot: the
  *     matrix is not SPD -> the Python layer raises numpy.linalg.LinAlgError like gp_functions.py:143 would);
- *     < 0 = bad argument (-1), CUDA failure (-2), not ready (-3).  gpb_error_string() describes the last error.
+ *     < 0 = bad argument (-1), CUDA failure (-2), not ready (-3), eigen-solver failure (-4).  gpb_error_string() describes the last error.
  *   - One handle = one device + one stream; calls on a handle must be serialised by the caller.
  *   - Stream semantics for device pointers: the handle's stream is a blocking stream, i.e. it is ordered after work
  *     already queued on the legacy default stream (the one torch uses unless told otherwise).  A caller that
@@ -168,6 +168,34 @@ int gpb_invert_cholesky(gpb_handle_t h, const double* L, long long n, double* Ki
 
 /* x = L^T \ (L \ b), b: (n, nrhs) -- gp_functions.solve_cholesky (gp_functions.py:72-100). nrhs <= 128. */
 int gpb_solve_cholesky(gpb_handle_t h, const double* L, long long n, const double* b, int nrhs, double* x);
+
+/* Truncated eigen-decomposition exits of the reference (the branches taken when the Cholesky factorisation is not used).
+ * Device solver: Lanczos with full re-orthogonalisation + implicit QL on the projected tridiagonal matrix, deterministic
+ * start vector, Ritz pairs converged to ~1e-13 |lambda_max| (the reference's ARPACK call stops at tol = 1e-3 min|l| from a
+ * random start; its values scatter by ~5e-7 relative).  Status -4 = the solver did not converge / broke down.
+ *
+ * gpb_eigsh: the k largest eigenpairs of Ky(theta) of the resident training set -- eigsh(Ky, neig, tol=clip_eig) in the
+ * loop of gp_functions.negative_log_likelihood (gp_functions.py:273-275).  w_out: k eigenvalues ascending (eigsh's order,
+ * so w_out[0] is what the loop compares with clip_eig, :280).  Calls with the same (kind, theta) continue one Lanczos run.
+ * steps_out (may be NULL) <- Lanczos steps used. */
+int gpb_eigsh(gpb_handle_t h, int kind, const double* theta, int n_ell, int k, double* w_out, int* steps_out);
+
+/* NLL and gradient on that exit (gp_functions.py:283-300) from the eigenpairs gpb_eigsh left resident:
+ * w <- max(w, 1e-10), alpha = Q diag(1/w) Q^T y, nll = 1/2 (y^T alpha + sum log w + neig_term log 2 pi) with
+ * neig_term = min(neig, N) of :286; grad = 1/2 tr((invert(Ky) - alpha alpha^T) dKy) on the linear scale, invert(Ky) by
+ * Cholesky with the reference's single 1e-6 diagonal retry (:340-343) -- a second failure returns the pivot index (> 0),
+ * as np.linalg.cholesky would raise there.  Single-output training sets only (the reference calls nll.item()). */
+int gpb_nll_eig(gpb_handle_t h, int neig_term, int want_grad, double* nll, double* grad);
+
+/* eigsh(K, neig, tol) of gp_functions.invert (gp_functions.py:351,359) for a caller-provided symmetric matrix A (n, n).
+ * reuse != 0: A is the matrix of the previous call (its Lanczos run is continued; A is not read and may be NULL).
+ * w_out: k eigenvalues ascending; Qt_out: (k, n), row i = eigenvector of w_out[i], or NULL. */
+int gpb_eigsh_matrix(gpb_handle_t h, const double* A, long long n, int k, int reuse, double* w_out, double* Qt_out,
+                     int* steps_out);
+
+/* K^-1 = Q diag(1/w) Q^T (gp_functions.py:366-369) from the resident eigenvectors of gpb_eigsh_matrix and the caller's
+ * eigenvalues w (host, k entries: the reference replaces slightly negative ones by 1e-2 first).  Kinv: (n, n). */
+int gpb_eig_inverse(gpb_handle_t h, const double* w, double* Kinv);
 
 /* Device milliseconds of each stage of the last gpb_nll / gpb_factorize / gpb_predict call (CUDA events on the
  * handle's stream).  out has GPB_NUM_STAGES entries. */

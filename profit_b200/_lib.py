@@ -48,6 +48,13 @@ SIGNATURES = {
     "gpb_cholesky": (ctypes.c_int, [ctypes.c_void_p, _c_double_p, _ll, _c_double_p]),
     "gpb_invert_cholesky": (ctypes.c_int, [ctypes.c_void_p, _c_double_p, _ll, _c_double_p]),
     "gpb_solve_cholesky": (ctypes.c_int, [ctypes.c_void_p, _c_double_p, _ll, _c_double_p, ctypes.c_int, _c_double_p]),
+    "gpb_eigsh": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _c_double_p, ctypes.c_int, ctypes.c_int, _c_double_p,
+                                 ctypes.POINTER(ctypes.c_int)]),
+    "gpb_nll_eig": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double),
+                                   _c_double_p]),
+    "gpb_eigsh_matrix": (ctypes.c_int, [ctypes.c_void_p, _c_double_p, _ll, ctypes.c_int, ctypes.c_int, _c_double_p,
+                                        _c_double_p, ctypes.POINTER(ctypes.c_int)]),
+    "gpb_eig_inverse": (ctypes.c_int, [ctypes.c_void_p, _c_double_p, _c_double_p]),
     "gpb_stage_ms": (ctypes.c_int, [ctypes.c_void_p, _c_double_p]),
     "gpb_launch_count": (_ll, [ctypes.c_void_p]),
     "gpb_debug_plan": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, _ll, ctypes.c_void_p, _ll,
@@ -125,4 +132,6 @@ def check(status, handle=None, what=""):
         raise np.linalg.LinAlgError(msg or f"{what}: matrix is not positive definite (info={status})")
     if status == -1:
         raise ValueError(msg or f"{what}: bad argument")
+    if status == -4:   # scipy raises ArpackNoConvergence (a RuntimeError) when eigsh does not converge
+        raise RuntimeError(msg or f"{what}: the device eigen-solver did not converge")
     raise RuntimeError(msg or f"{what}: CUDA backend failure (status {status})")

@@ -321,6 +321,52 @@ class GPBackend:
                    self._h, "solve_cholesky")
         return x
 
+    # -- truncated eigen-decomposition exits (gp_functions.py:273-301, 350-373) -----------------------------------
+    def eigsh(self, kind, theta, k):
+        """The k largest eigenvalues of Ky(theta) of the resident training set, ascending like
+        ``scipy.sparse.linalg.eigsh(Ky, k)`` at gp_functions.py:273-275; the eigenvectors stay on the device."""
+        theta = np.ascontiguousarray(theta, dtype=np.float64).ravel()
+        k = int(min(k, self.n))
+        w = np.empty(k)
+        steps = ctypes.c_int()
+        self.factor_key = self.noise_override = None
+        _lib.check(self._lib.gpb_eigsh(self._h, int(kind), _lib.ptr(theta), theta.size - 2, k, _lib.ptr(w),
+                                       ctypes.byref(steps)), self._h, "eigsh")
+        self.last_eig_steps = steps.value
+        return w
+
+    def nll_eig(self, neig_term, want_grad=False, n_params=None):
+        """NLL [, gradient on the linear scale] from the eigenpairs the last ``eigsh`` call left resident
+        (gp_functions.py:283-300)."""
+        out = ctypes.c_double()
+        grad = np.empty(int(n_params)) if want_grad else None
+        self.factor_key = self.noise_override = None
+        _lib.check(self._lib.gpb_nll_eig(self._h, int(neig_term), int(bool(want_grad)), ctypes.byref(out), _lib.ptr(grad)),
+                   self._h, "nll_eig")
+        return (out.value, grad) if want_grad else out.value
+
+    def eigsh_matrix(self, A, k, reuse=False, want_vectors=False):
+        """``eigsh(A, k)`` of gp_functions.invert (:351,359): (w ascending, Q (n, k) or None)."""
+        A = _lib.as_f64(A)
+        self._check_square(A, "K")
+        n = int(A.shape[0])
+        k = int(min(k, n))
+        w = np.empty(k)
+        Qt = np.empty((k, n)) if want_vectors else None
+        steps = ctypes.c_int()
+        self._order(A)
+        _lib.check(self._lib.gpb_eigsh_matrix(self._h, _lib.ptr(A), n, k, int(bool(reuse)), _lib.ptr(w), _lib.ptr(Qt),
+                                              ctypes.byref(steps)), self._h, "eigsh_matrix")
+        self.last_eig_steps = steps.value
+        return w, (Qt.T if want_vectors else None)
+
+    def eig_inverse(self, w, n):
+        """Q diag(1/w) Q^T from the eigenvectors the last ``eigsh_matrix`` call left resident (gp_functions.py:366-369)."""
+        w = np.ascontiguousarray(w, dtype=np.float64).ravel()
+        out = np.empty((int(n), int(n)))
+        _lib.check(self._lib.gpb_eig_inverse(self._h, _lib.ptr(w), _lib.ptr(out)), self._h, "eig_inverse")
+        return out
+
     # -- introspection --------------------------------------------------------------------------------
     def stage_ms(self):
         out = np.zeros(_lib.NUM_STAGES)

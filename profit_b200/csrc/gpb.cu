@@ -36,6 +36,7 @@
 #include "acquisition.cuh"
 #include "assemble.cuh"
 #include "dgemm_tasks.cuh"
+#include "eig.cuh"
 #include "potrf_diag.cuh"
 #include "potrf_diagr.cuh"
 #include "trsm_panel.cuh"
@@ -158,6 +159,23 @@ struct gpb_handle_s {
   size_t dapp_cap = 0;
   double* dacq = nullptr;     // acquisition scratch: staged host inputs, block partials, statistics
   size_t dacq_cap = 0;
+
+  // truncated eigen-decomposition (eig.cuh): Lanczos basis, projected problem, Ritz pairs
+  struct Eig {
+    double* K = nullptr;        // dense symmetric matrix (n x n, ld = n)
+    size_t K_cap = 0;
+    double* buf = nullptr;      // one allocation: Vt, w, c1, c2, alpha, beta, d, Zt, Qt, wsel, qy, t, avec
+    size_t buf_cap = 0;
+    double *Vt = nullptr, *w = nullptr, *c1 = nullptr, *c2 = nullptr, *alpha = nullptr, *beta = nullptr, *d = nullptr,
+           *Zt = nullptr, *Qt = nullptr, *wsel = nullptr, *qy = nullptr, *t = nullptr, *avec = nullptr;
+    int* ibuf = nullptr;        // sel[mcap], flag[2]
+    int n = 0, mcap = 0, m = 0, k = 0, restarts = 0;
+    double grad_jitter = 0.0;   // diagonal shift under which invert(Ky) of the last gpb_nll_eig gradient factorised
+    bool matrix_ready = false;  // K holds the matrix described by key
+    bool from_train = false;    // K = Ky(theta) of the resident training set (gpb_eigsh) rather than an uploaded matrix
+    std::vector<double> key;    // kind, n_ell, theta...
+    std::vector<double> w_host; // the k resident eigenvalues, ascending
+  } eig;
 
   cudaEvent_t ev0[GPB_NUM_STAGES], ev1[GPB_NUM_STAGES];
   cudaEvent_t evx[3];   // scratch timing events (gradient tail, predict chunk phases, debug GEMM)
@@ -1306,6 +1324,202 @@ __global__ void quadform_kernel(const double* __restrict__ dm, int M, int P, con
 
 }  // namespace
 
+
+// ------------------------------------------------------------------------------------------------ eigen-decomposition
+constexpr int EIG_MCAP = 4096;   // most Lanczos steps (= largest projected problem the QL kernel holds in shared memory)
+
+// (Re)allocate the work buffers for an n x n matrix; invalidates the resident matrix when the size changes.
+int eig_reserve(H* h, int n) {
+  H::Eig& e = h->eig;
+  const int mcap = std::min(n, EIG_MCAP);
+  if (e.n == n && e.buf) return 0;
+  const size_t nn = (size_t)n, mm = (size_t)mcap;
+  const size_t need = (mm + 1) * nn + nn + 5 * mm + 8 + mm * mm + mm * nn + 3 * mm + nn;
+  int rc = ensure_cap(h, &e.buf, &e.buf_cap, need);
+  if (rc) return rc;
+  double* p = e.buf;
+  e.Vt = p, p += (mm + 1) * nn;
+  e.w = p, p += nn;
+  e.c1 = p, p += mm;
+  e.c2 = p, p += mm;
+  e.alpha = p, p += mm;
+  e.beta = p, p += mm + 8;
+  e.d = p, p += mm;
+  e.Zt = p, p += mm * mm;
+  e.Qt = p, p += mm * nn;
+  e.wsel = p, p += mm;
+  e.qy = p, p += mm;
+  e.t = p, p += mm;
+  e.avec = p, p += nn;
+  if (e.ibuf) CK(cudaFree(e.ibuf));
+  e.ibuf = nullptr;
+  CK(cudaMalloc(&e.ibuf, (mm + 2) * sizeof(int)));
+  if ((rc = ensure_cap(h, &e.K, &e.K_cap, nn * nn))) return rc;
+  e.n = n;
+  e.mcap = mcap;
+  e.m = e.k = 0;
+  e.matrix_ready = false;
+  return 0;
+}
+
+// Start a Lanczos run on the resident matrix: v_0 = normalised deterministic pseudo-random vector.
+int eig_begin(H* h) {
+  H::Eig& e = h->eig;
+  CK(cudaMemsetAsync(e.ibuf + e.mcap, 0, 2 * sizeof(int), h->stream));
+  eig_start_kernel<<<(unsigned)((e.n + 255) / 256), 256, 0, h->stream>>>(e.w, e.n, 0x5DEECE66Dull);
+  eig_next_kernel<<<1, 1024, 0, h->stream>>>(e.w, e.n, e.Vt, nullptr);
+  h->launches += 2;
+  CK(cudaGetLastError());
+  e.m = e.k = 0;
+  e.restarts = 0;
+  return 0;
+}
+
+// One pass of classical Gram-Schmidt of e.w against the first cnt basis vectors (coefficients into c).
+void eig_gs_pass(H* h, int cnt, double* c, const double* c_first, double* alpha_out) {
+  H::Eig& e = h->eig;
+  const int n = e.n;
+  eig_dots_kernel<<<(unsigned)cnt, EIG_BLOCK, 0, h->stream>>>(e.Vt, n, n, e.w, c);
+  eig_update_kernel<<<(unsigned)((n + EIG_BLOCK - 1) / EIG_BLOCK), EIG_BLOCK, 0, h->stream>>>(e.Vt, n, n, cnt, c, e.w, c_first,
+                                                                                               alpha_out);
+  h->launches += 2;
+}
+
+// Orthogonalise e.w against the first cnt basis vectors and leave the normalised result in row cnt of the basis.
+// Two Gram-Schmidt passes, then more while a pass still removes more than half of the vector (a vector that lies
+// numerically inside span(V) needs them: "twice is enough" only holds for vectors that do not).  norms <- {|w| before,
+// after the first pass, at the end}; alpha_out (device, may be nullptr) <- coefficient along the last basis vector.
+int eig_orthonormalise(H* h, int cnt, double* alpha_out, double norms[3]) {
+  H::Eig& e = h->eig;
+  const int n = e.n;
+  double* vnext = e.Vt + (size_t)cnt * n;       // the basis buffer has mcap + 1 rows
+  double* dn = e.beta + e.mcap;                 // 8 spare doubles behind the beta array
+  eig_next_kernel<<<1, 1024, 0, h->stream>>>(e.w, n, nullptr, dn);
+  eig_gs_pass(h, cnt, e.c1, nullptr, nullptr);
+  eig_next_kernel<<<1, 1024, 0, h->stream>>>(e.w, n, nullptr, dn + 1);
+  eig_gs_pass(h, cnt, e.c2, e.c1, alpha_out);
+  eig_next_kernel<<<1, 1024, 0, h->stream>>>(e.w, n, vnext, dn + 2);
+  h->launches += 3;
+  CK(cudaMemcpyAsync(norms, dn, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  double prev = norms[1];
+  for (int extra = 0; extra < 4 && norms[2] > 0.0 && norms[2] < 0.5 * prev; ++extra) {
+    prev = norms[2];
+    eig_gs_pass(h, cnt, e.c2, nullptr, nullptr);
+    eig_next_kernel<<<1, 1024, 0, h->stream>>>(e.w, n, vnext, dn + 2);
+    h->launches++;
+    CK(cudaMemcpyAsync(norms + 2, dn + 2, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// Lanczos steps m .. m_target-1 with full re-orthogonalisation.  After every step the host reads alpha_j and the norms of
+// the residual: a residual at the rounding level of the vector it was computed from (64 eps |A v_j|) means that span(V)
+// is invariant under the matrix (rank-deficient or repeated spectrum) -- what is left is rounding noise, not a Krylov
+// direction.  The run then continues from a fresh pseudo-random vector orthogonalised against V, with beta_j = 0 in T,
+// so that T stays the projection V^T A V (block diagonal) to working accuracy.
+int eig_extend(H* h, int m_target) {
+  H::Eig& e = h->eig;
+  const int n = e.n;
+  const unsigned gr = (unsigned)((n + 7) / 8);
+  for (int j = e.m; j < m_target; ++j) {
+    const double* vj = e.Vt + (size_t)j * n;
+    eig_symv_kernel<<<gr, EIG_BLOCK, 0, h->stream>>>(e.K, n, n, vj, e.w);
+    h->launches++;
+    double norms[3], alpha_j = 0.0;
+    int rc = eig_orthonormalise(h, j + 1, e.alpha + j, norms);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(e.beta + j, e.beta + e.mcap + 2, sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(&alpha_j, e.alpha + j, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (!std::isfinite(alpha_j) || !std::isfinite(norms[2]))
+      return fail(h, -4, "eigsh: non-finite Lanczos coefficients at step " + std::to_string(j + 1));
+    e.m = j + 1;
+    if (j + 1 < n && norms[2] <= 64.0 * 2.220446049250313e-16 * norms[0]) {
+      CK(cudaMemsetAsync(e.beta + j, 0, sizeof(double), h->stream));
+      eig_start_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(e.w, n, 0x5DEECE66Dull + 7919ull * (unsigned long long)(j + 1));
+      h->launches++;
+      if ((rc = eig_orthonormalise(h, j + 1, nullptr, norms))) return rc;
+      e.restarts++;
+    }
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// The k largest eigenpairs of the resident matrix; leaves the eigenvalues (ascending, like eigsh) in e.wsel / e.w_host
+// and the orthonormal Ritz vectors in the rows of e.Qt.  steps_out <- Lanczos steps used.
+int eig_topk(H* h, int k, int* steps_out) {
+  H::Eig& e = h->eig;
+  const int n = e.n;
+  if (k < 1) return fail(h, -1, "eigsh: k must be positive");
+  k = std::min(k, n);
+  if (k > e.mcap)
+    return fail(h, -4, "eigsh: " + std::to_string(k) + " eigenpairs requested, the device solver holds at most " +
+                           std::to_string(e.mcap) + " Lanczos vectors");
+  std::vector<double> d, zlast;
+  std::vector<int> order;
+  int m = std::min(std::min(n, e.mcap), std::max(e.m, std::max(2 * k + 16, 48)));
+  while (true) {
+    int rc = eig_extend(h, m);
+    if (rc) return rc;
+    const size_t smem = 4 * (size_t)m * sizeof(double);
+    CK(cudaFuncSetAttribute(eig_tql2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    eig_tql2_kernel<<<1, EIG_QL_THREADS, smem, h->stream>>>(e.alpha, e.beta, m, e.d, e.Zt, m, e.ibuf + e.mcap + 1);
+    h->launches++;
+    CK(cudaGetLastError());
+    d.resize(m);
+    zlast.resize(m);
+    int flags[2] = {0, 0};
+    double beta_last = 0.0;
+    CK(cudaMemcpyAsync(d.data(), e.d, m * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpy2DAsync(zlast.data(), sizeof(double), e.Zt + (m - 1), (size_t)m * sizeof(double), sizeof(double), m,
+                         cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(&beta_last, e.beta + (m - 1), sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(flags, e.ibuf + e.mcap, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (flags[1]) return fail(h, -4, "eigsh: the QL iteration on the projected tridiagonal matrix did not converge");
+    for (int i = 0; i < m; ++i)
+      if (!std::isfinite(d[i])) return fail(h, -4, "eigsh: non-finite Ritz values");
+    order.resize(m);
+    for (int i = 0; i < m; ++i) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return d[a] > d[b] || (d[a] == d[b] && a < b); });
+    double scale = 0.0;
+    for (int i = 0; i < m; ++i) scale = std::max(scale, std::fabs(d[i]));
+    // residual of Ritz pair i: |beta_m z_{m,i}|; the basis spans everything once m == n
+    bool ok = (m >= n);
+    if (!ok) {
+      ok = true;
+      for (int i = 0; i < k && ok; ++i) ok = std::fabs(beta_last * zlast[order[i]]) <= 5e-13 * scale;
+    }
+    if (ok) break;
+    if (m >= e.mcap)
+      return fail(h, -4, "eigsh: " + std::to_string(k) + " eigenpairs did not converge within " + std::to_string(m) +
+                             " Lanczos steps");
+    m = std::min(std::min(n, e.mcap), m + std::max(16, m / 2));
+  }
+  // eigsh order: ascending, the largest k
+  std::vector<int> sel(k);
+  e.w_host.resize(k);
+  for (int i = 0; i < k; ++i) {
+    sel[i] = order[k - 1 - i];
+    e.w_host[i] = d[sel[i]];
+  }
+  CK(cudaMemcpyAsync(e.ibuf, sel.data(), k * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(e.wsel, e.w_host.data(), k * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  dim3 grid((unsigned)((n + EIG_BLOCK - 1) / EIG_BLOCK), (unsigned)k);
+  eig_ritz_kernel<<<grid, EIG_BLOCK, 0, h->stream>>>(e.Vt, n, n, m, e.Zt, m, e.ibuf, e.Qt, n);
+  eig_project_kernel<<<(unsigned)k, EIG_BLOCK, 0, h->stream>>>(e.Qt, n, n, nullptr, e.wsel, 0.0, nullptr, nullptr);
+  h->launches += 2;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  e.k = k;
+  if (steps_out) *steps_out = m;
+  return 0;
+}
+
 // ================================================================================================ C ABI
 extern "C" {
 
@@ -1407,6 +1621,9 @@ int gpb_destroy(gpb_handle_t h) {
   cudaFree(h->dbbq);
   cudaFree(h->dapp);
   cudaFree(h->dacq);
+  cudaFree(h->eig.K);
+  cudaFree(h->eig.buf);
+  cudaFree(h->eig.ibuf);
   for (int s = 0; s < GPB_NUM_STAGES; ++s) {
     cudaEventDestroy(h->ev0[s]);
     cudaEventDestroy(h->ev1[s]);
@@ -1468,6 +1685,7 @@ int gpb_set_train(gpb_handle_t h, const double* X, const double* y, long long n,
   CK(cudaMemcpyAsync(h->dy, y, (size_t)n * n_out * sizeof(double), cudaMemcpyDefault, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   h->factor_ready = false;
+  if (h->eig.from_train) h->eig.matrix_ready = false;
   return 0;
 }
 
@@ -1537,6 +1755,173 @@ int gpb_nll(gpb_handle_t h, int kind, const double* theta, int n_ell, int want_g
   if ((rc = check_info(h))) return rc;
   stages_collect(h);
   *nll = host0;
+  return 0;
+}
+
+// Largest-k eigenpairs of Ky(theta) of the resident training set -- scipy.sparse.linalg.eigsh(Ky, neig, tol=clip_eig) inside
+// the loop of gp_functions.negative_log_likelihood (gp_functions.py:273-275).  Repeated calls with the same (kind, theta)
+// continue the same Lanczos run.
+int gpb_eigsh(gpb_handle_t h, int kind, const double* theta, int n_ell, int k, double* w_out, int* steps_out) {
+  int rc = need_train(h);
+  if (rc) return rc;
+  if (!theta || !w_out) return fail(h, -1, "gpb_eigsh: null argument");
+  CK(cudaSetDevice(h->device));
+  if (int rc_order = order_after_caller(h)) return rc_order;
+  if ((rc = set_hyp(h, kind, theta, n_ell))) return rc;
+  const int n = (int)h->ws.N;
+  if ((rc = eig_reserve(h, n))) return rc;
+  H::Eig& e = h->eig;
+  std::vector<double> key = {(double)kind, (double)n_ell};
+  key.insert(key.end(), theta, theta + n_ell + 2);
+  if (!(e.matrix_ready && e.from_train && e.key == key)) {
+    e.matrix_ready = false;
+    if ((rc = dense_kernel_device(h, h->hyp, h->dX, n, h->dX, n, e.K, nullptr, false))) return rc;
+    if ((rc = eig_begin(h))) return rc;
+    e.key = key;
+    e.from_train = true;
+    e.matrix_ready = true;
+  }
+  if ((rc = eig_topk(h, k, steps_out))) {
+    e.matrix_ready = false;
+    return rc;
+  }
+  std::memcpy(w_out, e.w_host.data(), e.k * sizeof(double));
+  return 0;
+}
+
+// The same for a caller-provided symmetric matrix A (n x n) -- eigsh(K, neig, tol=tol) in gp_functions.invert
+// (gp_functions.py:351,359).  reuse != 0: A is the matrix of the previous call (continue its Lanczos run, A is not read).
+// Qt_out (k x n, row i = eigenvector of w_out[i]) may be NULL.
+int gpb_eigsh_matrix(gpb_handle_t h, const double* A, long long n, int k, int reuse, double* w_out, double* Qt_out,
+                     int* steps_out) {
+  if (!h || !w_out || n < 1 || n > 2000000000LL || (!A && !reuse)) return fail(h, -1, "gpb_eigsh_matrix: bad argument");
+  CK(cudaSetDevice(h->device));
+  if (int rc_order = order_after_caller(h)) return rc_order;
+  H::Eig& e = h->eig;
+  int rc;
+  if (!(reuse && e.matrix_ready && !e.from_train && e.n == (int)n)) {
+    if (!A) return fail(h, -3, "gpb_eigsh_matrix: nothing to reuse");
+    if ((rc = eig_reserve(h, (int)n))) return rc;
+    e.matrix_ready = false;
+    CK(cudaMemcpyAsync(e.K, A, (size_t)n * n * sizeof(double), cudaMemcpyDefault, h->stream));
+    if ((rc = eig_begin(h))) return rc;
+    e.from_train = false;
+    e.key.clear();
+    e.matrix_ready = true;
+  }
+  if ((rc = eig_topk(h, k, steps_out))) {
+    e.matrix_ready = false;
+    return rc;
+  }
+  std::memcpy(w_out, e.w_host.data(), e.k * sizeof(double));
+  if (Qt_out) {
+    CK(cudaMemcpyAsync(Qt_out, e.Qt, (size_t)e.k * n * sizeof(double), cudaMemcpyDefault, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  return 0;
+}
+
+// K^-1 = Q diag(1/w) Q^T from the resident Ritz vectors and the caller's (adjusted) eigenvalues -- the last line of
+// gp_functions.invert (gp_functions.py:366-369).  w: host, k entries; Kinv: (n, n).
+int gpb_eig_inverse(gpb_handle_t h, const double* w, double* Kinv) {
+  if (!h || !w || !Kinv) return fail(h, -1, "gpb_eig_inverse: null argument");
+  H::Eig& e = h->eig;
+  if (!e.matrix_ready || e.k < 1) return fail(h, -3, "gpb_eig_inverse: no resident eigenpairs (call gpb_eigsh_matrix first)");
+  CK(cudaSetDevice(h->device));
+  const int n = e.n;
+  CK(cudaMemcpyAsync(e.wsel, w, e.k * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  const bool dev = is_device_ptr(Kinv);
+  int rc;
+  if (!dev && (rc = ensure_cap(h, &h->dstage2, &h->dstage2_cap, (size_t)n * n))) return rc;
+  double* out = dev ? Kinv : h->dstage2;
+  dim3 grid((unsigned)((n + EIG_BLOCK - 1) / EIG_BLOCK), (unsigned)n);
+  eig_outer_kernel<<<grid, EIG_BLOCK, 0, h->stream>>>(e.Qt, n, n, e.k, e.wsel, out);
+  h->launches++;
+  CK(cudaGetLastError());
+  if (!dev) CK(cudaMemcpyAsync(Kinv, out, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+// NLL (and gradient) on the truncated eigen-decomposition exit of gp_functions.negative_log_likelihood
+// (gp_functions.py:283-300) from the eigenpairs left resident by gpb_eigsh:
+//   w <- max(w, 1e-10), alpha = Q diag(1/w) Q^T y, nll = 1/2 (y^T alpha + sum log w + neig_term log 2 pi);
+//   gradient = 1/2 tr((invert(Ky) - alpha alpha^T) dKy) with invert(Ky) through the Cholesky factorisation, retried once
+//   with 1e-6 on the diagonal (invert, gp_functions.py:340-348); a second failure returns the pivot index like gpb_nll.
+int gpb_nll_eig(gpb_handle_t h, int neig_term, int want_grad, double* nll, double* grad) {
+  int rc = need_train(h);
+  if (rc) return rc;
+  if (!nll || (want_grad && !grad)) return fail(h, -1, "gpb_nll_eig: null argument");
+  H::Eig& e = h->eig;
+  if (!e.matrix_ready || !e.from_train || e.k < 1 || e.n != (int)h->ws.N)
+    return fail(h, -3, "gpb_nll_eig: no resident eigenpairs of the training covariance (call gpb_eigsh first)");
+  if (h->n_out != 1) return fail(h, -1, "gpb_nll_eig: the eigen-decomposition branch handles one output column (nll.item())");
+  CK(cudaSetDevice(h->device));
+  Workspace& w = h->ws;
+  const int n = e.n, k = e.k;
+  h->factor_ready = false;
+  stages_reset(h);
+  CK(cudaMemcpyAsync(e.wsel, e.w_host.data(), k * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  eig_project_kernel<<<(unsigned)k, EIG_BLOCK, 0, h->stream>>>(e.Qt, n, n, h->dy, e.wsel, 1e-10, e.qy, e.t);
+  eig_alpha_kernel<<<(unsigned)((n + EIG_BLOCK - 1) / EIG_BLOCK), EIG_BLOCK, 0, h->stream>>>(e.Qt, n, n, k, e.t, e.avec);
+  eig_nll_kernel<<<1, EIG_BLOCK, 0, h->stream>>>(e.wsel, e.qy, e.t, k, 1e-10, (double)neig_term, h->dscal);
+  h->launches += 3;
+  CK(cudaGetLastError());
+  double host[64];
+  if (!want_grad) {
+    CK(cudaMemcpyAsync(host, h->dscal, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    *nll = host[0];
+    return 0;
+  }
+  CK(cudaMemcpyAsync(host, h->dscal, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  *nll = host[0];
+  if ((rc = ensure_inverse_buffers(h, w))) return rc;
+  const double sn_true = h->hyp.sn;
+  const int P = h->hyp.n_ell + 2, width = h->DP + 2;
+  // invert(Ky): Cholesky, then Cholesky of Ky + 1e-6 I (gp_functions.py:340-343).  Where the reference would now raise
+  // inside np.linalg.cholesky, the drop-in keeps the optimiser alive with the relative jitter ladder of the "jitter"
+  // policy (1e-8 .. 1e-2 sigma_f^2); only if that fails too is the pivot index returned.
+  const double sf2 = h->hyp.sf * h->hyp.sf;
+  const double jitter[6] = {0.0, 1e-6, 1e-8 * sf2, 1e-6 * sf2, 1e-4 * sf2, 1e-2 * sf2};
+  double used = 0.0;
+  int info = 0;
+  for (int attempt = 0; attempt < 6; ++attempt) {
+    if (attempt >= 2 && jitter[attempt] <= used) continue;
+    used = jitter[attempt];
+    h->hyp.sn = std::sqrt(sn_true * sn_true + used);
+    rc = assemble_and_factor(h, true);
+    if (!rc) rc = triangular_inverse(h, w, true);
+    if (!rc) rc = run_plan(h, w, w.syrk, false);
+    h->hyp.sn = sn_true;
+    if (rc) return rc;
+    info = check_info(h);
+    if (info <= 0) break;
+  }
+  if (info) return info;
+  h->eig.grad_jitter = used;
+  CK(cudaMemsetAsync(w.alpha, 0, (size_t)w.Np * sizeof(double), h->stream));
+  CK(cudaMemcpyAsync(w.alpha, e.avec, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  dim3 grid((unsigned)(w.Np / AS_TN), (unsigned)(w.Np / AS_TM));
+  const size_t ncta = (size_t)grid.x * grid.y;
+  if ((rc = ensure_cap(h, &h->dpart, &h->dpart_cap, ncta * width))) return rc;
+  rc = (h->hyp.kind == KIND_RBF) ? contract_dispatch<KIND_RBF>(h, w, grid) : contract_dispatch<KIND_MATERN52>(h, w, grid);
+  if (rc) return rc;
+  reduce_partials_kernel<<<width, 256, 0, h->stream>>>(h->dpart, (int)ncta, width, h->dscal + 1);
+  h->launches++;
+  CK(cudaMemcpyAsync(host, h->dscal, (1 + width) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  const double* acc = host + 1;
+  if (h->hyp.n_ell == 1) {
+    double sum = 0.0;
+    for (int d = 0; d < h->D; ++d) sum += acc[d];
+    grad[0] = 0.5 * sum / h->hyp.ell[0];
+  } else {
+    for (int d = 0; d < h->D; ++d) grad[d] = 0.5 * acc[d] / h->hyp.ell[d];
+  }
+  grad[P - 2] = 0.5 * (2.0 / h->hyp.sf) * acc[h->DP];
+  grad[P - 1] = 0.5 * (2.0 * sn_true) * acc[h->DP + 1];
   return 0;
 }
 

@@ -10,18 +10,22 @@ Same names, argument meaning and error behaviour as the reference:
 * ``marginal_variance_BBQ``             gp_functions.py:376-454
 * ``predict_f``                         gp_functions.py:457-491
 
-Non-SPD contract of ``negative_log_likelihood`` (the objective handed to SciPy).  The reference runs eigsh warm-up
-passes and leaves its loop on a TRUNCATED EIGEN-DECOMPOSITION either when the Cholesky factorisation fails or --
-without ever trying it -- when sigma_n^2 < 1e-3 min|l| and the spectrum decays inside the first 0.05 N eigenvalues
-(:254-301).  That value is not the Cholesky NLL (tests/golden/reference_nonspd.json: +19.37 against -2517.99 on a
-perfectly SPD 1000 x 1000 matrix) and is only reproducible to the eigsh tolerance 1e-3 min|l| from a random start
-vector, so it cannot be a parity target.  Here:
+``negative_log_likelihood`` (the objective handed to SciPy) and the reference's eigen-decomposition exits.  The reference
+runs eigsh passes with a doubling ``neig`` and leaves its loop on a TRUNCATED EIGEN-DECOMPOSITION either when the Cholesky
+factorisation fails or -- without ever trying it -- when the ``neig``-th eigenvalue of Ky drops below
+``clip_eig = max(1e-3 min|l|, 1e-10)`` inside the first 0.05 N eigenvalues (:254-301; only possible when
+sigma_n^2 <= clip_eig).  That value is not the Cholesky NLL (tests/golden/reference_nonspd.json: +19.37 against -2517.99
+on a perfectly SPD 1000 x 1000 matrix).  ``NON_SPD_POLICY`` (per call: ``on_non_spd``) selects what happens:
 
-* whenever the covariance matrix factorises, the value IS ``negative_log_likelihood_cholesky`` (north-star target a3);
-* when it does not, ``NON_SPD_POLICY`` decides: ``"jitter"`` (default) retries on the device with a growing diagonal
-  jitter (equivalently an inflated sigma_n), emits a ``NonSPDWarning`` and records the event on the backend
-  (``backend.non_spd_events``; ``optimize`` / ``B200GPSurrogate.optimize`` expose the count), so that a caller can see
-  that the optimiser visited this region; ``"raise"`` lets ``np.linalg.LinAlgError`` propagate.
+* ``"reference"`` (default): the reference's loop, branch for branch, with the eigenpairs from the device solver
+  (``gpb_eigsh`` / ``gpb_nll_eig``: Lanczos with full re-orthogonalisation, deterministic).  The eigsh passes are skipped
+  when they provably cannot change the outcome (sigma_n^2 > clip_eig: every eigenvalue of Ky is at least sigma_n^2), so the
+  usual evaluation is exactly ``negative_log_likelihood_cholesky``.  On the eig exit the value agrees with the reference
+  to the reference's own reproducibility (its ARPACK call starts from a random vector and stops at tol = clip_eig: three
+  runs scatter by 5e-7 relative); a ``NonSPDWarning`` is emitted and the event is recorded on the backend.
+* ``"jitter"``: whenever K does not factorise, retry on the device with a growing diagonal jitter (an inflated sigma_n),
+  ``NonSPDWarning`` + recorded event; never takes the eig exit.
+* ``"raise"``: ``np.linalg.LinAlgError`` propagates.
 """
 import warnings
 
@@ -35,7 +39,7 @@ class NonSPDWarning(RuntimeWarning):
     """The covariance matrix of an NLL evaluation was not positive definite and a jittered one was used instead."""
 
 
-NON_SPD_POLICY = "jitter"        # "jitter" | "raise"; per call: negative_log_likelihood(..., on_non_spd=...)
+NON_SPD_POLICY = "reference"     # "reference" | "jitter" | "raise"; per call: negative_log_likelihood(..., on_non_spd=...)
 JITTER_LADDER = (1e-10, 1e-8, 1e-6, 1e-4, 1e-2)   # relative to sigma_f^2
 
 
@@ -58,21 +62,30 @@ def invert_cholesky(L):
 
 
 def invert(K, neig=0, tol=1e-10, eps=1e-6, max_iter=1000):
-    """Inverse of an SPD matrix via Cholesky (gp_functions.py:325-349).
-
-    Like the reference, a failed factorisation is retried once with ``eps`` added to the diagonal (:343-346).
-    The eigen-decomposition branch (``neig > 0``, :350-373) is not part of the accelerated path.
-    """
-    if neig and 0 < neig <= 0.05 * len(K):
-        raise NotImplementedError("invert(neig > 0): the truncated eigen-decomposition branch (gp_functions.py:350-373) has no "
-                                  "in-package caller and is not implemented on the GPU path; use neig=0")
+    """Inverse of a symmetric positive-definite matrix, gp_functions.py:325-373: through the Cholesky factorisation
+    (retried once with ``eps`` on the diagonal, :340-343) and, for ``0 < neig <= 0.05 len(K)``, the reference's doubling
+    eigsh loop that may leave on ``Q diag(1/w) Q^T`` (:350-369), with the eigenpairs from the device solver."""
     be = shared_backend()
     K = np.asarray(K, dtype=np.float64)
     try:
-        L = be.cholesky(K)
+        L = be.cholesky(K)                                       # :341
     except np.linalg.LinAlgError:
-        L = be.cholesky(K + eps * np.eye(K.shape[0], K.shape[1]))
-    return be.invert_cholesky(L)
+        L = be.cholesky(K + eps * np.eye(K.shape[0], K.shape[1]))    # :343
+    if neig <= 0 or neig > 0.05 * len(K):                        # :344-348
+        return be.invert_cholesky(L)
+    n = len(K)
+    neig = int(neig)
+    w, _ = be.eigsh_matrix(K, neig)                              # :351
+    for _iteration in range(max_iter):                           # :352
+        if neig > 0.05 * n:                                      # :353-357
+            return be.invert_cholesky(L)
+        neig = 2 * neig                                          # :358
+        w, _ = be.eigsh_matrix(K, neig, reuse=True)              # :359
+        if np.abs(w[0] - tol) <= tol or neig >= n:               # :362-363
+            break
+    w = np.array(w)
+    w[(-1e-2 < w) & (w < 0)] = 1e-2                              # :366-367
+    return be.eig_inverse(w, n)                                  # :368-369
 
 
 def negative_log_likelihood_cholesky(hyp, X, y, kernel, eval_gradient=False, log_scale_hyp=False,
@@ -102,18 +115,17 @@ def negative_log_likelihood_cholesky(hyp, X, y, kernel, eval_gradient=False, log
 
 def negative_log_likelihood(hyp, X, y, kernel, eval_gradient=False, log_scale_hyp=False,
                             fixed_sigma_n_value=None, neig=0, max_iter=1000, backend=None, on_non_spd=None):
-    """Objective handed to the optimiser (gp_functions.py:190-270): ``hyp`` on the log10 scale if
-    ``log_scale_hyp``; a fixed sigma_n is appended before evaluation.  ``neig`` / ``max_iter`` are accepted for
-    signature compatibility (they steer the reference's eigsh passes, which are not reproduced).
+    """Objective handed to the optimiser (gp_functions.py:190-301): ``hyp`` on the log10 scale if ``log_scale_hyp``; a
+    fixed sigma_n is appended before evaluation; ``neig`` / ``max_iter`` steer the eigsh passes as in the reference.
 
-    Returns ``negative_log_likelihood_cholesky`` whenever K factorises.  Otherwise see the module docstring:
-    ``on_non_spd`` (default ``NON_SPD_POLICY``) = ``"jitter"`` retries with K + j sigma_f^2 I for j in ``JITTER_LADDER``,
-    warns with ``NonSPDWarning``, appends ``{"jitter": j, "hyp": ...}`` to ``backend.non_spd_events`` and returns that
-    NLL (gradient by the chain rule through the inflated noise); ``"raise"`` propagates ``np.linalg.LinAlgError``.
+    ``on_non_spd`` (default ``NON_SPD_POLICY``, see the module docstring): ``"reference"`` follows the reference's loop
+    including its truncated-eigen-decomposition exit; ``"jitter"`` retries a failed factorisation with
+    K + j sigma_f^2 I for j in ``JITTER_LADDER``; ``"raise"`` propagates ``np.linalg.LinAlgError``.  The eig exit and the
+    jitter retry emit a ``NonSPDWarning`` and append an event to ``backend.non_spd_events``.
     """
     policy = on_non_spd or NON_SPD_POLICY
-    if policy not in ("jitter", "raise"):
-        raise ValueError(f"on_non_spd must be 'jitter' or 'raise', got {policy!r}")
+    if policy not in ("reference", "jitter", "raise"):
+        raise ValueError(f"on_non_spd must be 'reference', 'jitter' or 'raise', got {policy!r}")
     hyp = np.asarray(hyp, dtype=np.float64)
     if log_scale_hyp:
         hyp = 10**hyp                      # :239-240
@@ -124,6 +136,8 @@ def negative_log_likelihood(hyp, X, y, kernel, eval_gradient=False, log_scale_hy
         backend = shared_backend()
         Xc, yc = _train_arrays(X, y)
         backend.set_train(Xc, yc)
+    if policy == "reference":
+        return _nll_reference_loop(hyp, X, y, kernel, eval_gradient, log_scale_hyp, fixed_sigma_n, neig, max_iter, backend)
     try:
         return negative_log_likelihood_cholesky(hyp, X, y, kernel, eval_gradient=eval_gradient,
                                                 log_scale_hyp=log_scale_hyp, fixed_sigma_n=fixed_sigma_n,
@@ -156,6 +170,65 @@ def negative_log_likelihood(hyp, X, y, kernel, eval_gradient=False, log_scale_hy
             dnll = dnll * (hyp * np.log(10))
         return nll, dnll
     raise np.linalg.LinAlgError("covariance matrix is not positive definite even with diagonal jitter")
+
+
+def _nll_reference_loop(hyp, X, y, kernel, eval_gradient, log_scale_hyp, fixed_sigma_n, neig, max_iter, backend):
+    """The loop of gp_functions.py:254-301 on the linear-scale ``hyp`` (sigma_n already appended).
+
+    eigsh -> ``backend.eigsh`` (device Lanczos; passes with growing ``neig`` continue one run), the Cholesky attempt ->
+    ``negative_log_likelihood_cholesky``, the exit -> ``backend.nll_eig``.  An eigsh pass whose outcome is known in advance
+    is not run: every eigenvalue of Ky = K + sigma_n^2 I is at least sigma_n^2 (K is positive semi-definite for the RBF and
+    Matern kernels), so ``w[0] <= clip_eig`` (:280) cannot hold while sigma_n^2 exceeds clip_eig by more than the rounding
+    of the spectrum -- until a factorisation has failed, which shows that the numerical spectrum is not what the exact
+    one promises.
+    """
+    kind = kernel_kind(kernel)
+    n = backend.n
+    clip_eig = max(1e-3 * min(abs(hyp[:-2])), 1e-10)             # :245
+    sf2, sn2 = float(hyp[-2]) ** 2, float(hyp[-1]) ** 2
+    spectrum_rounding = 64 * np.finfo(float).eps * (n * sf2 + sn2)      # trace(Ky) bounds the largest eigenvalue
+    eigenvalues_matter = not (sn2 - spectrum_rounding > clip_eig) or max_iter <= 0
+    neig = max(int(neig), 1)                                     # :256
+    iteration = 0
+    failed = 0
+    w = None
+    while True:                                                  # :257
+        if not neig or neig > 0.05 * n:                          # :258-272
+            try:
+                return negative_log_likelihood_cholesky(hyp, X, y, kernel, eval_gradient=eval_gradient,
+                                                        log_scale_hyp=log_scale_hyp, fixed_sigma_n=fixed_sigma_n,
+                                                        backend=backend)
+            except np.linalg.LinAlgError:
+                failed += 1                                      # the reference prints "Warning! Fallback to eig solver!"
+                eigenvalues_matter = True
+        k_used = min(neig, n)
+        w = backend.eigsh(kind, hyp, k_used) if eigenvalues_matter else None      # :273-275
+        if iteration >= max_iter:                                # :276-278 (``iteration`` is never incremented upstream)
+            break
+        neig *= 2                                                # :279
+        if (w is not None and w[0] <= clip_eig) or neig >= n:    # :280
+            break
+    if w is None:                                                # left by ``neig >= n`` with the passes skipped
+        w = backend.eigsh(kind, hyp, k_used)
+    backend.non_spd_events.append({"branch": "eig", "k": int(k_used), "neig": int(neig), "failed_cholesky": failed,
+                                   "hyp": hyp.copy()})
+    warnings.warn(NonSPDWarning(
+        f"negative_log_likelihood left the Cholesky branch at hyp={hyp.tolist()}: NLL from the {k_used} largest "
+        f"eigenpairs (gp_functions.py:283-301), {failed} failed factorisation(s), smallest kept eigenvalue {w[0]:.3e}"),
+        stacklevel=3)
+    neig_term = min(neig, n)                                     # :286
+    if not eval_gradient:
+        return backend.nll_eig(neig_term)
+    try:
+        nll, dnll = backend.nll_eig(neig_term, want_grad=True, n_params=hyp.size)   # :291-294
+    except np.linalg.LinAlgError as exc:         # invert(Ky) failed even with the diagonal shifts (the reference raises too)
+        raise np.linalg.LinAlgError(f"{exc}; eig-branch gradient at hyp={hyp.tolist()}") from None
+    if fixed_sigma_n:                                            # :295-297
+        dnll = dnll[:-1]
+        hyp = hyp[:-1]
+    if log_scale_hyp:                                            # :298-300
+        dnll = dnll * (hyp * np.log(10))
+    return nll, dnll
 
 
 def optimize(xtrain, ytrain, a0, kernel, fixed_sigma_n=False, eval_gradient=False, return_hess_inv=False,

@@ -611,52 +611,85 @@ def test_linear_embedding_kernel_matrix(backend, golden):
 
 
 def test_non_spd_contract(backend):
-    """The non-SPD contract of gp_functions.negative_log_likelihood (module docstring): Cholesky value whenever K
-    factorises; otherwise jitter retry + NonSPDWarning + a recorded event, or LinAlgError with on_non_spd="raise".
-    Pinned against tests/golden/reference_nonspd.json (generated from the unmodified reference)."""
+    """The policies of gp_functions.negative_log_likelihood (module docstring) on the two regimes where the reference
+    leaves the Cholesky branch, pinned against tests/golden/reference_nonspd.json (generated from the unmodified
+    reference): "reference" (default) returns the reference's truncated-eigen-decomposition numbers, "jitter" the Cholesky
+    NLL of a jittered matrix, "raise" a LinAlgError."""
     import json
     import warnings
 
-    from profit_b200 import RBF, B200GPSurrogate, gp_functions as gpf
+    from test_oracle import nonspd_problems
+
+    from profit_b200 import RBF, B200GPSurrogate, Matern52, gp_functions as gpf
 
     gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_nonspd.json")))
-    # (1) the survey's quirk case: the reference leaves on the eig branch (+19.37) although K is SPD; the drop-in
-    # returns the Cholesky NLL -- the reference's own negative_log_likelihood_cholesky value -- without any warning
+    P = nonspd_problems()
+    be = gpf.shared_backend()
+    # (1) the survey's quirk case: K is SPD, but sigma_n^2 < clip_eig and the 8th eigenvalue is below clip_eig, so the
+    # reference leaves on the eig branch (+19.37, not the Cholesky NLL -2517.99) -- and so does the drop-in.  Tolerance:
+    # the reference's three stored runs scatter by 5e-7 relative (random ARPACK start vector, tol = 1e-3 min|l|).
     q = gold["quirk"]
-    X = np.linspace(0.0, 1.0, q["N"]).reshape(-1, 1)
-    y = np.sin(3 * X[:, 0]) + 0.02 * np.random.default_rng(q["noise_seed"]).standard_normal(q["N"])
+    X, y = P["quirk"]
     hyp = np.array(q["hyp"])
+    be.non_spd_events = []
+    with pytest.warns(gpf.NonSPDWarning, match="left the Cholesky branch"):
+        nll, g = gpf.negative_log_likelihood(np.log10(hyp), X, y, RBF, eval_gradient=True, log_scale_hyp=True)
+    assert all(abs(nll - r["nll"]) <= 5e-6 * abs(r["nll"]) for r in q["a4_eig_branch_runs"]), nll
+    assert rel_err(g, q["a4_eig_branch_grad_log10"]) <= 1e-6
+    ev = be.non_spd_events[-1]
+    assert (ev["branch"], ev["k"], ev["neig"], ev["failed_cholesky"]) == ("eig", 8, 16, 0)
+    # against the oracle's restatement of the same loop with LAPACK eigenpairs.  The value itself is ill-conditioned: the
+    # 8th eigenvalue (4.0000226e-4) sits 6e-6 relative above the sigma_n^2 cluster, so its eigenvector -- and with it
+    # (q^T y)^2 / w -- moves at the 1e-6 level between any two eigen-solvers (LAPACK on two hosts: 2e-6).
+    o_nll, o_g = oracle.nll_full(np.log10(hyp), X, y, oracle.rbf, True, True)
+    assert abs(nll - o_nll) <= 1e-5 * abs(o_nll) and rel_err(g, o_g) <= 1e-6
+    again = gpf.negative_log_likelihood(np.log10(hyp), X, y, RBF, eval_gradient=True, log_scale_hyp=True)
+    assert again[0] == nll and np.array_equal(again[1], g)                          # bit-reproducible
+    # the other policies on the same input: the Cholesky NLL of the reference's own negative_log_likelihood_cholesky
     with warnings.catch_warnings():
         warnings.simplefilter("error", gpf.NonSPDWarning)
-        nll, g = gpf.negative_log_likelihood(np.log10(hyp), X, y, RBF, eval_gradient=True, log_scale_hyp=True)
-    assert abs(nll - q["a3_nll"]) <= 1e-9 * abs(q["a3_nll"])
-    assert np.all(np.abs(g / (hyp * np.log(10)) - q["a3_grad"]) <= 2e-7 * np.abs(q["a3_grad"]))   # cond(K) ~ 1e7
-    assert all(abs(r["nll"] - 19.37) < 0.01 for r in q["a4_eig_branch_runs"])     # what upstream returns instead
+        nll_c, g_c = gpf.negative_log_likelihood(np.log10(hyp), X, y, RBF, eval_gradient=True, log_scale_hyp=True,
+                                                 on_non_spd="jitter")
+    assert abs(nll_c - q["a3_nll"]) <= 1e-9 * abs(q["a3_nll"])
+    assert np.all(np.abs(g_c / (hyp * np.log(10)) - q["a3_grad"]) <= 2e-7 * np.abs(q["a3_grad"]))   # cond(K) ~ 1e7
 
     # (2) exactly singular K (every point three times, no noise): the Cholesky twin raises like the reference's
     s = gold["singular"]
-    Xs = np.repeat(np.random.default_rng(0).random((10, 2)), 3, axis=0)
-    ys = np.sin(Xs[:, 0])
+    Xs, ys = P["singular"]
     hs = np.array(s["hyp"])
     assert s["a3"] == "LinAlgError"
     with pytest.raises(np.linalg.LinAlgError):
         gpf.negative_log_likelihood_cholesky(np.array([0.5, 1.0, 0.0]), Xs, ys, RBF, eval_gradient=True)
     with pytest.raises(np.linalg.LinAlgError):
         gpf.negative_log_likelihood(np.log10(hs), Xs, ys, RBF, log_scale_hyp=True, on_non_spd="raise")
-    # default policy: warning + event + the Cholesky NLL of K + j sf^2 I for the first j of the ladder that factorises
-    be = gpf.shared_backend()
+    # default: the reference's exit after four failed factorisations, eigenvalues clipped at 1e-10 (-47.04)
+    be.non_spd_events = []
+    with pytest.warns(gpf.NonSPDWarning, match="left the Cholesky branch"):
+        nll, g = gpf.negative_log_likelihood(hs, Xs, ys, RBF, eval_gradient=True)
+    assert abs(nll - s["a4_eig_branch_nll"]) <= 1e-9 * abs(nll), nll
+    assert np.allclose(g, s["a4_eig_branch_grad_linear"], rtol=1e-5, atol=1e-9)
+    assert be.non_spd_events[-1]["failed_cholesky"] == s["fallback_warnings"] == 4 and be.non_spd_events[-1]["k"] == 16
+    # "jitter": warning + event + the Cholesky NLL of K + j sf^2 I for the first j of the ladder that factorises
     be.non_spd_events = []
     with pytest.warns(gpf.NonSPDWarning, match="diagonal jitter"):
-        nll, g = gpf.negative_log_likelihood(np.log10(hs), Xs, ys, RBF, eval_gradient=True, log_scale_hyp=True)
+        nll, g = gpf.negative_log_likelihood(np.log10(hs), Xs, ys, RBF, eval_gradient=True, log_scale_hyp=True,
+                                             on_non_spd="jitter")
     assert np.isfinite(nll) and np.all(np.isfinite(g)) and g.shape == (3,)
     assert len(be.non_spd_events) == 1 and be.non_spd_events[0]["jitter"] in gpf.JITTER_LADDER
     j = be.non_spd_events[0]["jitter"]
     ref = oracle.nll_cholesky(np.array([hs[0], hs[1], np.sqrt(hs[2] ** 2 + j * hs[1] ** 2)]), Xs, ys, oracle.rbf)
     assert abs(nll - ref) <= 1e-6 * abs(ref)            # K is singular up to the jitter: cond ~ 1 / j
-    # the reference returns its truncated-eig number here (-47.04); recorded so that the difference is documented
-    assert abs(s["a4_eig_branch_nll"] + 47.04) < 0.01 and abs(nll - s["a4_eig_branch_nll"]) > 1.0
 
-    # (3) a fit that visits the region reports it
+    # (3) Matern-5/2 ARD in 2-D, sigma_n^2 < clip_eig (the oracle callable inside the reference's own loop)
+    m = gold["matern_quirk"]
+    Xm, ym = P["matern_quirk"]
+    with pytest.warns(gpf.NonSPDWarning):
+        nll, g = gpf.negative_log_likelihood(np.array(m["hyp"]), Xm, ym, Matern52, eval_gradient=True)
+    for run in m["runs"]:
+        assert abs(nll - run["nll"]) <= 1e-8 * abs(run["nll"]) and rel_err(g, run["grad"]) <= 1e-6
+    assert abs(nll - m["a3_nll"]) > 100
+
+    # (4) a fit that visits the region reports it
     sur = B200GPSurrogate()
     with warnings.catch_warnings():
         warnings.simplefilter("ignore", gpf.NonSPDWarning)
@@ -665,8 +698,56 @@ def test_non_spd_contract(backend):
     assert sur.non_spd_evaluations == len(sur.backend.non_spd_events) and sur.non_spd_evaluations >= 1
     with warnings.catch_warnings():
         warnings.simplefilter("ignore", gpf.NonSPDWarning)
-        m, v = sur.predict(Xs[:5])                      # predict tolerates it too (1e-6 retry of gp_functions.invert)
-    assert np.all(np.isfinite(m)) and np.all(v > 0)
+        mm, v = sur.predict(Xs[:5])                     # predict tolerates it too (1e-6 retry of gp_functions.invert)
+    assert np.all(np.isfinite(mm)) and np.all(v > 0)
+
+
+@pytest.mark.parametrize("n,k", [(40, 1), (40, 40), (300, 7), (300, 64), (1000, 33), (2100, 12)])
+def test_device_eigsh_against_lapack(backend, n, k):
+    """gpb_eigsh_matrix (Lanczos + implicit QL on the device, the twin of scipy's eigsh at gp_functions.py:273,351)
+    against numpy.linalg.eigh: eigenvalues to 1e-12 |lambda_max|, residuals and orthonormality of the vectors; on kernel
+    matrices (fast-decaying spectrum on top of a sigma_n^2 cluster) and on a random symmetric indefinite matrix."""
+    rng = np.random.default_rng(n + k)
+    X = rng.random((n, 2))
+    for A in (oracle.rbf(X, X, np.array([0.4, 0.7]), 1.3, 1e-3),
+              oracle.matern52(X, X, 0.8, 1.0, 0.05),
+              (lambda B: 0.5 * (B + B.T))(rng.standard_normal((n, n)))):
+        w, Q = backend.eigsh_matrix(A, k, want_vectors=True)
+        ref = np.linalg.eigvalsh(A)
+        scale = np.abs(ref).max()
+        assert w.shape == (k,) and Q.shape == (n, k) and np.all(np.diff(w) >= 0)
+        assert np.max(np.abs(w - ref[n - k:])) <= 1e-12 * scale, np.max(np.abs(w - ref[n - k:])) / scale
+        assert np.max(np.abs(A @ Q - Q * w)) <= 1e-11 * scale
+        assert np.max(np.abs(Q.T @ Q - np.eye(k))) <= 1e-12
+        # a larger request continues the same run
+        if 2 * k <= n:
+            w2, _ = backend.eigsh_matrix(A, 2 * k, reuse=True)
+            assert np.max(np.abs(w2 - ref[n - 2 * k:])) <= 1e-12 * scale
+
+
+def test_invert_eig_branch(backend):
+    """gp_functions.invert(K, neig > 0): the doubling eigsh loop of gp_functions.py:350-369 leaves on Q diag(1/w) Q^T;
+    checked against the unmodified reference's result (through its four non-zero eigenvalues and a matrix-vector probe)
+    and against the oracle's restatement; neig = 0 and neig > 0.05 n stay on the Cholesky branch."""
+    import json
+
+    from test_oracle import nonspd_problems
+
+    from profit_b200 import gp_functions as gpf
+
+    e = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_nonspd.json")))["invert_eig"]
+    K = nonspd_problems()["invert_eig"]
+    Kinv = gpf.invert(K, neig=e["neig"])
+    w = np.linalg.eigvalsh(Kinv)
+    # the kept eigenvalue 1e-10 sits 1e-10 |lambda_max| above zero: both eigen-solvers resolve it to ~1e-6 relative
+    assert np.allclose(w[-4:], e["top_eigenvalues_of_result"], rtol=1e-5) and int((np.abs(w) > 1e-3).sum()) == 4
+    assert np.allclose(Kinv @ np.linspace(-1.0, 1.0, e["n"]), e["probe"], rtol=1e-4, atol=1e-5 * e["frobenius_norm"])
+    ref = oracle.invert_full(K, neig=e["neig"])
+    assert np.max(np.abs(Kinv - ref)) <= 1e-5 * np.abs(ref).max()
+    X = np.random.default_rng(5).random((120, 3))
+    A = oracle.rbf(X, X, 0.5, 1.0, 0.2)
+    for neig in (0, 7):                                   # 7 > 0.05 * 120: Cholesky branch (:344-348)
+        assert np.max(np.abs(gpf.invert(A, neig=neig) @ A - np.eye(120))) <= 1e-9
 
 
 def test_predict_f_full_covariance(backend, golden):

@@ -30,11 +30,34 @@ class OracleBackedFake:
         self.noise_override = None
         self.X, self.y = np.array(X), np.array(y)
         self.n_out = 1 if self.y.ndim == 1 else self.y.shape[1]
+        self.n = len(self.X)
 
     def nll(self, kind, theta, want_grad=False):
         self.calls += 1
         kern = oracle.rbf if kind == 0 else oracle.matern52
         return oracle.nll_cholesky(np.asarray(theta), self.X, self.y, kern, eval_gradient=want_grad)
+
+    # -- the truncated eigen-decomposition exit (GPBackend.eigsh / nll_eig)
+    def eigsh(self, kind, theta, k):
+        self.eig_calls = getattr(self, "eig_calls", 0) + 1
+        kern = oracle.rbf if kind == 0 else oracle.matern52
+        theta = np.asarray(theta)
+        self._eig_kern, self._eig_theta = kern, theta
+        Ky = kern(self.X, self.X, theta[:-2], theta[-2], theta[-1])
+        self._eig_w, self._eig_Q = oracle.top_eigenpairs(Ky, k)
+        return self._eig_w.copy()
+
+    def nll_eig(self, neig_term, want_grad=False, n_params=None):
+        w = np.maximum(self._eig_w, 1e-10)
+        y = self.y.reshape(len(self.X))
+        alpha = self._eig_Q @ ((self._eig_Q.T @ y) / w)
+        nll = 0.5 * (y @ alpha + np.sum(np.log(w)) + neig_term * np.log(2 * np.pi))
+        if not want_grad:
+            return float(nll)
+        th = self._eig_theta
+        Ky, dKy = self._eig_kern(self.X, self.X, th[:-2], th[-2], th[-1], eval_gradient=True)
+        A = oracle.invert_full(Ky) - np.outer(alpha, alpha)
+        return float(nll), 0.5 * np.einsum("ij,jip->p", A, dKy)
 
     def mean_pairwise_distance(self, X):
         X = np.asarray(X, dtype=float)
@@ -68,6 +91,63 @@ def test_select_kernel():
     assert kernels.RBF.__name__ == "RBF" and kernels.Matern52.__name__ == "Matern52"
     with pytest.raises(RuntimeError, match="not implemented"):       # custom_surrogate.py:238
         kernels.select_kernel("LinearEmbedding")
+
+
+def test_reference_loop_takes_the_same_exits_as_the_reference():
+    """negative_log_likelihood(on_non_spd="reference") against oracle.nll_full (the restated loop of
+    gp_functions.py:254-301, itself pinned to the unmodified reference in test_oracle.py): the quirk exit on an SPD matrix,
+    the exit after failed factorisations, and the usual Cholesky exit with the eigsh passes skipped."""
+    import warnings
+
+    be = OracleBackedFake()
+    # (1) quirk: sigma_n^2 < clip_eig and a fast-decaying spectrum -> eig exit at k = 8 without any factorisation
+    X = np.linspace(0.0, 1.0, 300).reshape(-1, 1)
+    y = np.sin(3 * X[:, 0]) + 0.02 * np.random.default_rng(7).standard_normal(300)
+    hyp = np.array([1.0, 1.5, 0.02])
+    be.set_train(X, y)
+    tr = {}
+    ref = oracle.nll_full(np.log10(hyp), X, y, oracle.rbf, True, True, trace=tr)
+    assert tr["branch"] == "eig" and tr["failed_cholesky"] == 0
+    with pytest.warns(gpf.NonSPDWarning, match="left the Cholesky branch"):
+        got = gpf.negative_log_likelihood(np.log10(hyp), X, y, kernels.RBF, True, True, backend=be)
+    assert rel_err(got[0], ref[0]) < 1e-12 and rel_err(got[1], ref[1]) < 1e-9
+    assert be.non_spd_events[-1]["k"] == tr["k"] and be.non_spd_events[-1]["neig"] == tr["neig"] and be.calls == 0
+    # fixed sigma_n, no gradient
+    ref = oracle.nll_full(np.log10(hyp[:-1]), X, y, oracle.rbf, False, True, fixed_sigma_n_value=0.02)
+    with pytest.warns(gpf.NonSPDWarning):
+        got = gpf.negative_log_likelihood(np.log10(hyp[:-1]), X, y, kernels.RBF, False, True, 0.02, backend=be)
+    assert rel_err(got, ref) < 1e-12
+    # (2) triplicated points without noise: every factorisation fails, exit on the clipped eigenvalues
+    Xs = np.repeat(np.random.default_rng(0).random((10, 2)), 3, axis=0)
+    ys = np.sin(Xs[:, 0])
+    hs = np.array([0.5, 1.0, 1e-12])
+    be.set_train(Xs, ys)
+    tr = {}
+    ref = oracle.nll_full(hs, Xs, ys, oracle.rbf, True, False, trace=tr)
+    assert tr["branch"] == "eig" and tr["failed_cholesky"] == 4
+    with pytest.warns(gpf.NonSPDWarning):
+        got = gpf.negative_log_likelihood(hs, Xs, ys, kernels.RBF, True, False, backend=be)
+    assert rel_err(got[0], ref[0]) < 1e-10 and rel_err(got[1], ref[1]) < 1e-6
+    assert be.non_spd_events[-1]["failed_cholesky"] == 4
+    # (3) the usual case: sigma_n^2 > clip_eig -> no eigsh pass is run at all and the value is the Cholesky NLL
+    X3, y3 = oracle.synthetic_problem(150, 3)
+    th = np.array([0.7, 0.9, 1.1, 1.5, 0.3])
+    be.set_train(X3, y3)
+    be.eig_calls = 0
+    with warnings.catch_warnings():
+        warnings.simplefilter("error", gpf.NonSPDWarning)
+        got = gpf.negative_log_likelihood(th, X3, y3, kernels.Matern52, True, False, backend=be)
+    tr = {}
+    ref = oracle.nll_full(th, X3, y3, oracle.matern52, True, False, trace=tr)
+    assert tr["branch"] == "cholesky" and be.eig_calls == 0
+    assert rel_err(got[0], ref[0]) < 1e-12 and rel_err(got[1], ref[1]) < 1e-10
+    # (4) sigma_n^2 < clip_eig but a slowly decaying spectrum: the passes run, nothing drops below clip_eig, Cholesky exit
+    th4 = np.array([0.05, 0.05, 0.05, 1.5, 0.005])
+    be.eig_calls = 0
+    tr = {}
+    ref = oracle.nll_full(th4, X3, y3, oracle.matern52, False, False, trace=tr)
+    got = gpf.negative_log_likelihood(th4, X3, y3, kernels.Matern52, False, False, backend=be)
+    assert tr["branch"] == "cholesky" and be.eig_calls == 3 and rel_err(got, ref) < 1e-12      # neig = 1, 2, 4; 8 > 0.05 N
 
 
 @pytest.mark.parametrize("idx", [0, 3])

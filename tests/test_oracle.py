@@ -228,3 +228,63 @@ def test_oracle_against_the_reference_at_c1_shape():
     nll, g = oracle.nll_cholesky(np.array(c["theta"]), X, y, oracle.rbf, eval_gradient=True, block=512)
     assert abs(nll - c["nll"]) <= 1e-11 * abs(c["nll"])
     assert np.max(np.abs(g - np.array(c["grad"])) / np.abs(c["grad"])) <= 1e-9
+
+
+def _nonspd_golden():
+    import json
+
+    return json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_nonspd.json")))
+
+
+def nonspd_problems():
+    """The inputs of tests/golden/make_golden_nonspd.py (shared with the GPU twin of this test)."""
+    X = np.linspace(0.0, 1.0, 1000).reshape(-1, 1)
+    y = np.sin(3 * X[:, 0]) + 0.02 * np.random.default_rng(7).standard_normal(1000)
+    Xs = np.repeat(np.random.default_rng(0).random((10, 2)), 3, axis=0)
+    ys = np.sin(Xs[:, 0])
+    Xm = np.random.default_rng(3).random((400, 2))
+    ym = np.sin(3 * Xm[:, 0]) * np.cos(2 * Xm[:, 1]) + 0.01 * np.random.default_rng(4).standard_normal(400)
+    n = 100
+    Qr, _ = np.linalg.qr(np.random.default_rng(11).standard_normal((n, n)))
+    lam = np.concatenate([[1.0, 0.5, 0.25, 1e-10], 1e-12 * np.linspace(1.0, 0.1, n - 4)])
+    Kp = (Qr * lam) @ Qr.T
+    return {"quirk": (X, y), "singular": (Xs, ys), "matern_quirk": (Xm, ym), "invert_eig": 0.5 * (Kp + Kp.T)}
+
+
+def test_nll_full_takes_the_reference_eig_exits():
+    """oracle.nll_full / invert_full (the whole loops of gp_functions.py:254-301 and :350-373) against values of the
+    unmodified reference.  Tolerances: the reference's eigsh starts from a random vector and stops at tol = 1e-3 min|l|
+    (three stored runs scatter by ~5e-7 relative); the oracle takes the eigenpairs from LAPACK."""
+    gold = _nonspd_golden()
+    P = nonspd_problems()
+    q = gold["quirk"]
+    tr = {}
+    nll, g = oracle.nll_full(np.log10(q["hyp"]), *P["quirk"], oracle.rbf, True, True, trace=tr)
+    assert tr == {"branch": "eig", "neig": 16, "k": 8, "failed_cholesky": 0, "w_min": tr["w_min"]}
+    for run in q["a4_eig_branch_runs"]:
+        assert abs(nll - run["nll"]) <= 5e-6 * abs(run["nll"])
+    assert rel_err(g, q["a4_eig_branch_grad_log10"]) <= 1e-6
+    assert abs(nll - q["a3_nll"]) > 1000                      # and it is NOT the Cholesky NLL of the same SPD matrix
+    s = gold["singular"]
+    tr = {}
+    nll, g = oracle.nll_full(np.array(s["hyp"]), *P["singular"], oracle.rbf, True, False, trace=tr)
+    assert tr["branch"] == "eig" and tr["failed_cholesky"] == s["fallback_warnings"] == 4 and tr["k"] == 16
+    assert abs(nll - s["a4_eig_branch_nll"]) <= 1e-10 * abs(nll)
+    assert np.allclose(g, s["a4_eig_branch_grad_linear"], rtol=1e-6, atol=1e-10)
+    m = gold["matern_quirk"]
+    tr = {}
+    nll, g = oracle.nll_full(np.array(m["hyp"]), *P["matern_quirk"], oracle.matern52, True, False, trace=tr)
+    assert tr["branch"] == "eig" and tr["failed_cholesky"] == 0
+    for run in m["runs"]:
+        assert abs(nll - run["nll"]) <= 1e-8 * abs(run["nll"]) and rel_err(g, run["grad"]) <= 1e-6
+    e = gold["invert_eig"]
+    tr = {}
+    Kinv = oracle.invert_full(P["invert_eig"], neig=e["neig"], trace=tr)
+    assert tr == {"branch": "eig", "neig": 4}
+    w = np.linalg.eigvalsh(Kinv)
+    assert np.allclose(w[-4:], e["top_eigenvalues_of_result"], rtol=1e-6) and int((np.abs(w) > 1e-3).sum()) == 4
+    assert np.allclose(Kinv @ np.linspace(-1.0, 1.0, e["n"]), e["probe"], rtol=1e-5, atol=1e-5 * e["frobenius_norm"])
+    # neig = 0 (what every in-package caller passes) stays on the Cholesky branch
+    tr = {}
+    K = oracle.rbf(*[P["quirk"][0][:50]] * 2, 0.3, 1.0, 0.1)
+    assert np.allclose(oracle.invert_full(K, trace=tr) @ K, np.eye(50), atol=1e-8) and tr["branch"] == "cholesky"

@@ -274,10 +274,20 @@ Ym = Ym + np.array([0.25, 1.0]) * rng.standard_normal(Ym.shape)          # noisy
 Xq = np.column_stack([2 * Xc[:50, 0], 4 * Xc[:50, 1] - 1])
 mos = {}
 for label in ("CustomMultiOutputGP", "B200MultiOutputGP"):
-    cm = mo_config(label)
-    mo = Surrogate.from_config(cm["fit"], cm)
-    assert len(mo.input_encoders) >= 1 and len(mo.output_encoders) >= 1, "default encoders expected"
-    mo.train(Xm, Ym)
+    # The reference's children are fitted by finite-difference BFGS through its eigsh passes, which start from ARPACK's
+    # running random state (gp_functions.py:254-280): its fit is not reproducible and occasionally raises LinAlgError
+    # inside its own invert() (gp_functions.py:346).  Give the reference a few attempts; the B200 class gets exactly one.
+    for attempt in range(5 if label == "CustomMultiOutputGP" else 1):
+        cm = mo_config(label)
+        mo = Surrogate.from_config(cm["fit"], cm)
+        assert len(mo.input_encoders) >= 1 and len(mo.output_encoders) >= 1, "default encoders expected"
+        try:
+            mo.train(Xm, Ym)
+            break
+        except np.linalg.LinAlgError:
+            if label != "CustomMultiOutputGP" or attempt == 4:
+                raise
+            print("reference fit raised LinAlgError in its own invert(); retrying")
     mos[label] = mo
 mo_r, mo_g = mos["CustomMultiOutputGP"], mos["B200MultiOutputGP"]
 assert type(mo_g) is ps.B200MultiOutputGPSurrogate and mo_g.trained
