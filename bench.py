@@ -32,7 +32,7 @@ N_TRAIN_PRED, M_FULL = 8192, 1 << 22     # BASELINE configs[3]
 N_TRAIN_C4, DIM_C4 = 8192, 16            # BASELINE configs[4]
 METRIC = "NLL+grad evals/s (N=16384, D=10, fp64)"
 UNIT = "evals/s"
-NCU_DRAM_BYTES_SYRK_LAUNCH = 37.34e9     # profiles/r01_ncu_dgemm_syrk.txt (dram__bytes_read.sum + dram__bytes_write.sum)
+NCU_DRAM_BYTES_SYRK_LAUNCH = 15.49e9     # profiles/r02_ncu_syrk.txt (dram__bytes_read.sum 14.38 GB + dram__bytes_write.sum 1.11 GB)
 NCU_DRAM_BYTES_COLSQ_LAUNCH = None       # filled from profiles/r02_ncu_predict_colsq.txt once captured
 NCU_DRAM_BYTES_COLSQ_NOTE = "no ncu capture of the EPI_COLSQ launch yet"
 DMMA_CEILING_TFLOPS = 37.05              # profiles/r01_probe_fp64_dmma.txt: register-resident DMMA.8x8x4 issue rate
@@ -583,7 +583,7 @@ def run_gpu(args):
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": NCU_DRAM_BYTES_SYRK_LAUNCH,
                 "traffic_note": "dram__bytes_read+write of the K^-1 = U U^T launch (1.466e12 flop) from "
-                                "profiles/r01_ncu_dgemm_syrk.txt; compute-bound, tile re-reads served by L2/HBM",
+                                "profiles/r02_ncu_syrk.txt (super-tile task order; round 1: 37.3 GB); algorithmic minimum 2.1 GB (read U, write K^-1); compute-bound, DMMA sub-pipe 97.3 % active",
                 "kernel": "gpb::dgemm_tasks_kernel (DMMA.8x8x4 tile GEMM behind potrf / trtri / syrk)",
                 "algorithmic_flops_per_eval": float(N_TRAIN) ** 3,
                 "dense_ms_per_eval": dense_ms,

@@ -361,6 +361,8 @@ int g_early_mask = 0xF;         // which of the cut points {1/4, 1/2, 3/4, 7/8} 
 // Small launches are latency-bound (one CTA takes ~15 us for a 128x64x128 tile on its own SM): cut the tiles finer
 // so the same work spreads over more SMs.  `coarse` is the configuration used for large launches.
 int g_super = 12;                // super-tile edge of the K^-1 = U U^T launch in 128-blocks, ~sqrt(148) (env GPB_SUPER; 0 = off)
+int g_pred_super_m = 12;         // super-tile of the predict column-norm GEMM: row tiles of W x candidate tiles (env GPB_PRED_SUPER_M / _C;
+int g_pred_super_c = 12;         // M = 0: plain order).  12 x 12 blocks = 288 128x64 CTAs ~ the 296 resident ones
 int g_super_trtri = 0;           // the same for the triangular-inverse launches (env GPB_SUPER_TRTRI): measured +7 % time at
                                  // N=16384 (the heaviest-first order matters more there than the L2 hit rate), so off
 int g_fine_below = 148;          // launches with fewer 128-blocks than this use the fine tiles (env GPB_FINE_BELOW)
@@ -1591,6 +1593,8 @@ int gpb_create(int device, gpb_handle_t* out) {
   if (const char* e = getenv("GPB_TAIL_BLOCKS")) g_tail_blocks = std::max(0, atoi(e));
   if (const char* e = getenv("GPB_SUPER")) g_super = std::max(0, std::min(64, atoi(e)));
   if (const char* e = getenv("GPB_SUPER_TRTRI")) g_super_trtri = std::max(0, std::min(64, atoi(e)));
+  if (const char* e = getenv("GPB_PRED_SUPER_M")) g_pred_super_m = std::max(0, std::min(128, atoi(e)));
+  if (const char* e = getenv("GPB_PRED_SUPER_C")) g_pred_super_c = std::max(1, std::min(512, atoi(e)));
   if (const char* e = getenv("GPB_DIAG4")) g_diag4 = std::max(0, std::min(2, atoi(e)));
   *out = h;
   return 0;
@@ -1983,10 +1987,25 @@ int gpb_predict(gpb_handle_t h, const double* Xc, long long M, int add_data_vari
     // candidate rows beyond the last real one are never written by cross_mean_kernel: keep them finite
     CK(cudaMemsetAsync(h->dKsT, 0, (size_t)Mc * w.Np * sizeof(double), h->stream));
     h->pred.clear();
-    TaskSink s(h->pred);
-    for (int mt = (int)w.Nb - 1; mt >= 0; --mt)
-      for (long long ct = 0; ct < Mc / 128; ++ct) s.block(cfg, mt * 128, 0, (int)ct * 128, 0, 8 * (mt + 1), 0, (int)ct * 128, mt);
-    s.finish(cfg, EPI_COLSQ, M_W, M_KST, M_PART, M_NONE, 1.0, 0.0, false);
+    {  // launch 0: row tiles of W descending (longest k first), candidate tiles ascending -- the ragged last chunk
+       // launches a prefix of every row from this list
+      TaskSink s(h->pred);
+      for (int mt = (int)w.Nb - 1; mt >= 0; --mt)
+        for (long long ct = 0; ct < Mc / 128; ++ct) s.block(cfg, mt * 128, 0, (int)ct * 128, 0, 8 * (mt + 1), 0, (int)ct * 128, mt);
+      s.finish(cfg, EPI_COLSQ, M_W, M_KST, M_PART, M_NONE, 1.0, 0.0, false);
+    }
+    {  // launch 1 (full chunks): the same tiles super-tile by super-tile (see build_syrk_plan).  In the plain order every
+       // candidate panel is streamed from HBM once per row tile of W (ncu: 70.9 GB per 32768 candidates at N=8192); a
+       // g_pred_super_m x g_pred_super_c group of resident CTAs shares its W and candidate slabs through L2 instead.
+      TaskSink s(h->pred);
+      const int Gm = std::max(1, g_pred_super_m), Gc = std::max(1, g_pred_super_c), nct = (int)(Mc / 128);
+      for (int M1 = (int)w.Nb; M1 > 0; M1 -= Gm)
+        for (int C0 = 0; C0 < nct; C0 += Gc)
+          for (int mt = M1 - 1; mt >= std::max(0, M1 - Gm); --mt)
+            for (int ct = C0; ct < std::min(nct, C0 + Gc); ++ct)
+              s.block(cfg, mt * 128, 0, ct * 128, 0, 8 * (mt + 1), 0, ct * 128, mt);
+      s.finish(cfg, EPI_COLSQ, M_W, M_KST, M_PART, M_NONE, 1.0, 0.0, false);
+    }
     if ((rc = upload_plan(h, h->pred))) return rc;
     h->pred_Mc = Mc;
     h->pred_Nb = w.Nb;
@@ -2021,7 +2040,8 @@ int gpb_predict(gpb_handle_t h, const double* Xc, long long M, int add_data_vari
       ep.alpha = 1.0;
       ep.beta = 0.0;
       if (ctiles == Mc / 128) {
-        if ((rc = launch_gemm(h, w, cfg, EPI_COLSQ, M_W, M_KST, h->pred.d_tasks + L.task_off, L.ntasks, ep))) return rc;
+        const Launch& LS = h->pred.launches[g_pred_super_m > 0 ? 1 : 0];
+        if ((rc = launch_gemm(h, w, cfg, EPI_COLSQ, M_W, M_KST, h->pred.d_tasks + LS.task_off, LS.ntasks, ep))) return rc;
       } else {
         // ragged last chunk: tasks are ordered (mt desc, ct asc); launch the first ctiles of every mt row
         for (int r = 0; r < (int)w.Nb; ++r) {

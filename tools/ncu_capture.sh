@@ -47,7 +47,9 @@ run $NCU --set full --import-source on -k regex:potrf_diagr -s 200 -c 1 -o $OUT/
 run $NCU --set full --import-source on -k regex:kernel_matrix_kernel -s 1 -c 1 -o $OUT/prof_kernel_matrix python tools/ncu_target.py kmat > $OUT/ncu6.log 2>&1
 # 4. predict: cross kernel, column-norm GEMM, finish (the 65536-candidate chunk: skip the warm-up instances)
 run $NCU --set full --import-source on -k regex:cross_mean -s 1 -c 1 -o $OUT/prof_cross_mean python tools/ncu_target.py predict > $OUT/ncu7.log 2>&1
-run $NCU --set full --import-source on -k "regex:dgemm_tasks_kernel.*4,\s*(\(int\))?1,\s*(\(int\))?2>" -s 1 -c 1 -o $OUT/prof_predict_colsq python tools/ncu_target.py predict > $OUT/ncu8.log 2>&1
+# the column-norm GEMM launches are the last dgemm_tasks launches of the predict target (the 208 before them belong to the
+# factorisation and the triangular inverse): 208 = warm-up chunk, 209 / 210 = the two halves of the 65536-candidate chunk
+run $NCU --set full --import-source on -k regex:dgemm_tasks -s 209 -c 1 -o $OUT/prof_predict_colsq python tools/ncu_target.py predict > $OUT/ncu8.log 2>&1
 run $NCU --metrics gpu__time_duration.sum -k "regex:cross_mean|dgemm_tasks|finish_variance" --csv --log-file $OUT/launches_predict.csv python tools/ncu_target.py predict > $OUT/ncu9.log 2>&1
 # summarise on the box: the reports themselves are too large to travel back (64 MiB limit on gpurun_out)
 for f in $OUT/prof_*.ncu-rep; do
