@@ -1391,7 +1391,7 @@ void eig_gs_pass(H* h, int cnt, double* c, const double* c_first, double* alpha_
 // Two Gram-Schmidt passes, then more while a pass still removes more than half of the vector (a vector that lies
 // numerically inside span(V) needs them: "twice is enough" only holds for vectors that do not).  norms <- {|w| before,
 // after the first pass, at the end}; alpha_out (device, may be nullptr) <- coefficient along the last basis vector.
-int eig_orthonormalise(H* h, int cnt, double* alpha_out, double norms[3]) {
+int eig_orthonormalise(H* h, int cnt, double* alpha_out, double norms[3], double* alpha_host = nullptr) {
   H::Eig& e = h->eig;
   const int n = e.n;
   double* vnext = e.Vt + (size_t)cnt * n;       // the basis buffer has mcap + 1 rows
@@ -1403,7 +1403,8 @@ int eig_orthonormalise(H* h, int cnt, double* alpha_out, double norms[3]) {
   eig_next_kernel<<<1, 1024, 0, h->stream>>>(e.w, n, vnext, dn + 2);
   h->launches += 3;
   CK(cudaMemcpyAsync(norms, dn, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
+  if (alpha_out && alpha_host) CK(cudaMemcpyAsync(alpha_host, alpha_out, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));   // the one host synchronisation of a regular step
   double prev = norms[1];
   for (int extra = 0; extra < 4 && norms[2] > 0.0 && norms[2] < 0.5 * prev; ++extra) {
     prev = norms[2];
@@ -1431,11 +1432,9 @@ int eig_extend(H* h, int m_target) {
     eig_symv_kernel<<<gr, EIG_BLOCK, 0, h->stream>>>(e.K, n, n, vj, e.w);
     h->launches++;
     double norms[3], alpha_j = 0.0;
-    int rc = eig_orthonormalise(h, j + 1, e.alpha + j, norms);
+    int rc = eig_orthonormalise(h, j + 1, e.alpha + j, norms, &alpha_j);
     if (rc) return rc;
     CK(cudaMemcpyAsync(e.beta + j, e.beta + e.mcap + 2, sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-    CK(cudaMemcpyAsync(&alpha_j, e.alpha + j, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
     if (!std::isfinite(alpha_j) || !std::isfinite(norms[2]))
       return fail(h, -4, "eigsh: non-finite Lanczos coefficients at step " + std::to_string(j + 1));
     e.m = j + 1;
