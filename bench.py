@@ -33,8 +33,10 @@ N_TRAIN_C4, DIM_C4 = 8192, 16            # BASELINE configs[4]
 METRIC = "NLL+grad evals/s (N=16384, D=10, fp64)"
 UNIT = "evals/s"
 NCU_DRAM_BYTES_SYRK_LAUNCH = 15.49e9     # profiles/r02_ncu_syrk.txt (dram__bytes_read.sum 14.38 GB + dram__bytes_write.sum 1.11 GB)
-NCU_DRAM_BYTES_COLSQ_LAUNCH = None       # filled from profiles/r02_ncu_predict_colsq.txt once captured
-NCU_DRAM_BYTES_COLSQ_NOTE = "no ncu capture of the EPI_COLSQ launch yet"
+NCU_DRAM_BYTES_COLSQ_LAUNCH = 28.26e9    # profiles/r02_ncu_predict_colsq.txt (28.11 GB read + 0.15 GB written per launch)
+NCU_DRAM_BYTES_COLSQ_NOTE = ("dram__bytes_read+write of ONE column-norm GEMM launch (32768 candidates x N=8192, 2.2e12 flop, "
+                             "61.6 ms, DMMA sub-pipe 97.5 % active) with the super-tile task order; plain order 71.1 GB "
+                             "(profiles/r02_ncu_predict_colsq_plain_order.txt); algorithmic minimum 2.4 GB (K* chunk + W)")
 DMMA_CEILING_TFLOPS = 37.05              # profiles/r01_probe_fp64_dmma.txt: register-resident DMMA.8x8x4 issue rate
 
 
@@ -161,7 +163,7 @@ def cpu_nll_grad_sample(n_sample):
     dt, cores, tm = cpu_nll_grad_eval(n_sample, want_timings=True)
     r = N_TRAIN / n_sample
     full = tm["cubic"] * r**3 + tm["quadratic"] * r**2
-    return {"value": 1.0 / full, "unit": UNIT, "cores": cores, "kind": "port-extrapolated",
+    return {"value": 1.0 / full, "unit": UNIT, "cores": cores, "kind": "port", "extrapolated": True,
             "sample": f"one NLL+grad eval of the oracle port at N={n_sample}, D={DIM} Matern-5/2: {dt:.2f} s "
                       f"({tm['cubic']:.2f} s O(N^3) phases scaled by {r**3:.0f}, {tm['quadratic']:.2f} s O(N^2 P) phases "
                       f"scaled by {r**2:.0f}) -> {full:.0f} s per eval at N=16384 (EXTRAPOLATED; `--impl reference` "
@@ -197,7 +199,7 @@ def cpu_predict_sample(n_train=4096, chunk=1024, chunks=2):
     r = N_TRAIN_PRED / n_train
     cached = chunk / (t_chunk * r**2)
     uncached = chunk / (t_chunk * r**2 + t_factor * r**3)
-    return {"value": cached, "unit": "candidates/s", "cores": cores, "kind": "port-extrapolated",
+    return {"value": cached, "unit": "candidates/s", "cores": cores, "kind": "port", "extrapolated": True,
             "uncached_value": uncached,
             "sample": f"oracle port of GPSurrogate.predict at N={n_train}, D={DIM} Matern-5/2: factor (alpha, K^-1) "
                       f"{t_factor:.2f} s, {chunks} chunks of {chunk} candidates {t_chunk:.2f} s each; scaled to N={N_TRAIN_PRED} "

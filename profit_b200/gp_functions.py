@@ -27,6 +27,7 @@ on a perfectly SPD 1000 x 1000 matrix).  ``NON_SPD_POLICY`` (per call: ``on_non_
   ``NonSPDWarning`` + recorded event; never takes the eig exit.
 * ``"raise"``: ``np.linalg.LinAlgError`` propagates.
 """
+import os
 import warnings
 
 import numpy as np
@@ -39,7 +40,9 @@ class NonSPDWarning(RuntimeWarning):
     """The covariance matrix of an NLL evaluation was not positive definite and a jittered one was used instead."""
 
 
-NON_SPD_POLICY = "reference"     # "reference" | "jitter" | "raise"; per call: negative_log_likelihood(..., on_non_spd=...)
+# "reference" | "jitter" | "raise"; per call: negative_log_likelihood(..., on_non_spd=...); process-wide default from the
+# environment (PROFIT_B200_NON_SPD=jitter gives the Cholesky NLL -- row a3 of SURVEY.md section 8 -- wherever K factorises)
+NON_SPD_POLICY = os.environ.get("PROFIT_B200_NON_SPD", "reference")
 JITTER_LADDER = (1e-10, 1e-8, 1e-6, 1e-4, 1e-2)   # relative to sigma_f^2
 
 

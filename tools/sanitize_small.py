@@ -1,5 +1,7 @@
 """Small end-to-end pass for compute-sanitizer (memcheck / racecheck / initcheck): every kernel once on ragged small sizes.
-    compute-sanitizer --tool memcheck python tools/sanitize_small.py"""
+    compute-sanitizer --tool memcheck python tools/sanitize_small.py
+(compute-sanitizer is closed on the shared B200 pool of round 2; run plain, the script still touches every kernel on ragged
+sizes and prints values that can be compared with the oracle.)"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
