@@ -273,14 +273,17 @@ __global__ void __launch_bounds__(EIG_BLOCK) eig_nll_kernel(const double* __rest
   if (threadIdx.x == 0) out[0] = 0.5 * (s + neig_term * 1.8378770664093453);   // log(2 pi)
 }
 
-// out[a][b] = sum_i Qt[i][a] Qt[i][b] / w[i]   (K^-1 = Q diag(1/w) Q^T, gp_functions.py:369); grid (ceil(n/EIG_BLOCK), n).
+// out[a][b] = sum_i Qt[i][a] Qt[i][b] / w[i]   (K^-1 = Q diag(1/w) Q^T, gp_functions.py:369); grid (ceil(n/EIG_BLOCK), rows),
+// rows <= 65535: every block row strides over the matrix rows.
 __global__ void __launch_bounds__(EIG_BLOCK) eig_outer_kernel(const double* __restrict__ Qt, long long ldq, int n, int k,
                                                               const double* __restrict__ w, double* __restrict__ out) {
-  const int b = blockIdx.x * EIG_BLOCK + threadIdx.x, a = blockIdx.y;
+  const int b = blockIdx.x * EIG_BLOCK + threadIdx.x;
   if (b >= n) return;
-  double s = 0.0;
-  for (int i = 0; i < k; ++i) s = fma(Qt[(long long)i * ldq + a] / w[i], Qt[(long long)i * ldq + b], s);
-  out[(long long)a * n + b] = s;
+  for (int a = blockIdx.y; a < n; a += gridDim.y) {
+    double s = 0.0;
+    for (int i = 0; i < k; ++i) s = fma(Qt[(long long)i * ldq + a] / w[i], Qt[(long long)i * ldq + b], s);
+    out[(long long)a * n + b] = s;
+  }
 }
 
 }  // namespace gpb

@@ -175,6 +175,12 @@ struct gpb_handle_s {
     bool from_train = false;    // K = Ky(theta) of the resident training set (gpb_eigsh) rather than an uploaded matrix
     std::vector<double> key;    // kind, n_ell, theta...
     std::vector<double> w_host; // the k resident eigenvalues, ascending
+    // the last diagonalisation of the projected problem (size solved_m): Ritz values, last components of their vectors,
+    // descending order, so that a request for more pairs at the same size needs no second QL run
+    std::vector<double> ritz, zlast;
+    std::vector<int> order, sel;
+    int solved_m = 0, vectors_k = 0, vectors_m = 0;
+    double beta_last = 0.0, ritz_scale = 0.0;
   } eig;
 
   cudaEvent_t ev0[GPB_NUM_STAGES], ev1[GPB_NUM_STAGES];
@@ -1373,6 +1379,7 @@ int eig_begin(H* h) {
   h->launches += 2;
   CK(cudaGetLastError());
   e.m = e.k = 0;
+  e.solved_m = e.vectors_k = e.vectors_m = 0;
   e.restarts = 0;
   return 0;
 }
@@ -1460,40 +1467,43 @@ int eig_topk(H* h, int k, int* steps_out) {
   if (k > e.mcap)
     return fail(h, -4, "eigsh: " + std::to_string(k) + " eigenpairs requested, the device solver holds at most " +
                            std::to_string(e.mcap) + " Lanczos vectors");
-  std::vector<double> d, zlast;
-  std::vector<int> order;
+  std::vector<double>& d = e.ritz;
+  std::vector<double>& zlast = e.zlast;
+  std::vector<int>& order = e.order;
   int m = std::min(std::min(n, e.mcap), std::max(e.m, std::max(2 * k + 16, 48)));
   while (true) {
     int rc = eig_extend(h, m);
     if (rc) return rc;
-    const size_t smem = 4 * (size_t)m * sizeof(double);
-    CK(cudaFuncSetAttribute(eig_tql2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    eig_tql2_kernel<<<1, EIG_QL_THREADS, smem, h->stream>>>(e.alpha, e.beta, m, e.d, e.Zt, m, e.ibuf + e.mcap + 1);
-    h->launches++;
-    CK(cudaGetLastError());
-    d.resize(m);
-    zlast.resize(m);
-    int flags[2] = {0, 0};
-    double beta_last = 0.0;
-    CK(cudaMemcpyAsync(d.data(), e.d, m * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpy2DAsync(zlast.data(), sizeof(double), e.Zt + (m - 1), (size_t)m * sizeof(double), sizeof(double), m,
-                         cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(&beta_last, e.beta + (m - 1), sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(flags, e.ibuf + e.mcap, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    if (flags[1]) return fail(h, -4, "eigsh: the QL iteration on the projected tridiagonal matrix did not converge");
-    for (int i = 0; i < m; ++i)
-      if (!std::isfinite(d[i])) return fail(h, -4, "eigsh: non-finite Ritz values");
-    order.resize(m);
-    for (int i = 0; i < m; ++i) order[i] = i;
-    std::sort(order.begin(), order.end(), [&](int a, int b) { return d[a] > d[b] || (d[a] == d[b] && a < b); });
-    double scale = 0.0;
-    for (int i = 0; i < m; ++i) scale = std::max(scale, std::fabs(d[i]));
+    if (e.solved_m != m) {   // the projected problem of this size has not been diagonalised yet
+      const size_t smem = 4 * (size_t)m * sizeof(double);
+      CK(cudaFuncSetAttribute(eig_tql2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      eig_tql2_kernel<<<1, EIG_QL_THREADS, smem, h->stream>>>(e.alpha, e.beta, m, e.d, e.Zt, m, e.ibuf + e.mcap + 1);
+      h->launches++;
+      CK(cudaGetLastError());
+      d.resize(m);
+      zlast.resize(m);
+      int flags[2] = {0, 0};
+      CK(cudaMemcpyAsync(d.data(), e.d, m * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaMemcpy2DAsync(zlast.data(), sizeof(double), e.Zt + (m - 1), (size_t)m * sizeof(double), sizeof(double), m,
+                           cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaMemcpyAsync(&e.beta_last, e.beta + (m - 1), sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaMemcpyAsync(flags, e.ibuf + e.mcap, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      if (flags[1]) return fail(h, -4, "eigsh: the QL iteration on the projected tridiagonal matrix did not converge");
+      for (int i = 0; i < m; ++i)
+        if (!std::isfinite(d[i])) return fail(h, -4, "eigsh: non-finite Ritz values");
+      order.resize(m);
+      for (int i = 0; i < m; ++i) order[i] = i;
+      std::sort(order.begin(), order.end(), [&](int a, int b) { return d[a] > d[b] || (d[a] == d[b] && a < b); });
+      e.ritz_scale = 0.0;
+      for (int i = 0; i < m; ++i) e.ritz_scale = std::max(e.ritz_scale, std::fabs(d[i]));
+      e.solved_m = m;
+    }
     // residual of Ritz pair i: |beta_m z_{m,i}|; the basis spans everything once m == n
     bool ok = (m >= n);
     if (!ok) {
       ok = true;
-      for (int i = 0; i < k && ok; ++i) ok = std::fabs(beta_last * zlast[order[i]]) <= 5e-13 * scale;
+      for (int i = 0; i < k && ok; ++i) ok = std::fabs(e.beta_last * zlast[order[i]]) <= 5e-13 * e.ritz_scale;
     }
     if (ok) break;
     if (m >= e.mcap)
@@ -1501,23 +1511,34 @@ int eig_topk(H* h, int k, int* steps_out) {
                              " Lanczos steps");
     m = std::min(std::min(n, e.mcap), m + std::max(16, m / 2));
   }
-  // eigsh order: ascending, the largest k
-  std::vector<int> sel(k);
+  // eigsh order: ascending, the largest k.  The Ritz vectors are formed when somebody needs them (eig_vectors).
+  e.sel.resize(k);
   e.w_host.resize(k);
   for (int i = 0; i < k; ++i) {
-    sel[i] = order[k - 1 - i];
-    e.w_host[i] = d[sel[i]];
+    e.sel[i] = order[k - 1 - i];
+    e.w_host[i] = d[e.sel[i]];
   }
-  CK(cudaMemcpyAsync(e.ibuf, sel.data(), k * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  e.k = k;
+  e.vectors_k = 0;
+  if (steps_out) *steps_out = m;
+  return 0;
+}
+
+// Ritz vectors of the k pairs selected by the last eig_topk: rows of e.Qt (orthonormal), eigenvalues in e.wsel.
+int eig_vectors(H* h) {
+  H::Eig& e = h->eig;
+  if (e.vectors_k == e.k && e.vectors_m == e.solved_m) return 0;
+  const int n = e.n, k = e.k, m = e.solved_m;
+  CK(cudaMemcpyAsync(e.ibuf, e.sel.data(), k * sizeof(int), cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(e.wsel, e.w_host.data(), k * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   dim3 grid((unsigned)((n + EIG_BLOCK - 1) / EIG_BLOCK), (unsigned)k);
   eig_ritz_kernel<<<grid, EIG_BLOCK, 0, h->stream>>>(e.Vt, n, n, m, e.Zt, m, e.ibuf, e.Qt, n);
   eig_project_kernel<<<(unsigned)k, EIG_BLOCK, 0, h->stream>>>(e.Qt, n, n, nullptr, e.wsel, 0.0, nullptr, nullptr);
   h->launches += 2;
   CK(cudaGetLastError());
-  CK(cudaStreamSynchronize(h->stream));
-  e.k = k;
-  if (steps_out) *steps_out = m;
+  CK(cudaStreamSynchronize(h->stream));   // e.sel / e.w_host are pageable host memory
+  e.vectors_k = k;
+  e.vectors_m = m;
   return 0;
 }
 
@@ -1818,6 +1839,7 @@ int gpb_eigsh_matrix(gpb_handle_t h, const double* A, long long n, int k, int re
   }
   std::memcpy(w_out, e.w_host.data(), e.k * sizeof(double));
   if (Qt_out) {
+    if ((rc = eig_vectors(h))) return rc;
     CK(cudaMemcpyAsync(Qt_out, e.Qt, (size_t)e.k * n * sizeof(double), cudaMemcpyDefault, h->stream));
     CK(cudaStreamSynchronize(h->stream));
   }
@@ -1832,12 +1854,13 @@ int gpb_eig_inverse(gpb_handle_t h, const double* w, double* Kinv) {
   if (!e.matrix_ready || e.k < 1) return fail(h, -3, "gpb_eig_inverse: no resident eigenpairs (call gpb_eigsh_matrix first)");
   CK(cudaSetDevice(h->device));
   const int n = e.n;
+  int rc;
+  if ((rc = eig_vectors(h))) return rc;
   CK(cudaMemcpyAsync(e.wsel, w, e.k * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   const bool dev = is_device_ptr(Kinv);
-  int rc;
   if (!dev && (rc = ensure_cap(h, &h->dstage2, &h->dstage2_cap, (size_t)n * n))) return rc;
   double* out = dev ? Kinv : h->dstage2;
-  dim3 grid((unsigned)((n + EIG_BLOCK - 1) / EIG_BLOCK), (unsigned)n);
+  dim3 grid((unsigned)((n + EIG_BLOCK - 1) / EIG_BLOCK), (unsigned)std::min(n, 65535));
   eig_outer_kernel<<<grid, EIG_BLOCK, 0, h->stream>>>(e.Qt, n, n, e.k, e.wsel, out);
   h->launches++;
   CK(cudaGetLastError());
@@ -1864,6 +1887,7 @@ int gpb_nll_eig(gpb_handle_t h, int neig_term, int want_grad, double* nll, doubl
   const int n = e.n, k = e.k;
   h->factor_ready = false;
   stages_reset(h);
+  if ((rc = eig_vectors(h))) return rc;
   CK(cudaMemcpyAsync(e.wsel, e.w_host.data(), k * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   eig_project_kernel<<<(unsigned)k, EIG_BLOCK, 0, h->stream>>>(e.Qt, n, n, h->dy, e.wsel, 1e-10, e.qy, e.t);
   eig_alpha_kernel<<<(unsigned)((n + EIG_BLOCK - 1) / EIG_BLOCK), EIG_BLOCK, 0, h->stream>>>(e.Qt, n, n, k, e.t, e.avec);
