@@ -176,9 +176,10 @@ int gpb_solve_cholesky(gpb_handle_t h, const double* L, long long n, const doubl
  *
  * gpb_eigsh: the k largest eigenpairs of Ky(theta) of the resident training set -- eigsh(Ky, neig, tol=clip_eig) in the
  * loop of gp_functions.negative_log_likelihood (gp_functions.py:273-275).  w_out: k eigenvalues ascending (eigsh's order,
- * so w_out[0] is what the loop compares with clip_eig, :280).  Calls with the same (kind, theta) continue one Lanczos run.
- * steps_out (may be NULL) <- Lanczos steps used. */
-int gpb_eigsh(gpb_handle_t h, int kind, const double* theta, int n_ell, int k, double* w_out, int* steps_out);
+ * so w_out[0] is what the loop compares with clip_eig, :280).  Calls with the same (kind, theta) continue one Lanczos run;
+ * k_hint (0 = none) is the largest k the caller expects to request for this theta -- the reference's loop doubles neig up to
+ * 0.05 N -- so that the Krylov space is built and diagonalised once.  steps_out (may be NULL) <- Lanczos steps used. */
+int gpb_eigsh(gpb_handle_t h, int kind, const double* theta, int n_ell, int k, int k_hint, double* w_out, int* steps_out);
 
 /* NLL and gradient on that exit (gp_functions.py:283-300) from the eigenpairs gpb_eigsh left resident:
  * w <- max(w, 1e-10), alpha = Q diag(1/w) Q^T y, nll = 1/2 (y^T alpha + sum log w + neig_term log 2 pi) with

@@ -48,8 +48,8 @@ SIGNATURES = {
     "gpb_cholesky": (ctypes.c_int, [ctypes.c_void_p, _c_double_p, _ll, _c_double_p]),
     "gpb_invert_cholesky": (ctypes.c_int, [ctypes.c_void_p, _c_double_p, _ll, _c_double_p]),
     "gpb_solve_cholesky": (ctypes.c_int, [ctypes.c_void_p, _c_double_p, _ll, _c_double_p, ctypes.c_int, _c_double_p]),
-    "gpb_eigsh": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _c_double_p, ctypes.c_int, ctypes.c_int, _c_double_p,
-                                 ctypes.POINTER(ctypes.c_int)]),
+    "gpb_eigsh": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _c_double_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                 _c_double_p, ctypes.POINTER(ctypes.c_int)]),
     "gpb_nll_eig": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double),
                                    _c_double_p]),
     "gpb_eigsh_matrix": (ctypes.c_int, [ctypes.c_void_p, _c_double_p, _ll, ctypes.c_int, ctypes.c_int, _c_double_p,

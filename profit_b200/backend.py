@@ -322,16 +322,17 @@ class GPBackend:
         return x
 
     # -- truncated eigen-decomposition exits (gp_functions.py:273-301, 350-373) -----------------------------------
-    def eigsh(self, kind, theta, k):
+    def eigsh(self, kind, theta, k, k_hint=0):
         """The k largest eigenvalues of Ky(theta) of the resident training set, ascending like
-        ``scipy.sparse.linalg.eigsh(Ky, k)`` at gp_functions.py:273-275; the eigenvectors stay on the device."""
+        ``scipy.sparse.linalg.eigsh(Ky, k)`` at gp_functions.py:273-275; the eigenvectors stay on the device.
+        ``k_hint``: the largest k the caller expects to ask for with this theta (one Krylov space for all passes)."""
         theta = np.ascontiguousarray(theta, dtype=np.float64).ravel()
         k = int(min(k, self.n))
         w = np.empty(k)
         steps = ctypes.c_int()
         self.factor_key = self.noise_override = None
-        _lib.check(self._lib.gpb_eigsh(self._h, int(kind), _lib.ptr(theta), theta.size - 2, k, _lib.ptr(w),
-                                       ctypes.byref(steps)), self._h, "eigsh")
+        _lib.check(self._lib.gpb_eigsh(self._h, int(kind), _lib.ptr(theta), theta.size - 2, k, int(min(k_hint, self.n)),
+                                       _lib.ptr(w), ctypes.byref(steps)), self._h, "eigsh")
         self.last_eig_steps = steps.value
         return w
 

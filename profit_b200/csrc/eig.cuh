@@ -106,6 +106,106 @@ __global__ void __launch_bounds__(1024) eig_next_kernel(const double* __restrict
   for (int k = threadIdx.x; k < n; k += blockDim.x) dst[k] = w[k] * inv;
 }
 
+// The whole Lanczos recurrence for a SMALL matrix (n <= EIG_SMALL_N) in one CTA: steps [m0, m1) of the same algorithm as
+// the kernels above (matrix-vector product, Gram-Schmidt passes until the vector stops shrinking, invariant-subspace
+// detection and restart), without a launch or a host round trip per step -- at N = 400 a step costs ~8 us instead of
+// ~80 us.  One SM cannot stream a large matrix (8 n^2 bytes per step from L2), hence the size limit.
+// Dynamic shared memory: n + m1 doubles (the work vector and the Gram-Schmidt coefficients).
+// info[0] += restarts, info[1] <- step at which a non-finite coefficient appeared (0 = none).
+constexpr int EIG_SMALL_N = 1024;
+
+__device__ __forceinline__ double eig_hash_uniform(unsigned long long seed, int i) {
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(i + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (double)(z >> 11) * (2.0 / 9007199254740992.0) - 1.0;
+}
+
+__global__ void __launch_bounds__(1024) eig_lanczos_small_kernel(const double* __restrict__ A, int n, double* Vt,
+                                                                 double* __restrict__ alpha, double* __restrict__ beta,
+                                                                 int m0, int m1, unsigned long long seed,
+                                                                 int* __restrict__ info) {
+  extern __shared__ double sm[];
+  double* w = sm;
+  double* c = sm + n;
+  __shared__ double red[32];
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+  auto norm = [&]() {
+    double s = 0.0;
+    for (int k = tid; k < n; k += nt) s = fma(w[k], w[k], s);
+    return sqrt(eig_block_sum(s, red));
+  };
+  // one classical Gram-Schmidt pass of w against the first cnt basis vectors; returns the coefficient along the last one
+  auto gs_pass = [&](int cnt) {
+    for (int i = warp; i < cnt; i += nw) {
+      const double* v = Vt + (size_t)i * n;
+      double s = 0.0;
+      for (int k = lane; k < n; k += 32) s = fma(v[k], w[k], s);
+      s = eig_warp_sum(s);
+      if (lane == 0) c[i] = s;
+    }
+    __syncthreads();
+    const double last = c[cnt - 1];
+    for (int k = tid; k < n; k += nt) {
+      double s = w[k];
+      for (int i = 0; i < cnt; ++i) s = fma(-c[i], Vt[(size_t)i * n + k], s);
+      w[k] = s;
+    }
+    __syncthreads();
+    return last;
+  };
+  // orthogonalise w against the first cnt basis vectors, normalise into row cnt; n0 / n2 = norm before / after
+  auto orthonormalise = [&](int cnt, double& coeff, double& n0, double& n2) {
+    n0 = norm();
+    coeff = gs_pass(cnt);
+    const double n1 = norm();
+    coeff += gs_pass(cnt);
+    n2 = norm();
+    double prev = n1;
+    for (int extra = 0; extra < 4 && n2 > 0.0 && n2 < 0.5 * prev; ++extra) {
+      prev = n2;
+      gs_pass(cnt);
+      n2 = norm();
+    }
+    const double inv = (n2 > 0.0) ? 1.0 / n2 : 0.0;
+    double* dst = Vt + (size_t)cnt * n;
+    for (int k = tid; k < n; k += nt) dst[k] = w[k] * inv;
+    __syncthreads();
+  };
+  for (int j = m0; j < m1; ++j) {
+    const double* vj = Vt + (size_t)j * n;
+    for (int row = warp; row < n; row += nw) {
+      const double* a = A + (size_t)row * n;
+      double s = 0.0;
+      for (int k = lane; k < n; k += 32) s = fma(a[k], vj[k], s);
+      s = eig_warp_sum(s);
+      if (lane == 0) w[row] = s;
+    }
+    __syncthreads();
+    double aj, n0, n2;
+    orthonormalise(j + 1, aj, n0, n2);
+    if (tid == 0) {
+      alpha[j] = aj;
+      beta[j] = n2;
+    }
+    if (!(fabs(aj) < 1e300) || !(n2 < 1e300)) {   // NaN / Inf (uniform across the block)
+      if (tid == 0) info[1] = j + 1;
+      return;
+    }
+    if (j + 1 < n && n2 <= 64.0 * 2.220446049250313e-16 * n0) {
+      if (tid == 0) {
+        beta[j] = 0.0;
+        info[0] += 1;
+      }
+      for (int k = tid; k < n; k += nt) w[k] = eig_hash_uniform(seed + 7919ull * (unsigned long long)(j + 1), k);
+      __syncthreads();
+      double q, q0, q2;
+      orthonormalise(j + 1, q, q0, q2);
+    }
+  }
+}
+
 // Eigen-decomposition of the symmetric tridiagonal matrix (alpha[0..m), beta[0..m-1)) by the implicit QL iteration
 // (the EISPACK tql2 recurrences).  d[0..m) <- eigenvalues (unsorted); Zt[i * ldz + r] <- component r of eigenvector i.
 // One CTA: thread 0 generates the plane rotations of a sweep into shared memory, then every thread applies them to the

@@ -369,6 +369,7 @@ int g_early_mask = 0xF;         // which of the cut points {1/4, 1/2, 3/4, 7/8} 
 int g_super = 12;                // super-tile edge of the K^-1 = U U^T launch in 128-blocks, ~sqrt(148) (env GPB_SUPER; 0 = off)
 int g_pred_super_m = 12;         // super-tile of the predict column-norm GEMM: row tiles of W x candidate tiles (env GPB_PRED_SUPER_M / _C;
 int g_pred_super_c = 12;         // M = 0: plain order).  12 x 12 blocks = 288 128x64 CTAs ~ the 296 resident ones
+int g_eig_small = 1;             // one-CTA Lanczos kernel for matrices up to EIG_SMALL_N rows (env GPB_EIG_SMALL; 0 = always the multi-kernel path)
 int g_super_trtri = 0;           // the same for the triangular-inverse launches (env GPB_SUPER_TRTRI): measured +7 % time at
                                  // N=16384 (the heaviest-first order matters more there than the L2 hit rate), so off
 int g_fine_below = 148;          // launches with fewer 128-blocks than this use the fine tiles (env GPB_FINE_BELOW)
@@ -1361,7 +1362,7 @@ int eig_reserve(H* h, int n) {
   e.avec = p, p += nn;
   if (e.ibuf) CK(cudaFree(e.ibuf));
   e.ibuf = nullptr;
-  CK(cudaMalloc(&e.ibuf, (mm + 2) * sizeof(int)));
+  CK(cudaMalloc(&e.ibuf, (mm + 4) * sizeof(int)));
   if ((rc = ensure_cap(h, &e.K, &e.K_cap, nn * nn))) return rc;
   e.n = n;
   e.mcap = mcap;
@@ -1373,7 +1374,7 @@ int eig_reserve(H* h, int n) {
 // Start a Lanczos run on the resident matrix: v_0 = normalised deterministic pseudo-random vector.
 int eig_begin(H* h) {
   H::Eig& e = h->eig;
-  CK(cudaMemsetAsync(e.ibuf + e.mcap, 0, 2 * sizeof(int), h->stream));
+  CK(cudaMemsetAsync(e.ibuf + e.mcap, 0, 4 * sizeof(int), h->stream));
   eig_start_kernel<<<(unsigned)((e.n + 255) / 256), 256, 0, h->stream>>>(e.w, e.n, 0x5DEECE66Dull);
   eig_next_kernel<<<1, 1024, 0, h->stream>>>(e.w, e.n, e.Vt, nullptr);
   h->launches += 2;
@@ -1433,6 +1434,21 @@ int eig_orthonormalise(H* h, int cnt, double* alpha_out, double norms[3], double
 int eig_extend(H* h, int m_target) {
   H::Eig& e = h->eig;
   const int n = e.n;
+  if (n <= EIG_SMALL_N && g_eig_small) {   // small matrix: the whole recurrence in one CTA, no per-step round trips
+    if (e.m >= m_target) return 0;
+    const size_t smem = (size_t)(n + m_target) * sizeof(double);
+    eig_lanczos_small_kernel<<<1, 1024, smem, h->stream>>>(e.K, n, e.Vt, e.alpha, e.beta, e.m, m_target, 0x5DEECE66Dull,
+                                                          e.ibuf + e.mcap);
+    h->launches++;
+    CK(cudaGetLastError());
+    int info[2] = {0, 0};
+    CK(cudaMemcpyAsync(info, e.ibuf + e.mcap, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (info[1]) return fail(h, -4, "eigsh: non-finite Lanczos coefficients at step " + std::to_string(info[1]));
+    e.restarts = info[0];
+    e.m = m_target;
+    return 0;
+  }
   const unsigned gr = (unsigned)((n + 7) / 8);
   for (int j = e.m; j < m_target; ++j) {
     const double* vj = e.Vt + (size_t)j * n;
@@ -1459,7 +1475,7 @@ int eig_extend(H* h, int m_target) {
 
 // The k largest eigenpairs of the resident matrix; leaves the eigenvalues (ascending, like eigsh) in e.wsel / e.w_host
 // and the orthonormal Ritz vectors in the rows of e.Qt.  steps_out <- Lanczos steps used.
-int eig_topk(H* h, int k, int* steps_out) {
+int eig_topk(H* h, int k, int* steps_out, int k_hint = 0) {
   H::Eig& e = h->eig;
   const int n = e.n;
   if (k < 1) return fail(h, -1, "eigsh: k must be positive");
@@ -1470,24 +1486,25 @@ int eig_topk(H* h, int k, int* steps_out) {
   std::vector<double>& d = e.ritz;
   std::vector<double>& zlast = e.zlast;
   std::vector<int>& order = e.order;
-  int m = std::min(std::min(n, e.mcap), std::max(e.m, std::max(2 * k + 16, 48)));
+  // k_hint: the largest request the caller expects for this matrix -- size the Krylov space (and diagonalise it) once
+  int m = std::min(std::min(n, e.mcap), std::max(e.m, 2 * std::max(k, std::min(k_hint, e.mcap / 2)) + 16));
   while (true) {
     int rc = eig_extend(h, m);
     if (rc) return rc;
     if (e.solved_m != m) {   // the projected problem of this size has not been diagonalised yet
       const size_t smem = 4 * (size_t)m * sizeof(double);
       CK(cudaFuncSetAttribute(eig_tql2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      eig_tql2_kernel<<<1, EIG_QL_THREADS, smem, h->stream>>>(e.alpha, e.beta, m, e.d, e.Zt, m, e.ibuf + e.mcap + 1);
+      eig_tql2_kernel<<<1, EIG_QL_THREADS, smem, h->stream>>>(e.alpha, e.beta, m, e.d, e.Zt, m, e.ibuf + e.mcap + 2);
       h->launches++;
       CK(cudaGetLastError());
       d.resize(m);
       zlast.resize(m);
-      int flags[2] = {0, 0};
+      int flags[2] = {0, 0};   // flags[1] <- QL failure
       CK(cudaMemcpyAsync(d.data(), e.d, m * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
       CK(cudaMemcpy2DAsync(zlast.data(), sizeof(double), e.Zt + (m - 1), (size_t)m * sizeof(double), sizeof(double), m,
                            cudaMemcpyDeviceToHost, h->stream));
       CK(cudaMemcpyAsync(&e.beta_last, e.beta + (m - 1), sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-      CK(cudaMemcpyAsync(flags, e.ibuf + e.mcap, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaMemcpyAsync(flags, e.ibuf + e.mcap + 1, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
       CK(cudaStreamSynchronize(h->stream));
       if (flags[1]) return fail(h, -4, "eigsh: the QL iteration on the projected tridiagonal matrix did not converge");
       for (int i = 0; i < m; ++i)
@@ -1613,6 +1630,7 @@ int gpb_create(int device, gpb_handle_t* out) {
   if (const char* e = getenv("GPB_TAIL_BLOCKS")) g_tail_blocks = std::max(0, atoi(e));
   if (const char* e = getenv("GPB_SUPER")) g_super = std::max(0, std::min(64, atoi(e)));
   if (const char* e = getenv("GPB_SUPER_TRTRI")) g_super_trtri = std::max(0, std::min(64, atoi(e)));
+  if (const char* e = getenv("GPB_EIG_SMALL")) g_eig_small = atoi(e) != 0;
   if (const char* e = getenv("GPB_PRED_SUPER_M")) g_pred_super_m = std::max(0, std::min(128, atoi(e)));
   if (const char* e = getenv("GPB_PRED_SUPER_C")) g_pred_super_c = std::max(1, std::min(512, atoi(e)));
   if (const char* e = getenv("GPB_DIAG4")) g_diag4 = std::max(0, std::min(2, atoi(e)));
@@ -1785,7 +1803,7 @@ int gpb_nll(gpb_handle_t h, int kind, const double* theta, int n_ell, int want_g
 // Largest-k eigenpairs of Ky(theta) of the resident training set -- scipy.sparse.linalg.eigsh(Ky, neig, tol=clip_eig) inside
 // the loop of gp_functions.negative_log_likelihood (gp_functions.py:273-275).  Repeated calls with the same (kind, theta)
 // continue the same Lanczos run.
-int gpb_eigsh(gpb_handle_t h, int kind, const double* theta, int n_ell, int k, double* w_out, int* steps_out) {
+int gpb_eigsh(gpb_handle_t h, int kind, const double* theta, int n_ell, int k, int k_hint, double* w_out, int* steps_out) {
   int rc = need_train(h);
   if (rc) return rc;
   if (!theta || !w_out) return fail(h, -1, "gpb_eigsh: null argument");
@@ -1805,7 +1823,7 @@ int gpb_eigsh(gpb_handle_t h, int kind, const double* theta, int n_ell, int k, d
     e.from_train = true;
     e.matrix_ready = true;
   }
-  if ((rc = eig_topk(h, k, steps_out))) {
+  if ((rc = eig_topk(h, k, steps_out, k_hint))) {
     e.matrix_ready = false;
     return rc;
   }

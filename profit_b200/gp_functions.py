@@ -195,6 +195,9 @@ def _nll_reference_loop(hyp, X, y, kernel, eval_gradient, log_scale_hyp, fixed_s
     iteration = 0
     failed = 0
     w = None
+    k_hint = neig                                                # the largest pass before the first Cholesky attempt
+    while 2 * k_hint <= 0.05 * n:
+        k_hint *= 2
     while True:                                                  # :257
         if not neig or neig > 0.05 * n:                          # :258-272
             try:
@@ -205,7 +208,7 @@ def _nll_reference_loop(hyp, X, y, kernel, eval_gradient, log_scale_hyp, fixed_s
                 failed += 1                                      # the reference prints "Warning! Fallback to eig solver!"
                 eigenvalues_matter = True
         k_used = min(neig, n)
-        w = backend.eigsh(kind, hyp, k_used) if eigenvalues_matter else None      # :273-275
+        w = backend.eigsh(kind, hyp, k_used, k_hint) if eigenvalues_matter else None      # :273-275
         if iteration >= max_iter:                                # :276-278 (``iteration`` is never incremented upstream)
             break
         neig *= 2                                                # :279

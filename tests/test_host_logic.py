@@ -38,7 +38,7 @@ class OracleBackedFake:
         return oracle.nll_cholesky(np.asarray(theta), self.X, self.y, kern, eval_gradient=want_grad)
 
     # -- the truncated eigen-decomposition exit (GPBackend.eigsh / nll_eig)
-    def eigsh(self, kind, theta, k):
+    def eigsh(self, kind, theta, k, k_hint=0):
         self.eig_calls = getattr(self, "eig_calls", 0) + 1
         kern = oracle.rbf if kind == 0 else oracle.matern52
         theta = np.asarray(theta)
