@@ -208,8 +208,8 @@ long long gpb_launch_count(gpb_handle_t h);
 /* Test hook, host only (no device is touched): the launch / tile-task lists the library would run for a matrix of
  * n_blocks 128-blocks.  which: 0 = Cholesky, 1 = full triangular inverse, 2 = K^-1 = U U^T, 10 + i = early phase i of
  * the triangular inverse, 20 = its late part.  tasks_out: 8 ints per task {a_row, a_k, b_row, b_k, nk, c_row, c_col, aux};
- * launches_out: 16 doubles per launch {type (0 = diagonal block, 1 = tile GEMM), k, cfg, matA, matB, matC, matCt, alpha,
- * beta, task_off, ntasks, epi, stream, wait_ev, wait_ev2, rec_ev} with matrices 0 = L, 1 = U, 2 = W, 3 = Dinv.
+ * launches_out: 17 doubles per launch {type (0 = diagonal block, 1 = tile GEMM), k, cfg, matA, matB, matC, matCt, alpha,
+ * beta, task_off, ntasks, epi, stream, wait_ev, wait_ev2, rec_ev, wait_ev3} with matrices 0 = L, 1 = U, 2 = W, 3 = Dinv.
  * counts (11 entries): {n_tasks, n_launches, n_phases, cut[0..3], event[0..3]} -- phase i may start once `event[i]`
  * of the Cholesky plan has fired (always filled; pass NULL / 0 for the arrays to size them).
  * tests/test_plans.py replays these lists with numpy and checks that they compute the factor and the inverses. */

@@ -226,9 +226,9 @@ dgemm_tasks_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
   }
 #ifdef GPB_TRACE
-  // tag: nk | BM << 16 | (beta != 0) << 28 | (Ct != nullptr) << 29 | EPI << 30; consumer warp 0 reports for the CTA
+  // tag: nk | (BN / 32) << 12 | BM << 16 | (beta != 0) << 28 | (Ct != nullptr) << 29 | EPI << 30; consumer warp 0 reports for the CTA
   if (threadIdx.x == 0)
-    trace_emit(trace_t0, gridDim.x, (unsigned)task.nk | (BM << 16) | ((ep.beta != 0.0) << 28) | ((ep.Ct != nullptr) << 29) | (EPI << 30));
+    trace_emit(trace_t0, gridDim.x, (unsigned)task.nk | ((BN / 32) << 12) | (BM << 16) | ((ep.beta != 0.0) << 28) | ((ep.Ct != nullptr) << 29) | (EPI << 30));
 #endif
 }
 

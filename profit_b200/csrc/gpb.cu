@@ -56,9 +56,11 @@ struct Launch {
   size_t task_off;
   int ntasks;
   int epi;
-  int stream = 0;    // 0 = main stream, 1 = panel (look-ahead) stream, 2 = second trailing-update stream
+  int stream = 0;    // 0 = main stream, 1 = panel (look-ahead) stream, 2 = second trailing-update stream,
+                     // 3 = look-ahead update stream (T2a: the columns of the panel after next)
   int wait_ev = -1;  // event to wait for before the launch (index into the handle's event pool)
   int wait_ev2 = -1; // optional second event
+  int wait_ev3 = -1; // optional third event
   int rec_ev = -1;   // event recorded after the launch
   int pdl = 0;       // launch with programmatic stream serialization (overlaps the launch with the previous kernel)
   int trsm = 0;      // diag block: factor-only variant (32x32 diagonal inverses);  panel solve: blocked triangular solve
@@ -120,6 +122,7 @@ struct gpb_handle_s {
   cudaStream_t stream2 = nullptr;   // high-priority panel stream for the Cholesky look-ahead
   cudaStream_t stream3 = nullptr;   // low-priority stream of the early triangular inverse
   cudaStream_t stream4 = nullptr;   // second trailing-update stream (same priority as the main stream)
+  cudaStream_t stream5 = nullptr;   // high-priority stream of the look-ahead updates T2a (see build_potrf_plan)
   cudaEvent_t ev_early = nullptr;   // recorded on stream3 after the last early phase
   cudaStream_t caller = nullptr;    // gpb_set_stream: producer stream of the caller's device buffers (nullptr = legacy default)
   cudaEvent_t ev_caller = nullptr;
@@ -358,7 +361,8 @@ int g_early_min_blocks = 16;    // smallest matrix (in 128-blocks) whose triangu
 int g_super_min_blocks = 48;    // smallest matrix for the super-tile order of K^-1 = U U^T (below, the plain order is 5 % faster)
 int g_pdl = 1;                  // programmatic dependent launch along the panel chain (env GPB_PDL)
 int g_tail_blocks = 32;         // the last this-many block columns use single-block panels (env GPB_TAIL_BLOCKS)
-int g_lookahead = 1;            // overlap the next panel factorisation with the trailing update (env GPB_LOOKAHEAD)
+int g_lookahead = 2;            // panels of look-ahead: the panel chain runs this many panels ahead of the bulk trailing update
+                                // (env GPB_LOOKAHEAD; 0 = one stream in dependency order)
 int g_split_t2 = 1;             // trailing updates as two interleaved halves on two streams (env GPB_SPLIT_T2)
 int g_early_trtri = 1;          // start the triangular inverse of the leading blocks during the Cholesky (env GPB_EARLY_TRTRI)
 int g_early_cfg = CFG_32x128;   // tiles of the early phases: short CTAs delay the trailing updates least; -1 = as late (env GPB_EARLY_CFG)
@@ -372,7 +376,7 @@ int g_pred_super_c = 12;         // M = 0: plain order).  12 x 12 blocks = 288 1
 int g_eig_small = 1;             // one-CTA Lanczos kernel for matrices up to EIG_SMALL_N rows (env GPB_EIG_SMALL; 0 = always the multi-kernel path)
 int g_super_trtri = 0;           // the same for the triangular-inverse launches (env GPB_SUPER_TRTRI): measured +7 % time at
                                  // N=16384 (the heaviest-first order matters more there than the L2 hit rate), so off
-int g_fine_below = 148;          // launches with fewer 128-blocks than this use the fine tiles (env GPB_FINE_BELOW)
+int g_fine_below = 300;          // launches with fewer 128-blocks than this use the fine tiles (env GPB_FINE_BELOW)
 int cfg_for_blocks(int coarse, int nblocks) {
   if (nblocks >= g_fine_below) return coarse;
   return (coarse == CFG_64x128) ? CFG_32x128 : CFG_32x64;
@@ -458,7 +462,8 @@ void build_potrf_plan(Workspace& w) {
   auto evP = [&](int J) { return J; };
   auto evM = [&](int J) { return nJ + J; };
   auto evM2 = [&](int J) { return 2 * nJ + J; };   // second half of a split trailing update
-  p.num_events = la ? 3 * nJ : 0;
+  auto evA = [&](int J) { return 3 * nJ + J; };    // T2a(J): panel J+2's columns updated with panel J
+  p.num_events = la ? 4 * nJ : 0;
   std::vector<char> split(nJ, 0);
   // Cut points of the early triangular inverse: L[0:c, 0:c] is final once the panel that contains block column
   // c - 1 has been factored and solved (event evP of that panel).
@@ -517,7 +522,8 @@ void build_potrf_plan(Workspace& w) {
   };
   // columns [jb0, jb1) (in 128-blocks) updated with panel J
   // parity: -1 = every block column, 0 / 1 = only the even / odd ones
-  auto emit_update = [&](int J, int jb0, int jb1, int stream, int wait_ev, int rec_ev, int parity = -1, int wait_ev2 = -1) {
+  auto emit_update = [&](int J, int jb0, int jb1, int stream, int wait_ev, int rec_ev, int parity = -1, int wait_ev2 = -1,
+                         int wait_ev3 = -1) {
     const int J0 = pb[J], Je = pb[J + 1];
     TaskSink s(p);
     int nblk = 0;
@@ -532,6 +538,7 @@ void build_potrf_plan(Workspace& w) {
       p.launches[s.last].stream = stream;
       p.launches[s.last].wait_ev = wait_ev;
       p.launches[s.last].wait_ev2 = wait_ev2;
+      p.launches[s.last].wait_ev3 = wait_ev3;
       p.launches[s.last].rec_ev = rec_ev;
     }
     return s.last >= 0;
@@ -542,20 +549,32 @@ void build_potrf_plan(Workspace& w) {
     const int next0 = pb[J + 1], next1 = pb[J + 2];
     if (la) {
       const bool has_t2 = next1 < Nb;
+      // Two panels of look-ahead (g_lookahead == 2): the columns of panel J+2 are updated by a small launch of their own,
+      // T2a(J), on a high-priority stream (same-priority grids are dispatched first come first served, so behind a bulk
+      // update it would wait for the whole of it).  T1(J+1) then only waits for T2a(J) (event evA) instead of the whole
+      // trailing update: the panel chain P(J+1) -> T1(J+1) -> P(J+2) runs up to two panels ahead of the bulk, and the
+      // main stream always has the next bulk update queued.
+      const int deep = (g_lookahead >= 2 && has_t2) ? 1 : 0;
+      const int next2 = deep ? pb[std::min(J + 3, nJ)] : next1;
+      const int cross = (J > 0 && split[J - 1]) ? evM2(J - 1) : -1;   // the previous bulk update of the other parity
       // T2(J) first so that the big launch is queued early on the main stream.  While the trailing matrix is large it
       // goes out as two halves (even / odd block columns) on two streams: the drain of one half is covered by the
       // other, and the column -> stream map is static, so each half only depends on its own predecessor.
       if (has_t2) {
-        split[J] = g_split_t2 && (Nb - next1) >= 16;
+        if (deep) emit_update(J, next1, next2, 3, evP(J), evA(J), -1, J > 0 ? evM(J - 1) : -1, cross);
+        const bool bulk = next2 < Nb;
+        split[J] = bulk && g_split_t2 && (Nb - next2) >= 16;
         if (split[J]) {
-          emit_update(J, next1, Nb, 0, evP(J), evM(J), 0);
-          emit_update(J, next1, Nb, 2, evP(J), evM2(J), 1);
-        } else {
+          emit_update(J, next2, Nb, 0, evP(J), evM(J), 0);
+          emit_update(J, next2, Nb, 2, evP(J), evM2(J), 1);
+        } else if (bulk) {
           // an unsplit update touches both parities: it follows the last split one on the other stream as well
-          emit_update(J, next1, Nb, 0, evP(J), evM(J), -1, (J > 0 && split[J - 1]) ? evM2(J - 1) : -1);
+          emit_update(J, next2, Nb, 0, evP(J), evM(J), -1, cross);
         }
       }
-      emit_update(J, next0, next1, 1, J > 0 ? evM(J - 1) : -1, -1, -1, (J > 0 && split[J - 1]) ? evM2(J - 1) : -1);
+      // T1(J): with two panels of look-ahead its columns were last touched by T2a(J-1), otherwise by T2(J-1)
+      if (g_lookahead >= 2 && J > 0) emit_update(J, next0, next1, 1, evA(J - 1), -1);
+      else emit_update(J, next0, next1, 1, J > 0 ? evM(J - 1) : -1, -1, -1, (J > 0 && split[J - 1]) ? evM2(J - 1) : -1);
       emit_panel(J + 1);
     } else {
       emit_update(J, next0, Nb, 0, -1, -1);
@@ -677,7 +696,7 @@ int run_plan(H* h, Workspace& w, Plan& p, bool factor_diag, cudaStream_t only_st
   const bool multi = p.num_events > 0 && !only_stream;
   if (factor_diag) w.dinv_partial_from = 1 << 30;   // set again below by the factor-only diagonal blocks of this plan
   if (multi) {
-    while ((int)h->events.size() < p.num_events + 3) {
+    while ((int)h->events.size() < p.num_events + 4) {
       cudaEvent_t e;
       CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
       h->events.push_back(e);
@@ -686,12 +705,17 @@ int run_plan(H* h, Workspace& w, Plan& p, bool factor_diag, cudaStream_t only_st
     CK(cudaEventRecord(h->events[p.num_events], h->stream));
     CK(cudaStreamWaitEvent(h->stream2, h->events[p.num_events], 0));
     CK(cudaStreamWaitEvent(h->stream4, h->events[p.num_events], 0));
+    CK(cudaStreamWaitEvent(h->stream5, h->events[p.num_events], 0));
   }
   for (const Launch& L : p.launches) {
     cudaStream_t st = only_stream ? only_stream
-                                  : ((multi && L.stream == 1) ? h->stream2 : (multi && L.stream == 2) ? h->stream4 : h->stream);
+                                  : ((multi && L.stream == 1)   ? h->stream2
+                                     : (multi && L.stream == 2) ? h->stream4
+                                     : (multi && L.stream == 3) ? h->stream5
+                                                                : h->stream);
     if (multi && L.wait_ev >= 0) CK(cudaStreamWaitEvent(st, h->events[L.wait_ev], 0));
     if (multi && L.wait_ev2 >= 0) CK(cudaStreamWaitEvent(st, h->events[L.wait_ev2], 0));
+    if (multi && L.wait_ev3 >= 0) CK(cudaStreamWaitEvent(st, h->events[L.wait_ev3], 0));
     if (L.type == 0) {
       double* winv = w.Dinv + (long long)L.k * 128 * 128;
       if (factor_diag) {
@@ -765,6 +789,8 @@ int run_plan(H* h, Workspace& w, Plan& p, bool factor_diag, cudaStream_t only_st
     CK(cudaStreamWaitEvent(h->stream, h->events[p.num_events + 1], 0));
     CK(cudaEventRecord(h->events[p.num_events + 2], h->stream4));
     CK(cudaStreamWaitEvent(h->stream, h->events[p.num_events + 2], 0));
+    CK(cudaEventRecord(h->events[p.num_events + 3], h->stream5));
+    CK(cudaStreamWaitEvent(h->stream, h->events[p.num_events + 3], 0));
   }
   return 0;
 }
@@ -1585,6 +1611,7 @@ int gpb_create(int device, gpb_handle_t* out) {
         cudaStreamCreateWithPriority(&h->stream2, cudaStreamDefault, hi) != cudaSuccess ||
         cudaStreamCreateWithPriority(&h->stream3, cudaStreamNonBlocking, lo) != cudaSuccess ||
         cudaStreamCreateWithPriority(&h->stream4, cudaStreamNonBlocking, mid) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&h->stream5, cudaStreamNonBlocking, hi) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_early, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_caller, cudaEventDisableTiming) != cudaSuccess) {
       delete h;
@@ -1617,7 +1644,7 @@ int gpb_create(int device, gpb_handle_t* out) {
   cudaMalloc(&h->dinfo, sizeof(int));
   if (const char* e = getenv("GPB_CFG_UPDATE")) g_cfg_update = std::max(0, std::min(1, atoi(e)));
   if (const char* e = getenv("GPB_OUTER_BLOCKS")) g_outer_blocks = std::max(0, std::min(16, atoi(e)));
-  if (const char* e = getenv("GPB_LOOKAHEAD")) g_lookahead = atoi(e) != 0;
+  if (const char* e = getenv("GPB_LOOKAHEAD")) g_lookahead = std::max(0, std::min(2, atoi(e)));
   if (const char* e = getenv("GPB_EARLY_TRTRI")) g_early_trtri = atoi(e) != 0;
   if (const char* e = getenv("GPB_SPLIT_T2")) g_split_t2 = atoi(e) != 0;
   if (const char* e = getenv("GPB_EARLY_CFG")) g_early_cfg = atoi(e);
@@ -1675,6 +1702,7 @@ int gpb_destroy(gpb_handle_t h) {
   cudaStreamDestroy(h->stream2);
   cudaStreamDestroy(h->stream3);
   cudaStreamDestroy(h->stream4);
+  cudaStreamDestroy(h->stream5);
   cudaEventDestroy(h->ev_early);
   cudaEventDestroy(h->ev_caller);
   cudaStreamDestroy(h->stream);
@@ -2660,10 +2688,10 @@ int gpb_debug_plan(int n_blocks, int which, int* tasks_out, long long task_cap, 
   if (launches_out && launch_cap >= counts[1])
     for (size_t l = 0; l < p->launches.size(); ++l) {
       const Launch& L = p->launches[l];
-      const double row[16] = {(double)L.type, (double)L.k, (double)L.cfg, (double)L.matA, (double)L.matB, (double)L.matC,
+      const double row[17] = {(double)L.type, (double)L.k, (double)L.cfg, (double)L.matA, (double)L.matB, (double)L.matC,
                               (double)L.matCt, L.alpha, L.beta, (double)L.task_off, (double)L.ntasks, (double)L.epi,
-                              (double)L.stream, (double)L.wait_ev, (double)L.wait_ev2, (double)L.rec_ev};
-      memcpy(launches_out + 16 * l, row, sizeof(row));
+                              (double)L.stream, (double)L.wait_ev, (double)L.wait_ev2, (double)L.rec_ev, (double)L.wait_ev3};
+      memcpy(launches_out + 17 * l, row, sizeof(row));
     }
   return 0;
 }

@@ -26,7 +26,7 @@ def get_plan(lib, nb, which):
     assert lib.gpb_debug_plan(nb, which, None, 0, None, 0, counts) == 0
     nt, nl = int(counts[0]), int(counts[1])
     tasks = np.zeros((max(nt, 1), 8), dtype=np.int32)
-    launches = np.zeros((max(nl, 1), 16))
+    launches = np.zeros((max(nl, 1), 17))
     assert lib.gpb_debug_plan(nb, which, tasks.ctypes.data_as(ctypes.c_void_p), nt, launches.ctypes.data_as(ctypes.c_void_p),
                               nl, counts) == 0
     cuts = [int(c) for c in counts[3:3 + int(counts[2])]]
@@ -125,7 +125,7 @@ def test_split_trailing_updates_use_both_streams_and_every_tile_once(lib):
             else:
                 assert beta == 1.0
                 upd[i, j] += round(frac * nk * 1024)
-    assert streams == {0, 1, 2}
+    assert streams == {0, 1, 2, 3}
     for j in range(nb):
         for i in range(j, nb + 1):
             assert upd[i, j] == 8 * j * 1024, (i, j, upd[i, j])
@@ -206,7 +206,7 @@ def _happens_before(launches):
     """reach[j] = bitmask of launches ordered before j by stream order and event record -> wait pairs (run_plan)."""
     last_on_stream, last_record, reach = {}, {}, []
     for j, L in enumerate(launches):
-        stream, waits, rec = int(L[12]), [int(L[13]), int(L[14])], int(L[15])
+        stream, waits, rec = int(L[12]), [int(L[13]), int(L[14]), int(L[16])], int(L[15])
         preds = [last_on_stream[stream]] if stream in last_on_stream else []
         preds += [last_record[e] for e in waits if e >= 0 and e in last_record]
         bits = 1 << j
@@ -240,7 +240,7 @@ def test_cholesky_plan_orders_every_conflicting_pair_of_launches(lib, nb):
     tasks, launches, _ = get_plan(lib, nb, 0)
     _assert_race_free(tasks, launches, nb)
     if nb >= 24:
-        assert {int(L[12]) for L in launches} == {0, 1, 2}
+        assert {int(L[12]) for L in launches} == {0, 1, 2, 3}
 
 
 def test_removing_an_event_is_detected(lib):
@@ -251,6 +251,27 @@ def test_removing_an_event_is_detected(lib):
     broken[victim, 13] = -1
     with pytest.raises(AssertionError, match="without an ordering path"):
         _assert_race_free(tasks, broken, 24)
+
+
+def test_two_panel_lookahead_orders_the_next_column_update(lib):
+    """Two panels of look-ahead: the update of panel J+1's columns (panel stream) waits for the small launch that applied
+    panel J-1 to the same columns on the look-ahead update stream (T2a), not for the whole trailing update; dropping that wait
+    must be detected."""
+    nb = 24
+    tasks, launches, _ = get_plan(lib, nb, 0)
+    t1 = [n for n, L in enumerate(launches) if L[0] == 1 and int(L[12]) == 1 and int(L[13]) >= 0 and L[8] == 1.0]
+    assert len(t1) >= nb - 3
+    for n in t1[:5]:
+        ev = int(launches[n][13])
+        rec = next(m for m, L in enumerate(launches) if int(L[15]) == ev)
+        assert rec < n and int(launches[rec][12]) == 3                      # recorded on the look-ahead update stream, earlier in issue order
+        col = int(tasks[int(launches[n][9])][6]) // 128
+        cols = {int(t[6]) // 128 for t in tasks[int(launches[rec][9]):int(launches[rec][9]) + int(launches[rec][10])]}
+        assert cols == {col}                                                # ... by a launch that only touches that block column
+    broken = launches.copy()
+    broken[t1[3], 13] = -1
+    with pytest.raises(AssertionError, match="without an ordering path"):
+        _assert_race_free(tasks, broken, nb)
 
 
 def test_early_inverse_phases_are_ordered_after_the_columns_they_read(lib):
@@ -266,16 +287,16 @@ def test_early_inverse_phases_are_ordered_after_the_columns_they_read(lib):
     for i, cut in enumerate(cuts):
         ev = events[i]
         assert any(int(L[15]) == ev for L in launches)
-        seed = np.zeros((1, 16))
+        seed = np.zeros((1, 17))
         seed[0, :3] = [2, k0, cut]                      # pseudo launch: seed blocks [k0, cut)
         seed[0, 3:7] = M_NONE
-        seed[0, 12:16] = [3, ev, -1, -1]
+        seed[0, 12:17] = [9, ev, -1, -1, -1]
         k0 = cut
         pt, pl, _ = get_plan(lib, nb, 10 + i)
         pl = pl.copy()
         pl[:, 9] += off
-        pl[:, 12] = 3                                   # stream3
-        pl[:, 13:16] = -1
+        pl[:, 12] = 9                                   # stream3 of the handle (not a plan stream)
+        pl[:, 13:17] = -1
         all_tasks.append(pt)
         all_launches += [seed, pl]
         off += len(pt)

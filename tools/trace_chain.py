@@ -47,7 +47,7 @@ order = np.argsort(t0)
 d_idx = [i for i in order if is_diag[i]]
 print(f"N={N} want_grad={want_grad}: potrf stage {st['potrf']:.3f} ms, {len(d_idx)} diagonal blocks, {len(rec)} CTAs")
 print(" blk  diag[us]  | launches until the next diagonal block: (grid x nk, BM) start-after-diag-end .. end-after-diag-end")
-nk, bm, beta = tag & 0xFFFF, (tag >> 16) & 0xFFF, (tag >> 28) & 1
+nk, bm, beta = tag & 0xFFF, (tag >> 16) & 0xFFF, (tag >> 28) & 1
 rows = []
 for b, i in enumerate(d_idx):
     end = t1[i]

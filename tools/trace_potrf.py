@@ -41,7 +41,7 @@ grid = (rec[:, 2] >> np.uint64(32)).astype(np.int64)
 tag = rec[:, 3].astype(np.int64)
 base = t0.min()
 t0, t1 = (t0 - base) * 1e-6, (t1 - base) * 1e-6      # ms
-nk, bm, has_beta, has_ct = tag & 0xFFFF, (tag >> 16) & 0xFFF, (tag >> 28) & 1, (tag >> 29) & 1
+nk, bm, has_beta, has_ct = tag & 0xFFF, (tag >> 16) & 0xFFF, (tag >> 28) & 1, (tag >> 29) & 1
 keep = (tag != 0xD1A7) & (tag != 0xD1A8)      # phase stamps of the diag kernel, analysed at the end
 rec_all, tag_all = rec, tag
 rec, t0, t1, grid, tag, nk, bm, has_beta, has_ct = (a[keep] for a in (rec, t0, t1, grid, tag, nk, bm, has_beta, has_ct))
