@@ -11,6 +11,8 @@
 #include <cuda_runtime.h>
 #include <math.h>
 
+#include "ptx.cuh"
+
 namespace gpb {
 
 enum { KIND_RBF = 0, KIND_MATERN52 = 1 };
@@ -55,11 +57,22 @@ __global__ void prescale_kernel(const double* __restrict__ X, int n, KernelHyp h
 
 constexpr int AS_TM = 64, AS_TN = 128, AS_THREADS = 256;
 
+// Radial-factor stash: when a gradient follows, the assembly leaves k_pure and the derivative factor g of every pair of the
+// lower triangle behind, so that the gradient contraction needs neither exp nor sqrt again.  Layout: the lower 128x128
+// blocks (I >= J) packed one after the other, block (I, J) at index I (I + 1) / 2 + J, row-major inside the block -- half
+// the footprint of a square array, and a tile row of either kernel is one contiguous span.
+__device__ __forceinline__ long long stash_offset(int r, int c) {
+  const long long I = r >> 7, J = c >> 7;
+  return ((I * (I + 1) / 2 + J) << 14) + ((r & 127) << 7) + (c & 127);
+}
+
 // Lower-triangular tiles of K(X,X) + sn^2 I into L (row-major, ldl).  Rows/cols >= n are padding: identity.
+// G (and Kp for Matern-5/2, where g != k_pure) are the optional radial-factor stashes; nullptr = none.
 template <int KIND, int DP>
 __global__ void __launch_bounds__(AS_THREADS)
 assemble_sym_kernel(const double* __restrict__ Xs, const double* __restrict__ XsT, long long ldt, int n, int n_pad,
-                    double sf2, double sn2, double* __restrict__ L, long long ldl) {
+                    double sf2, double sn2, double* __restrict__ L, long long ldl, double* __restrict__ G,
+                    double* __restrict__ Kp) {
   const int row0 = blockIdx.y * AS_TM, col0 = blockIdx.x * AS_TN;
   if (col0 > row0 + AS_TM - 1) return;  // tile strictly above the diagonal
   __shared__ double xi[AS_TM][DP];
@@ -85,9 +98,14 @@ assemble_sym_kernel(const double* __restrict__ Xs, const double* __restrict__ Xs
       a0 = fma(u0, u0, a0);
       a1 = fma(u1, u1, a1);
     }
-    double k0, k1, gdummy;
-    kern_eval<KIND>(a0, sf2, k0, gdummy);
-    kern_eval<KIND>(a1, sf2, k1, gdummy);
+    double k0, k1, g0, g1;
+    kern_eval<KIND>(a0, sf2, k0, g0);
+    kern_eval<KIND>(a1, sf2, k1, g1);
+    if (G != nullptr) {
+      const long long so = stash_offset(r, c);
+      *reinterpret_cast<double2*>(G + so) = make_double2(g0, g1);
+      if (KIND != KIND_RBF) *reinterpret_cast<double2*>(Kp + so) = make_double2(k0, k1);
+    }
     if (r == c) k0 += sn2;
     if (r == c + 1) k1 += sn2;
     if (r >= n || c >= n) k0 = (r == c) ? 1.0 : 0.0;
@@ -311,6 +329,141 @@ grad_contract_kernel(const double* __restrict__ Xs, const double* __restrict__ X
   if (threadIdx.x < DP + 2) {
     double s = 0.0;
     for (int w = 0; w < AS_THREADS / 32; ++w) s += red[w][threadIdx.x];
+    part[(long long)cta * (DP + 2) + threadIdx.x] = s;
+  }
+}
+
+// The same contraction from the radial-factor stash of the assembly (see stash_offset): per pair two or three 8-byte
+// operands and ~3 FP64 operations per input dimension -- no exp, no sqrt, no distance sum -- which makes the kernel
+// HBM-bound (8 bytes of K^-1 + 8 (RBF) or 16 (Matern-5/2) bytes of stash per pair of the lower triangle).
+// One CTA owns a TM x 128 tile.  Its operand rows -- 1 KB contiguous each in K^-1 and in the stash blocks -- are streamed
+// through a GC_STAGES-deep shared-memory ring by bulk TMA copies (cp.async.bulk + mbarrier, one elected thread): the bytes
+// in flight sit in shared memory instead of registers, so two CTAs per SM keep ~100 KB outstanding.  The loop body is
+// branch-free (invalid pairs get weight zero).
+template <int DP>
+struct GcTile {
+  static constexpr int TM = (DP <= 16) ? 256 : 128;   // tall tile of large problems (shared memory: TM x DP doubles)
+  static constexpr int TM_SMALL = 64;                 // below ~8k rows: more, smaller CTAs fill the GPU
+};
+constexpr int GC_ROWS = 8, GC_STAGES = 3;             // rows per stage, stages in the ring
+
+template <int KIND, int DP, int TM>
+struct GcSmem {
+  static constexpr int NA = (KIND == KIND_RBF) ? 2 : 3;               // K^-1, g (, k_pure)
+  static constexpr int STAGE_DOUBLES = NA * GC_ROWS * AS_TN;
+  static constexpr int DOUBLES = GC_STAGES * STAGE_DOUBLES + TM * DP + TM + (AS_THREADS / 32) * (DP + 2);
+  static constexpr int BYTES = DOUBLES * 8 + GC_STAGES * 8 + 16;
+};
+
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <int KIND, int DP, int TM>
+__global__ void __launch_bounds__(AS_THREADS, (DP <= 16) ? 2 : 1)
+grad_contract_stash_kernel(const double* __restrict__ Xs, const double* __restrict__ XsT, long long ldt, int n, int n_pad,
+                           const double* __restrict__ Kinv, long long ldk, const double* __restrict__ alpha, long long lda,
+                           int n_out, const double* __restrict__ G, const double* __restrict__ Kp,
+                           double* __restrict__ part) {
+  using SM = GcSmem<KIND, DP, TM>;
+  extern __shared__ __align__(16) double gc_sm[];
+  double* stage = gc_sm;                                         // [GC_STAGES][NA][GC_ROWS][128]
+  double* xi = stage + GC_STAGES * SM::STAGE_DOUBLES;            // [TM][DP]
+  double* ar = xi + TM * DP;                                     // [TM]
+  double* red = ar + TM;                                         // [warps][DP + 2]
+  uint64_t* full = reinterpret_cast<uint64_t*>(red + (AS_THREADS / 32) * (DP + 2));
+
+  const int row0 = blockIdx.y * TM, col0 = blockIdx.x * AS_TN;
+  const int cta = blockIdx.y * gridDim.x + blockIdx.x;
+  double acc[DP + 2];
+#pragma unroll
+  for (int p = 0; p < DP + 2; ++p) acc[p] = 0.0;
+  const bool active = !(col0 > row0 + TM - 1) && row0 < n && col0 < n;
+  if (active) {
+    // rows above the diagonal block of this column tile carry no pairs: start at the block's first row
+    const int first = (col0 > row0) ? (col0 - row0) : 0;
+    const int step0 = first / GC_ROWS, nsteps = TM / GC_ROWS;
+    auto issue = [&](int step) {   // one thread: the GC_ROWS operand rows of a step into ring slot (step - step0) % GC_STAGES
+      const int slot = (step - step0) % GC_STAGES;
+      double* dst = stage + slot * SM::STAGE_DOUBLES;
+      mbar_arrive_expect_tx(&full[slot], SM::NA * GC_ROWS * AS_TN * 8);
+      for (int q = 0; q < GC_ROWS; ++q) {
+        const int r = row0 + step * GC_ROWS + q;
+        const long long so = stash_offset(r, col0);
+        bulk_load(dst + q * AS_TN, Kinv + (long long)r * ldk + col0, AS_TN * 8, &full[slot]);
+        bulk_load(dst + (GC_ROWS + q) * AS_TN, G + so, AS_TN * 8, &full[slot]);
+        if (KIND != KIND_RBF) bulk_load(dst + (2 * GC_ROWS + q) * AS_TN, Kp + so, AS_TN * 8, &full[slot]);
+      }
+    };
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int s = 0; s < GC_STAGES; ++s) mbar_init(&full[s], 1);
+      mbar_init_fence();
+      for (int s = 0; s < GC_STAGES - 1 && step0 + s < nsteps; ++s) issue(step0 + s);
+    }
+    // n_pad is a multiple of 128, not of TM: the last tile row may reach past the padded arrays
+    for (int e = threadIdx.x; e < TM * DP; e += AS_THREADS)
+      xi[e] = (row0 + e / DP < n_pad) ? Xs[(long long)row0 * DP + e] : 0.0;
+    for (int e = threadIdx.x; e < TM; e += AS_THREADS) ar[e] = (row0 + e < n_pad) ? alpha[row0 + e] : 0.0;
+    const int cl = threadIdx.x & 127, rg = threadIdx.x >> 7;
+    const int c = col0 + cl;
+    double xj[DP];
+#pragma unroll
+    for (int d = 0; d < DP; ++d) xj[d] = XsT[(long long)d * ldt + c];
+    const double ac = alpha[c];
+    __syncthreads();   // xi / ar filled, barriers initialised
+    for (int step = step0; step < nsteps; ++step) {
+      const int k = step - step0, slot = k % GC_STAGES;
+      // the slot refilled now was read in the previous step; every thread has passed that step's closing barrier
+      // (per-warp release barriers instead of the CTA barrier measured slower: 1.28 vs 1.10 ms at N = 16384)
+      if (threadIdx.x == 0 && step + GC_STAGES - 1 < nsteps) issue(step + GC_STAGES - 1);
+      mbar_wait(&full[slot], (k / GC_STAGES) & 1);
+      const double* sk = stage + slot * SM::STAGE_DOUBLES;
+#pragma unroll
+      for (int q = 0; q < GC_ROWS / 2; ++q) {
+        const int lr = rg + 2 * q, rr = step * GC_ROWS + lr, r = row0 + rr;
+        const bool ok = (r < n && c <= r && c < n);
+        const double kin = sk[lr * AS_TN + cl];
+        const double gq = sk[(GC_ROWS + lr) * AS_TN + cl];
+        const double kq = (KIND == KIND_RBF) ? gq : sk[(2 * GC_ROWS + lr) * AS_TN + cl];
+        double aa;
+        if (n_out == 1) {
+          aa = ar[rr] * ac;
+        } else {
+          aa = 0.0;
+          if (ok)
+            for (int o = 0; o < n_out; ++o) aa = fma(alpha[(long long)o * lda + r], alpha[(long long)o * lda + c], aa);
+        }
+        double w = ok ? (n_out * kin - aa) : 0.0;
+        const double wd = (c == r) ? w : 0.0;
+        w = (c == r) ? w : 2.0 * w;
+        const double wg = ok ? w * gq : 0.0;
+        const double wk = ok ? w * kq : 0.0;
+#pragma unroll
+        for (int d = 0; d < DP; ++d) {
+          const double v = xi[rr * DP + d] - xj[d];
+          acc[d] = fma(wg, v * v, acc[d]);
+        }
+        acc[DP] += wk;
+        acc[DP + 1] += wd;
+      }
+      __syncthreads();
+    }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int p = 0; p < DP + 2; ++p) {
+    double v = acc[p];
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if (lane == 0) red[warp * (DP + 2) + p] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < DP + 2) {
+    double s = 0.0;
+    for (int w = 0; w < AS_THREADS / 32; ++w) s += red[w * (DP + 2) + threadIdx.x];
     part[(long long)cta * (DP + 2) + threadIdx.x] = s;
   }
 }

@@ -101,6 +101,8 @@ struct Workspace {
   MatDesc mat[M_NONE];
   double *Lbuf = nullptr, *Ubuf = nullptr, *Wbuf = nullptr, *Dinv = nullptr;
   double *logdet = nullptr, *alpha = nullptr;
+  double *stashG = nullptr, *stashK = nullptr;   // radial-factor stashes of the assembly (assemble.cuh::stash_offset)
+  size_t stash_cap = 0, stashK_cap = 0;          // doubles per array
   Plan potrf, trtri, syrk;
   // Early triangular inverse: the sub-trees of the trtri recursion that only need the leading blocks of L run on a
   // low-priority stream while the Cholesky is still in its chain-bound second half (see build_trtri_plan).
@@ -376,6 +378,8 @@ int g_pred_super_c = 12;         // M = 0: plain order).  12 x 12 blocks = 288 1
 int g_eig_small = 1;             // one-CTA Lanczos kernel for matrices up to EIG_SMALL_N rows (env GPB_EIG_SMALL; 0 = always the multi-kernel path)
 int g_super_trtri = 0;           // the same for the triangular-inverse launches (env GPB_SUPER_TRTRI): measured +7 % time at
                                  // N=16384 (the heaviest-first order matters more there than the L2 hit rate), so off
+int g_stash = 1;                 // the assembly leaves k_pure and the derivative factor of every pair for the gradient
+                                 // contraction (env GPB_STASH; 0 = the contraction recomputes them)
 int g_fine_below = 300;          // launches with fewer 128-blocks than this use the fine tiles (env GPB_FINE_BELOW)
 int cfg_for_blocks(int coarse, int nblocks) {
   if (nblocks >= g_fine_below) return coarse;
@@ -797,6 +801,10 @@ int run_plan(H* h, Workspace& w, Plan& p, bool factor_diag, cudaStream_t only_st
 
 // ------------------------------------------------------------------------------------------------ workspace
 void free_ws(Workspace& w) {
+  cudaFree(w.stashG);
+  cudaFree(w.stashK);
+  w.stashG = w.stashK = nullptr;
+  w.stash_cap = w.stashK_cap = 0;
   cudaFree(w.Lbuf);
   cudaFree(w.Ubuf);
   cudaFree(w.Wbuf);
@@ -1036,14 +1044,41 @@ int set_hyp(H* h, int kind, const double* theta, int n_ell) {
   return 0;
 }
 
+// Radial-factor stashes for the gradient contraction (one array for RBF, two for Matern-5/2), Nb (Nb + 1) / 2 blocks of
+// 128 x 128 each.  Returns false -- and the caller recomputes the factors in the contraction -- when they are switched off
+// (GPB_STASH=0) or the device cannot spare the memory.
+bool ensure_stash(Workspace& w, bool need_kp) {
+  if (!g_stash) return false;
+  // one spare block row: the last tall tile of the contraction may reach 128 rows past the padded matrix
+  const size_t need = (size_t)((w.Nb + 1) * (w.Nb + 2) / 2) * 128 * 128;
+  auto grow = [&](double** p, size_t* cap) {
+    if (*cap >= need) return true;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    if (cudaMalloc(p, need * sizeof(double)) != cudaSuccess) {
+      cudaGetLastError();
+      *p = nullptr;
+      return false;
+    }
+    *cap = need;
+    return true;
+  };
+  if (!grow(&w.stashG, &w.stash_cap)) return false;
+  if (need_kp && !grow(&w.stashK, &w.stashK_cap)) return false;
+  return true;
+}
+
 template <int KIND>
-int assemble_dispatch(H* h, Workspace& w) {
+int assemble_dispatch(H* h, Workspace& w, bool stash) {
+  double* G = stash ? w.stashG : nullptr;
+  double* Kp = stash ? w.stashK : nullptr;
   const double sf2 = h->hyp.sf * h->hyp.sf, sn2 = h->hyp.sn * h->hyp.sn;
   dim3 grid((unsigned)(w.Np / AS_TN), (unsigned)(w.Np / AS_TM));
 #define GPB_AS(DPV)                                                                                              \
   case DPV:                                                                                                      \
     assemble_sym_kernel<KIND, DPV><<<grid, AS_THREADS, 0, h->stream>>>(h->dXs, h->dXsT, w.Np, (int)w.N, (int)w.Np, \
-                                                                      sf2, sn2, w.Lbuf, w.Np);                  \
+                                                                      sf2, sn2, w.Lbuf, w.Np, G, Kp);           \
     break;
   switch (h->DP) {
     GPB_AS(4) GPB_AS(8) GPB_AS(12) GPB_AS(16) GPB_AS(24) GPB_AS(32)
@@ -1073,6 +1108,59 @@ int contract_dispatch(H* h, Workspace& w, dim3 grid) {
   return 0;
 }
 
+template <int KIND, int DPV, int TM>
+int contract_stash_launch_tm(H* h, Workspace& w) {
+  dim3 grid((unsigned)(w.Np / AS_TN), (unsigned)((w.Np + TM - 1) / TM));
+  const size_t ncta = (size_t)grid.x * grid.y;
+  if (int rc = ensure_cap(h, &h->dpart, &h->dpart_cap, ncta * (DPV + 2))) return rc;
+  auto kern = grad_contract_stash_kernel<KIND, DPV, TM>;
+  constexpr int smem = GcSmem<KIND, DPV, TM>::BYTES;
+  static bool configured[64] = {};   // per device, like launch_cfg
+  if (!configured[h->device & 63]) {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured[h->device & 63] = true;
+  }
+  kern<<<grid, AS_THREADS, smem, h->stream>>>(h->dXs, h->dXsT, w.Np, (int)w.N, (int)w.Np, w.Lbuf, w.Np, w.alpha, w.Np,
+                                              h->n_out, w.stashG, w.stashK, h->dpart);
+  h->launches++;
+  CK(cudaGetLastError());
+  reduce_partials_kernel<<<DPV + 2, 256, 0, h->stream>>>(h->dpart, (int)ncta, DPV + 2, h->dscal + 1);
+  h->launches++;
+  return 0;
+}
+
+template <int KIND, int DPV>
+int contract_stash_launch(H* h, Workspace& w) {
+  // tall tiles once they still give every SM several CTAs (64 block columns x 32 tile rows / 2 at 8192 rows)
+  if (w.Nb >= 64) return contract_stash_launch_tm<KIND, DPV, GcTile<DPV>::TM>(h, w);
+  return contract_stash_launch_tm<KIND, DPV, GcTile<DPV>::TM_SMALL>(h, w);
+}
+
+// Gradient sums into dscal[1 ...] (DP + 2 slots): from the stash when the assembly of this evaluation left one,
+// otherwise with the radial factors recomputed pair by pair.
+template <int KIND>
+int contract_and_reduce(H* h, Workspace& w, bool stash) {
+  if (stash) {
+    switch (h->DP) {
+      case 4: return contract_stash_launch<KIND, 4>(h, w);
+      case 8: return contract_stash_launch<KIND, 8>(h, w);
+      case 12: return contract_stash_launch<KIND, 12>(h, w);
+      case 16: return contract_stash_launch<KIND, 16>(h, w);
+      case 24: return contract_stash_launch<KIND, 24>(h, w);
+      case 32: return contract_stash_launch<KIND, 32>(h, w);
+      default: return fail(h, -1, "unsupported input dimension");
+    }
+  }
+  const int width = h->DP + 2;
+  dim3 grid((unsigned)(w.Np / AS_TN), (unsigned)(w.Np / AS_TM));
+  const size_t ncta = (size_t)grid.x * grid.y;
+  if (int rc = ensure_cap(h, &h->dpart, &h->dpart_cap, ncta * width)) return rc;
+  if (int rc = contract_dispatch<KIND>(h, w, grid)) return rc;
+  reduce_partials_kernel<<<width, 256, 0, h->stream>>>(h->dpart, (int)ncta, width, h->dscal + 1);
+  h->launches++;
+  return 0;
+}
+
 template <int KIND>
 int cross_dispatch(H* h, Workspace& w, const double* dXc, long long mc, double* KsT, long long ldk, double* mean) {
   const unsigned grid = (unsigned)((mc + CR_ROWS - 1) / CR_ROWS);
@@ -1094,7 +1182,7 @@ int cross_dispatch(H* h, Workspace& w, const double* dXc, long long mc, double* 
 // Stages shared by gpb_nll and gpb_factorize: K(theta) -> L, z, logdet.
 // early_inverse: also queue the early phases of the triangular inverse (the caller must have called
 // ensure_inverse_buffers and must finish with triangular_inverse(h, w, true)).
-int assemble_and_factor(H* h, bool early_inverse = false) {
+int assemble_and_factor(H* h, bool early_inverse = false, bool stash = false) {
   Workspace& w = h->ws;
   stage_begin(h, GPB_STAGE_ASSEMBLE);
   CK(cudaMemsetAsync(h->dinfo, 0, sizeof(int), h->stream));
@@ -1104,7 +1192,7 @@ int assemble_and_factor(H* h, bool early_inverse = false) {
                                                                         h->dXsT, w.Np, (int)w.Np);
     h->launches++;
   }
-  int rc = (h->hyp.kind == KIND_RBF) ? assemble_dispatch<KIND_RBF>(h, w) : assemble_dispatch<KIND_MATERN52>(h, w);
+  int rc = (h->hyp.kind == KIND_RBF) ? assemble_dispatch<KIND_RBF>(h, w, stash) : assemble_dispatch<KIND_MATERN52>(h, w, stash);
   if (rc) return rc;
   {
     const long long tot = 128 * w.Np;
@@ -1650,6 +1738,7 @@ int gpb_create(int device, gpb_handle_t* out) {
   if (const char* e = getenv("GPB_EARLY_CFG")) g_early_cfg = atoi(e);
   if (const char* e = getenv("GPB_EARLY_MASK")) g_early_mask = atoi(e);
   if (const char* e = getenv("GPB_FINE_BELOW")) g_fine_below = atoi(e);
+  if (const char* e = getenv("GPB_STASH")) g_stash = atoi(e) != 0;
   if (const char* e = getenv("GPB_PDL")) g_pdl = atoi(e) != 0;
   if (const char* e = getenv("GPB_TRSM")) g_trsm = atoi(e) != 0;
   if (const char* e = getenv("GPB_TRSM_BELOW")) g_trsm_below = std::max(0, atoi(e));
@@ -1771,7 +1860,8 @@ int gpb_nll(gpb_handle_t h, int kind, const double* theta, int n_ell, int want_g
   stages_reset(h);
   stage_begin(h, GPB_STAGE_TOTAL);
   if (want_grad && (rc = ensure_inverse_buffers(h, w))) return rc;
-  if ((rc = assemble_and_factor(h, want_grad != 0))) return rc;
+  const bool stash = want_grad && ensure_stash(w, kind != KIND_RBF);
+  if ((rc = assemble_and_factor(h, want_grad != 0, stash))) return rc;
   nll_kernel<<<1, 1024, 0, h->stream>>>(w.Lbuf + w.Np * w.Np, w.Np, h->n_out, w.Np, w.N, w.logdet, (int)w.Nb, h->dscal);
   h->launches++;
   const int P = n_ell + 2, width = h->DP + 2;
@@ -1787,13 +1877,8 @@ int gpb_nll(gpb_handle_t h, int kind, const double* theta, int n_ell, int want_g
     stage_end(h, GPB_STAGE_SYRK);
     cudaEvent_t g0 = h->evx[0], g1 = h->evx[1];  // the GRAD stage has two pieces; time the second with its own pair
     cudaEventRecord(g0, h->stream);
-    dim3 grid((unsigned)(w.Np / AS_TN), (unsigned)(w.Np / AS_TM));
-    const size_t ncta = (size_t)grid.x * grid.y;
-    if ((rc = ensure_cap(h, &h->dpart, &h->dpart_cap, ncta * width))) return rc;
-    rc = (kind == KIND_RBF) ? contract_dispatch<KIND_RBF>(h, w, grid) : contract_dispatch<KIND_MATERN52>(h, w, grid);
+    rc = (kind == KIND_RBF) ? contract_and_reduce<KIND_RBF>(h, w, stash) : contract_and_reduce<KIND_MATERN52>(h, w, stash);
     if (rc) return rc;
-    reduce_partials_kernel<<<width, 256, 0, h->stream>>>(h->dpart, (int)ncta, width, h->dscal + 1);
-    h->launches++;
     cudaEventRecord(g1, h->stream);
     stage_end(h, GPB_STAGE_TOTAL);
     double host[64];
@@ -1960,11 +2045,12 @@ int gpb_nll_eig(gpb_handle_t h, int neig_term, int want_grad, double* nll, doubl
   const double jitter[6] = {0.0, 1e-6, 1e-8 * sf2, 1e-6 * sf2, 1e-4 * sf2, 1e-2 * sf2};
   double used = 0.0;
   int info = 0;
+  const bool stash = ensure_stash(w, h->hyp.kind != KIND_RBF);   // the radial factors do not depend on the jittered sigma_n
   for (int attempt = 0; attempt < 6; ++attempt) {
     if (attempt >= 2 && jitter[attempt] <= used) continue;
     used = jitter[attempt];
     h->hyp.sn = std::sqrt(sn_true * sn_true + used);
-    rc = assemble_and_factor(h, true);
+    rc = assemble_and_factor(h, true, stash);
     if (!rc) rc = triangular_inverse(h, w, true);
     if (!rc) rc = run_plan(h, w, w.syrk, false);
     h->hyp.sn = sn_true;
@@ -1976,13 +2062,8 @@ int gpb_nll_eig(gpb_handle_t h, int neig_term, int want_grad, double* nll, doubl
   h->eig.grad_jitter = used;
   CK(cudaMemsetAsync(w.alpha, 0, (size_t)w.Np * sizeof(double), h->stream));
   CK(cudaMemcpyAsync(w.alpha, e.avec, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-  dim3 grid((unsigned)(w.Np / AS_TN), (unsigned)(w.Np / AS_TM));
-  const size_t ncta = (size_t)grid.x * grid.y;
-  if ((rc = ensure_cap(h, &h->dpart, &h->dpart_cap, ncta * width))) return rc;
-  rc = (h->hyp.kind == KIND_RBF) ? contract_dispatch<KIND_RBF>(h, w, grid) : contract_dispatch<KIND_MATERN52>(h, w, grid);
+  rc = (h->hyp.kind == KIND_RBF) ? contract_and_reduce<KIND_RBF>(h, w, stash) : contract_and_reduce<KIND_MATERN52>(h, w, stash);
   if (rc) return rc;
-  reduce_partials_kernel<<<width, 256, 0, h->stream>>>(h->dpart, (int)ncta, width, h->dscal + 1);
-  h->launches++;
   CK(cudaMemcpyAsync(host, h->dscal, (1 + width) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   const double* acc = host + 1;
