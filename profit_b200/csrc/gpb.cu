@@ -362,7 +362,8 @@ int g_trsm_below = 40;          // ... for the block columns with at most this m
 int g_early_min_blocks = 16;    // smallest matrix (in 128-blocks) whose triangular inverse starts during the Cholesky (env GPB_EARLY_MIN_BLOCKS)
 int g_super_min_blocks = 48;    // smallest matrix for the super-tile order of K^-1 = U U^T (below, the plain order is 5 % faster)
 int g_pdl = 1;                  // programmatic dependent launch along the panel chain (env GPB_PDL)
-int g_tail_blocks = 32;         // the last this-many block columns use single-block panels (env GPB_TAIL_BLOCKS)
+int g_tail_blocks = 16;         // the last this-many block columns use single-block panels (env GPB_TAIL_BLOCKS)
+int g_wide_above = 64;           // block columns left above which the panels are four blocks wide (env GPB_WIDE_ABOVE)
 int g_lookahead = 2;            // panels of look-ahead: the panel chain runs this many panels ahead of the bulk trailing update
                                 // (env GPB_LOOKAHEAD; 0 = one stream in dependency order)
 int g_split_t2 = 1;             // trailing updates as two interleaved halves on two streams (env GPB_SPLIT_T2)
@@ -457,7 +458,7 @@ void build_potrf_plan(Workspace& w) {
   std::vector<int> pb{0};
   while (pb.back() < Nb) {
     const int left = Nb - pb.back();
-    int wdt = g_outer_blocks > 0 ? g_outer_blocks : (left > 64 ? 4 : (left > g_tail_blocks ? 2 : 1));
+    int wdt = g_outer_blocks > 0 ? g_outer_blocks : (left > g_wide_above ? 4 : (left > g_tail_blocks ? 2 : 1));
     pb.push_back(std::min(Nb, pb.back() + wdt));
   }
   const int nJ = (int)pb.size() - 1;
@@ -1739,6 +1740,7 @@ int gpb_create(int device, gpb_handle_t* out) {
   if (const char* e = getenv("GPB_EARLY_MASK")) g_early_mask = atoi(e);
   if (const char* e = getenv("GPB_FINE_BELOW")) g_fine_below = atoi(e);
   if (const char* e = getenv("GPB_STASH")) g_stash = atoi(e) != 0;
+  if (const char* e = getenv("GPB_WIDE_ABOVE")) g_wide_above = atoi(e);
   if (const char* e = getenv("GPB_PDL")) g_pdl = atoi(e) != 0;
   if (const char* e = getenv("GPB_TRSM")) g_trsm = atoi(e) != 0;
   if (const char* e = getenv("GPB_TRSM_BELOW")) g_trsm_below = std::max(0, atoi(e));

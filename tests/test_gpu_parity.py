@@ -400,7 +400,7 @@ def test_train_latency_small_problem(backend, golden):
     s.train(np.array(c["X"]), np.array(c["y"]))
     dt = time.perf_counter() - t0
     print(f"train N=200: {dt*1e3:.1f} ms")
-    assert dt < 1.0
+    assert dt < 0.136          # half the reference's 0.272 s; measured 22-29 ms (profiles/r02_bench_n1.json, small.c0)
 
 
 def test_multi_output_surrogate_equals_independent_models(backend):
