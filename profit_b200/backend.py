@@ -89,6 +89,7 @@ class GPBackend:
         theta = np.ascontiguousarray(theta, dtype=np.float64).ravel()
         n_ell = theta.size - 2
         self.factor_key = self.noise_override = None
+        self.nll_calls = getattr(self, "nll_calls", 0) + 1        # objective evaluations (multistart_optimize reports them)
         out = ctypes.c_double()
         grad = np.empty(theta.size) if want_grad else None
         st = self._lib.gpb_nll(self._h, int(kind), _lib.ptr(theta), n_ell, int(bool(want_grad)), ctypes.byref(out),

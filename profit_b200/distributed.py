@@ -144,6 +144,8 @@ def multistart_optimize(xtrain, ytrain, starts, kernel, fixed_sigma_n=False, eva
     N=4096 with two streams (tools/concurrent_restarts.py).
 
     Returns (best_theta, best_nll, table) where table has one row per restart: [restart, nll, theta...].
+    The number of objective evaluations this rank spent (the length of the BFGS paths, which decides the wall time as
+    much as the speed of one evaluation does) is left in ``multistart_optimize.last_evaluations``.
     """
     import threading
 
@@ -159,6 +161,7 @@ def multistart_optimize(xtrain, ytrain, starts, kernel, fixed_sigma_n=False, eva
     first = backend or shared_backend()
     backends = [first] + [GPBackend(first.device) for _ in range(streams - 1)]
     rows, lock = [], threading.Lock()
+    calls0 = [getattr(be, "nll_calls", 0) for be in backends]
 
     def one(r, be):
         try:
@@ -171,8 +174,17 @@ def multistart_optimize(xtrain, ytrain, starts, kernel, fixed_sigma_n=False, eva
         with lock:
             rows.append(np.concatenate([[r, nll], theta]))
 
+    # The restarts of this rank are handed out dynamically: BFGS paths differ in length by a factor of several, and a
+    # static split would leave one stream idle while the other finishes its long ones.  Every restart is deterministic
+    # on whichever handle it runs, so the table does not depend on the order.
+    todo = iter(mine)
+
     def worker(k):
-        for r in mine[k::streams]:
+        while True:
+            with lock:
+                r = next(todo, None)
+            if r is None:
+                return
             one(r, backends[k])
 
     if streams == 1:
@@ -183,8 +195,9 @@ def multistart_optimize(xtrain, ytrain, starts, kernel, fixed_sigma_n=False, eva
             th.start()
         for th in threads:
             th.join()
-        for be in backends[1:]:
-            be.close()
+    multistart_optimize.last_evaluations = sum(getattr(be, "nll_calls", 0) - c for be, c in zip(backends, calls0))
+    for be in backends[1:]:
+        be.close()
     width = 2 + (starts.shape[1] - (1 if fixed_sigma_n else 0))
     local = np.array(sorted(rows, key=lambda row: row[0])) if rows else np.empty((0, width))
     best, table = gather_argmin_rows(local) if len(local) or ws > 1 else (None, local)

@@ -458,6 +458,39 @@ def test_baseline_shapes_nll_grad_vs_oracle(backend, baseline_golden, key):
     assert grad_err(g, c["grad"]) <= NLL_RTOL
 
 
+@pytest.mark.parametrize("N,D,n_out,kind_name", [(1000, 3, 1, "Matern52"), (900, 5, 3, "RBF"), (8250, 10, 1, "Matern52"),
+                                                 (8250, 16, 2, "RBF"), (8450, 20, 1, "RBF")])
+def test_stash_contraction_equals_the_recomputing_contraction(N, D, n_out, kind_name):
+    """The gradient contraction from the radial-factor stash of the assembly (bulk-TMA staged)
+    against the kernel that recomputes the factors pair by pair (GPB_STASH=0, the round-1 path pinned to the oracle
+    above): same sums up to the rounding of a different summation order.  N = 8250 / 8450 pad to an odd number of
+    128-blocks, so the last 256-row tile of the tall-tile variant reaches past the padded matrix; n_out > 1 takes the
+    multi-output weights; D = 20 the one-CTA-per-SM instantiation."""
+    from profit_b200 import GPBackend
+
+    X, y = oracle.synthetic_problem(N, D)
+    Y = np.hstack([y * (1.0 + 0.3 * o) + 0.1 * np.sin(5.0 * X[:, :1] * (o + 1)) for o in range(n_out)])
+    theta = np.concatenate([np.linspace(0.5, 1.3, D), [1.4, 0.25]])
+    kind = KERN[kind_name][0]
+    res = {}
+    old = os.environ.get("GPB_STASH")
+    try:
+        for flag in ("0", "1"):
+            os.environ["GPB_STASH"] = flag                 # read in gpb_create
+            be = GPBackend(0)
+            be.set_train(X, Y)
+            res[flag] = be.nll(kind, theta, want_grad=True)
+            be.close()
+    finally:
+        if old is None:
+            os.environ.pop("GPB_STASH", None)
+        else:
+            os.environ["GPB_STASH"] = old
+        GPBackend(0).close()                               # restores the process-wide default for later handles
+    assert res["0"][0] == res["1"][0]                      # the factorisation does not depend on the stash
+    assert grad_err(res["1"][1], res["0"][1]) <= 1e-10
+
+
 def test_baseline_shape_predict_vs_oracle(backend, baseline_golden):
     """BASELINE.json configs[3]: N=8192 training points, 4096 of the candidates."""
     c = baseline_golden["c3_predict"]
