@@ -337,7 +337,7 @@ grad_contract_kernel(const double* __restrict__ Xs, const double* __restrict__ X
 // operands and ~3 FP64 operations per input dimension -- no exp, no sqrt, no distance sum -- which makes the kernel
 // HBM-bound (8 bytes of K^-1 + 8 (RBF) or 16 (Matern-5/2) bytes of stash per pair of the lower triangle).
 // One CTA owns a TM x 128 tile.  Its operand rows -- 1 KB contiguous each in K^-1 and in the stash blocks -- are streamed
-// through a GC_STAGES-deep shared-memory ring by bulk TMA copies (cp.async.bulk + mbarrier, one elected thread): the bytes
+// through a GC_STAGES-deep shared-memory ring by bulk TMA copies (cp.async.bulk + mbarrier, issued by one warp, one copy per lane): the bytes
 // in flight sit in shared memory instead of registers, so two CTAs per SM keep ~100 KB outstanding.  The loop body is
 // branch-free (invalid pairs get weight zero).
 template <int DP>
@@ -386,22 +386,30 @@ grad_contract_stash_kernel(const double* __restrict__ Xs, const double* __restri
     // rows above the diagonal block of this column tile carry no pairs: start at the block's first row
     const int first = (col0 > row0) ? (col0 - row0) : 0;
     const int step0 = first / GC_ROWS, nsteps = TM / GC_ROWS;
-    auto issue = [&](int step) {   // one thread: the GC_ROWS operand rows of a step into ring slot (step - step0) % GC_STAGES
-      const int slot = (step - step0) % GC_STAGES;
+    // Warp 0 issues the copies of a step into ring slot (step - step0) % GC_STAGES, one copy per lane so that they leave
+    // together: lanes 0..7 the GC_ROWS rows of K^-1 (1 KB each, row stride ldk), lane 8 the GC_ROWS x 128 stash rows of g
+    // and lane 9 those of k_pure -- 8 KB contiguous each, because GC_ROWS rows of one 128-block follow one another in
+    // the packed layout.
+    auto issue = [&](int step) {
+      const int slot = (step - step0) % GC_STAGES, lane = threadIdx.x;
       double* dst = stage + slot * SM::STAGE_DOUBLES;
-      mbar_arrive_expect_tx(&full[slot], SM::NA * GC_ROWS * AS_TN * 8);
-      for (int q = 0; q < GC_ROWS; ++q) {
-        const int r = row0 + step * GC_ROWS + q;
-        const long long so = stash_offset(r, col0);
-        bulk_load(dst + q * AS_TN, Kinv + (long long)r * ldk + col0, AS_TN * 8, &full[slot]);
-        bulk_load(dst + (GC_ROWS + q) * AS_TN, G + so, AS_TN * 8, &full[slot]);
-        if (KIND != KIND_RBF) bulk_load(dst + (2 * GC_ROWS + q) * AS_TN, Kp + so, AS_TN * 8, &full[slot]);
-      }
+      const int r = row0 + step * GC_ROWS;
+      if (lane == 0) mbar_arrive_expect_tx(&full[slot], SM::NA * GC_ROWS * AS_TN * 8);
+      __syncwarp();
+      if (lane < GC_ROWS)
+        bulk_load(dst + lane * AS_TN, Kinv + (long long)(r + lane) * ldk + col0, AS_TN * 8, &full[slot]);
+      else if (lane == GC_ROWS)
+        bulk_load(dst + GC_ROWS * AS_TN, G + stash_offset(r, col0), GC_ROWS * AS_TN * 8, &full[slot]);
+      else if (lane == GC_ROWS + 1 && KIND != KIND_RBF)
+        bulk_load(dst + 2 * GC_ROWS * AS_TN, Kp + stash_offset(r, col0), GC_ROWS * AS_TN * 8, &full[slot]);
     };
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {
+      if (threadIdx.x == 0) {
 #pragma unroll
-      for (int s = 0; s < GC_STAGES; ++s) mbar_init(&full[s], 1);
-      mbar_init_fence();
+        for (int s = 0; s < GC_STAGES; ++s) mbar_init(&full[s], 1);
+        mbar_init_fence();
+      }
+      __syncwarp();
       for (int s = 0; s < GC_STAGES - 1 && step0 + s < nsteps; ++s) issue(step0 + s);
     }
     // n_pad is a multiple of 128, not of TM: the last tile row may reach past the padded arrays
@@ -419,7 +427,7 @@ grad_contract_stash_kernel(const double* __restrict__ Xs, const double* __restri
       const int k = step - step0, slot = k % GC_STAGES;
       // the slot refilled now was read in the previous step; every thread has passed that step's closing barrier
       // (per-warp release barriers instead of the CTA barrier measured slower: 1.28 vs 1.10 ms at N = 16384)
-      if (threadIdx.x == 0 && step + GC_STAGES - 1 < nsteps) issue(step + GC_STAGES - 1);
+      if (threadIdx.x < 32 && step + GC_STAGES - 1 < nsteps) issue(step + GC_STAGES - 1);
       mbar_wait(&full[slot], (k / GC_STAGES) & 1);
       const double* sk = stage + slot * SM::STAGE_DOUBLES;
 #pragma unroll

@@ -888,8 +888,19 @@ __global__ void __launch_bounds__(256) trigemv_kernel(const double* __restrict__
   if (i >= n) return;
   const long long k0 = lower ? 0 : i, k1 = lower ? i + 1 : n;
   for (int o = 0; o < n_out; ++o) {
-    double s = 0.0;
-    for (long long k = k0 + lane; k < k1; k += 32) s = fma(T[i * ld + k], z[k * sz_k + o * sz_o], s);
+    // four independent partial sums: four row segments in flight per lane (the kernel is bound by load latency:
+    // ncu long-scoreboard stall 129 cycles per issue with one), combined in a fixed order
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    long long k = k0 + lane;
+    for (; k + 96 < k1; k += 128) {
+      const double t0 = T[i * ld + k], t1 = T[i * ld + k + 32], t2 = T[i * ld + k + 64], t3 = T[i * ld + k + 96];
+      s0 = fma(t0, z[k * sz_k + o * sz_o], s0);
+      s1 = fma(t1, z[(k + 32) * sz_k + o * sz_o], s1);
+      s2 = fma(t2, z[(k + 64) * sz_k + o * sz_o], s2);
+      s3 = fma(t3, z[(k + 96) * sz_k + o * sz_o], s3);
+    }
+    for (; k < k1; k += 32) s0 = fma(T[i * ld + k], z[k * sz_k + o * sz_o], s0);
+    double s = (s0 + s1) + (s2 + s3);
     for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
     if (lane == 0) out[i * so_i + o * so_o] = s;
   }
