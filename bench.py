@@ -538,13 +538,15 @@ def run_gpu(args):
               "scaling": "strong", "seconds": c_elapsed, "restarts": int(args.c4_restarts),
               "workload": f"{args.c4_restarts} BFGS restarts (gp_functions.optimize, SciPy BFGS defaults), RBF ARD, "
                           f"N={N_TRAIN_C4}, D={DIM_C4}, P={DIM_C4 + 2} (BASELINE configs[4]); starts = theta_ref * "
-                          f"10^(halton - 1/2); restart r -> rank r mod {world}; {args.c4_streams} concurrent restart "
+                          f"10^(halton - 1/2); restarts handed out one at a time to the {world} rank(s) from a counter in the process "
+                          f"group's store; {args.c4_streams} concurrent restart "
                           f"stream(s) per GPU; one all_gather of (nll, theta) picks the best",
               "best_nll": float(best_nll), "best_restart": int(table[np.argmin(table[:, 1]), 0]),
               "finite_restarts": int(np.isfinite(table[:, 1]).sum()),
               "distinct_optima": int(len(set(np.round(table[np.isfinite(table[:, 1]), 1], 3)))),
               "gpu_launches_rank0_first_stream": int(bm.launch_count() - l0),
               "evaluations_rank0": int(getattr(multistart_optimize, "last_evaluations", 0)),
+              "restart_queue": getattr(multistart_optimize, "last_queue_mode", None),
               "evaluations_note": "NLL+gradient evaluations rank 0 spent on its restarts: the BFGS path lengths (SciPy's "
                                   "line searches, sensitive to the last bits of the gradient) decide the wall time as "
                                   "much as the 18 ms per evaluation do"}

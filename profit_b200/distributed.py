@@ -5,9 +5,12 @@ One process per GPU (torchrun); ``torch.distributed`` is only used for tiny resu
 * candidate prediction -- contiguous shards of ceil(M/G) candidates per rank, X/y/theta replicated, every rank
   factorises on its own; one all_gather of (best value, global index) = 16 B per rank, then a local arg-max
   with lowest-index tie-break (np.argmax semantics, aquisition_functions.py:68).
-* multi-start hyper-parameter optimisation -- restart r runs on rank r mod G; one all_gather of
-  (nll, theta[P]) per restart, arg-min with tie-break on the restart index.  The reference has a single start
-  (gp_functions.py:59-66); per restart the optimiser is exactly ``gp_functions.optimize``.
+* multi-start hyper-parameter optimisation -- the restarts are handed out one at a time from a counter in the
+  process group's key-value store (BFGS paths differ in length by an order of magnitude once a start wanders into the
+  reference's eigen-decomposition exit, so a static r -> rank r mod G map leaves most GPUs idle behind the unlucky one;
+  it remains the fallback without a store); one all_gather of (nll, theta[P]) per restart, arg-min with tie-break on
+  the restart index.  The reference has a single start (gp_functions.py:59-66); per restart the optimiser is exactly
+  ``gp_functions.optimize``, and a restart gives the same result on whichever rank it runs.
 
 A single NLL+gradient evaluation does not shard ("replicas only").  No data-path collective exists.
 """
@@ -94,6 +97,46 @@ def gather_concat(local, total):
     return _all_gather_rows(padded).ravel()[:total]        # shard r starts at r * per: rank-ordered rows line up
 
 
+_QUEUE_CALLS = [0]
+
+
+def restart_queue(total):
+    """Thread-safe ``next_index()`` over range(total), shared by every worker of every rank: a counter in the default
+    process group's store (``store.add`` is atomic; the key is unique per call because all ranks call this function the
+    same number of times).  Without a process group, or if the store cannot be reached, rank r walks r, r + G, ...
+    Returns (next_index, mode) with mode "store" or "static"."""
+    import itertools
+    import threading
+
+    rank, ws = world()
+    lock = threading.Lock()
+    _QUEUE_CALLS[0] += 1
+    store = None
+    if ws > 1:
+        try:
+            from torch.distributed import distributed_c10d
+
+            store = distributed_c10d._get_default_store()
+            key = f"profit_b200/restart_queue/{_QUEUE_CALLS[0]}"
+            store.add(key, 0)
+        except Exception:                      # noqa: BLE001 -- any failure falls back to the static map
+            store = None
+    if store is not None:
+        def next_index():
+            with lock:
+                i = int(store.add(key, 1)) - 1
+            return i if i < total else None
+
+        return next_index, "store"
+    static = iter(range(rank, int(total), ws))
+
+    def next_index():
+        with lock:
+            return next(static, None)
+
+    return next_index, "static"
+
+
 def gather_argmin_rows(local_rows):
     """local_rows: (k, 2+P) rows [restart_index, nll, theta...]; returns the row with the smallest nll over all
     ranks (ties -> smallest restart index).  Ranks may hold different numbers of rows."""
@@ -136,7 +179,8 @@ def acquisition_argmax(backend, Xpred, add_data_variance=True, mask=None):
 
 def multistart_optimize(xtrain, ytrain, starts, kernel, fixed_sigma_n=False, eval_gradient=True, backend=None,
                         streams=1):
-    """Run ``gp_functions.optimize`` from every start in ``starts`` (R, P), restarts sharded r -> rank r mod G.
+    """Run ``gp_functions.optimize`` from every start in ``starts`` (R, P), restarts handed to the ranks' workers one
+    at a time (``restart_queue``).
 
     ``streams`` > 1 runs that many restarts of this rank concurrently, each on its own device handle and stream
     (host threads; the C calls release the GIL).  One evaluation cannot fill the GPU while its Cholesky walks the
@@ -156,8 +200,7 @@ def multistart_optimize(xtrain, ytrain, starts, kernel, fixed_sigma_n=False, eva
     starts = np.atleast_2d(np.asarray(starts, dtype=np.float64))
     if starts.size == 0:
         raise ValueError("multistart_optimize needs at least one start point")
-    mine = list(range(rank, starts.shape[0], ws))
-    streams = max(1, min(int(streams), len(mine) or 1))
+    streams = max(1, min(int(streams), -(-starts.shape[0] // ws)))
     first = backend or shared_backend()
     backends = [first] + [GPBackend(first.device) for _ in range(streams - 1)]
     rows, lock = [], threading.Lock()
@@ -174,15 +217,13 @@ def multistart_optimize(xtrain, ytrain, starts, kernel, fixed_sigma_n=False, eva
         with lock:
             rows.append(np.concatenate([[r, nll], theta]))
 
-    # The restarts of this rank are handed out dynamically: BFGS paths differ in length by a factor of several, and a
-    # static split would leave one stream idle while the other finishes its long ones.  Every restart is deterministic
-    # on whichever handle it runs, so the table does not depend on the order.
-    todo = iter(mine)
+    # Every restart is deterministic on whichever handle of whichever rank it runs, so the table does not depend on
+    # who took what.
+    next_restart, multistart_optimize.last_queue_mode = restart_queue(starts.shape[0])
 
     def worker(k):
         while True:
-            with lock:
-                r = next(todo, None)
+            r = next_restart()
             if r is None:
                 return
             one(r, backends[k])

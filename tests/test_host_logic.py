@@ -296,7 +296,7 @@ def test_shard_bounds_cover_everything_once():
 _WORKER = r'''
 import os, sys
 sys.path.insert(0, sys.argv[1])
-import numpy as np, torch.distributed as dist
+import numpy as np, torch, torch.distributed as dist
 from profit_b200.distributed import gather_argmax, gather_argmin_rows, gather_concat, gather_minmax, shard_bounds, world
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + sys.argv[2], rank=int(sys.argv[3]), world_size=2)
 rank, ws = world()
@@ -323,6 +323,30 @@ assert np.array_equal(g, np.stack([cols.min(axis=0), cols.max(axis=0)], axis=1))
 g1 = gather_minmax([[np.inf, -np.inf]] if rank == 1 else [[0.5, 0.7]])
 assert np.array_equal(g1, [[0.5, 0.7]])
 assert np.array_equal(gather_concat(v[lo:hi], len(v)), v)         # ragged last shard (1001 = 501 + 500)
+# the restart queue of multistart_optimize: a counter in the group's store hands every index to exactly one worker
+import threading, time
+from profit_b200.distributed import restart_queue
+nxt, mode = restart_queue(37)
+assert mode == "store", mode
+got = []
+def pull():
+    while True:
+        i = nxt()
+        if i is None:
+            return
+        got.append(i); time.sleep(0.001 * (1 + rank))             # unequal speeds: the faster rank takes more
+ts = [threading.Thread(target=pull) for _ in range(2)]
+[t.start() for t in ts]; [t.join() for t in ts]
+mine = np.full(37, -1.0); mine[:len(got)] = sorted(got)
+both = [torch.empty(37, dtype=torch.float64) for _ in range(2)]
+dist.all_gather(both, torch.from_numpy(mine))
+taken = sorted(int(i) for t in both for i in t.tolist() if i >= 0)
+assert taken == list(range(37)), taken
+nxt2, _ = restart_queue(3)                                         # a second queue is independent of the first
+mine2 = np.full(3, -1.0); got2 = list(iter(nxt2, None)); mine2[:len(got2)] = got2
+both2 = [torch.empty(3, dtype=torch.float64) for _ in range(2)]
+dist.all_gather(both2, torch.from_numpy(mine2))
+assert sorted(int(i) for t in both2 for i in t.tolist() if i >= 0) == [0, 1, 2]
 dist.barrier(); dist.destroy_process_group()
 print("worker", rank, "ok")
 '''
