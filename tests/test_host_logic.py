@@ -93,6 +93,37 @@ def test_select_kernel():
         kernels.select_kernel("LinearEmbedding")
 
 
+def test_reference_loop_sizes_the_krylov_space_for_the_next_two_doublings():
+    """The hint handed to backend.eigsh: never more than the largest pass before the first Cholesky attempt (the largest
+    power of two <= 0.05 n), and for the early passes only enough for the next two doublings -- a loop that leaves at
+    neig = 1 (an optimiser start at a huge length scale: lambda_1 <= 1e-3 l) must not pay for the 256-pair pass of an
+    N = 8192 problem."""
+    import warnings
+
+    class Recorder(OracleBackedFake):
+        def eigsh(self, kind, theta, k, k_hint=0):
+            self.hints = getattr(self, "hints", []) + [(int(k), int(k_hint))]
+            return super().eigsh(kind, theta, k, k_hint)
+
+    # (1) leaves at the first pass: length scale 5e3 -> clip_eig = 5 > lambda_1 = trace bound n sf^2 + sn^2 ~ 3
+    be = Recorder()
+    X, y = oracle.synthetic_problem(1400, 2)
+    be.set_train(X, y)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", gpf.NonSPDWarning)
+        gpf.negative_log_likelihood(np.array([5e3, 5e3, 0.045, 0.3]), X, y, kernels.RBF, False, False, backend=be)
+    assert be.hints == [(1, 32)]                                   # 0.05 n = 70 -> largest pass 64, but only 32 asked for
+    # (2) the quirk case of the test below leaves at k = 8 of n = 300 (largest pass 8): the cap is the largest pass
+    be = Recorder()
+    X = np.linspace(0.0, 1.0, 300).reshape(-1, 1)
+    y = np.sin(3 * X[:, 0]) + 0.02 * np.random.default_rng(7).standard_normal(300)
+    be.set_train(X, y)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", gpf.NonSPDWarning)
+        gpf.negative_log_likelihood(np.log10([1.0, 1.5, 0.02]), X, y, kernels.RBF, False, True, backend=be)
+    assert [k for k, _ in be.hints] == [1, 2, 4, 8] and all(h == 8 for _, h in be.hints)
+
+
 def test_reference_loop_takes_the_same_exits_as_the_reference():
     """negative_log_likelihood(on_non_spd="reference") against oracle.nll_full (the restated loop of
     gp_functions.py:254-301, itself pinned to the unmodified reference in test_oracle.py): the quirk exit on an SPD matrix,
