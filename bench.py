@@ -604,6 +604,25 @@ def run_gpu(args):
                                  / ((stages["potrf"] + stages["trtri"]) / args.steps * 1e-3) * 1e-12,
                                  "syrk": (float(N_TRAIN) ** 3 / 3) / (stages["syrk"] / args.steps * 1e-3) * 1e-12},
                 "stage_ms": {s: stages[s] / args.steps for s in stages}}
+    # the element-wise (HBM-side) stages of the same evaluation against the measured copy bandwidth: algorithmic bytes
+    # per DESIGN.md section 3.3 -- the lower 128-blocks of K plus the two radial-factor stash arrays written by the
+    # assembly; K^-1, the stash and U (alpha = U z) read by the gradient stage
+    hbm_peak, hbm_src = measured_hbm_peak()
+    nb = -(-N_TRAIN // 128)
+    tri = nb * (nb + 1) / 2 * 128 * 128 * 8.0                       # bytes of one lower block triangle
+    asm_bytes, grad_bytes = 3 * tri, 4 * tri                         # Matern-5/2: K + g + k_pure;  K^-1 + g + k_pure + U
+    roofline["elementwise"] = {
+        "bound": "hbm", "peak": hbm_peak, "unit": "GB/s", "peak_source": hbm_src,
+        "assemble": {"ms": stages["assemble"] / args.steps, "algorithmic_bytes": asm_bytes,
+                     "achieved": asm_bytes / (stages["assemble"] / args.steps * 1e-3) * 1e-9,
+                     "frac": asm_bytes / (stages["assemble"] / args.steps * 1e-3) * 1e-9 / hbm_peak,
+                     "traffic": 3.204e9, "kernel": "gpb::assemble_sym_kernel (FP64 exp/sqrt-bound, profiles/r02_ncu_assemble_sym_stash.txt)"},
+        "gradient_stage": {"ms": stages["grad"] / args.steps, "algorithmic_bytes": grad_bytes,
+                           "achieved": grad_bytes / (stages["grad"] / args.steps * 1e-3) * 1e-9,
+                           "frac": grad_bytes / (stages["grad"] / args.steps * 1e-3) * 1e-9 / hbm_peak,
+                           "traffic": 3.270e9 + 1.075e9,
+                           "kernel": "gpb::grad_contract_stash_kernel (bulk-TMA ring) + trigemv_kernel "
+                                     "(profiles/r02_ncu_grad_contract_stash.txt, r02_ncu_trigemv.txt)"}}
     if pred is not None:
         pred["roofline"] = {"bound": "tensor", "achieved": pred["step_tflops_per_gpu"], "peak": peak,
                             "unit": "TFLOP/s", "frac": pred["step_tflops_per_gpu"] / peak,
