@@ -6,6 +6,8 @@
 //                        lower triangle is finally overwritten by K^-1 when a gradient is requested.
 //   Ubuf Np x Np       : U = L^-T (upper)            Wbuf Np x Np : W = L^-1 = U^T (lower)
 //   Dinv Np x 128      : inverses of the 128x128 diagonal blocks of L
+//   stashG, stashK     : (gradient evaluations) radial derivative factor and k_pure of every pair of the lower triangle,
+//                        packed 128x128 blocks, written by the assembly and read once by the gradient contraction
 // Padding rows/cols (index >= N) hold the identity, which every stage maps to the identity.
 //
 // Algorithms (all dense O(N^3) work is tile tasks for dgemm_tasks_kernel, see dgemm_tasks.cuh):
@@ -16,9 +18,9 @@
 //   predict variance : ||W k*||^2 as a tile GEMM with a column sum-of-squares epilogue.
 //   predict covariance: K** - Vt Vt^T, Vt = K*^T W^T (two tile GEMMs).
 //
-// Scheduling (build_potrf_plan / run_plan): one panel of look-ahead on a high-priority stream, large trailing updates
-// split over two streams by block-column parity, leading sub-trees of the triangular inverse started on a low-priority
-// stream while the Cholesky is still running.  tests/test_plans.py replays and race-checks these lists on the host.
+// Scheduling (build_potrf_plan / run_plan): two panels of look-ahead (the panel chain and the small update of the panel
+// after next on high-priority streams), large trailing updates split over two streams by block-column parity, leading
+// sub-trees of the triangular inverse started on a low-priority stream while the Cholesky is still running.  tests/test_plans.py replays and race-checks these lists on the host.
 //
 // Active learning (acquisition.cuh): acquisition losses + masked arg-max on device-resident predictions, and the
 // O(N^2) extension of W, U, alpha, z, log|K| by one observed point (gpb_append_train).
