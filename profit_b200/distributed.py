@@ -184,8 +184,9 @@ def multistart_optimize(xtrain, ytrain, starts, kernel, fixed_sigma_n=False, eva
 
     ``streams`` > 1 runs that many restarts of this rank concurrently, each on its own device handle and stream
     (host threads; the C calls release the GIL).  One evaluation cannot fill the GPU while its Cholesky walks the
-    panel chain, so independent restarts overlap: measured on B200 +2 % at N=16384, +13 % at N=8192, +47 % at
-    N=4096 with two streams (tools/concurrent_restarts.py).
+    panel chain, so independent restarts overlap: measured on B200 +4 % at N=8192 on plain evaluations
+    (tools/sweep_concurrent.sh; +13 % before the chain was shortened) and 59 -> 47 s on 12 BFGS restarts, where the second
+    stream also hides the latency-bound eig exits of an unlucky restart.
 
     Returns (best_theta, best_nll, table) where table has one row per restart: [restart, nll, theta...].
     The number of objective evaluations this rank spent (the length of the BFGS paths, which decides the wall time as
