@@ -71,7 +71,7 @@ def seed_diag(mats, nb):
         mats[M_U][k * 128:(k + 1) * 128, k * 128:(k + 1) * 128] = d.T
 
 
-@pytest.mark.parametrize("nb", [1, 2, 5, 21, 34])
+@pytest.mark.parametrize("nb", [1, 2, 5, 17, 21, 34])
 def test_replayed_plans_factor_and_invert(lib, nb):
     n = nb * 128
     K, Y = spd_problem(nb)
@@ -233,7 +233,7 @@ def _assert_race_free(tasks, launches, nb):
                 f"tiles without an ordering path")
 
 
-@pytest.mark.parametrize("nb", [3, 9, 24, 40, 70])
+@pytest.mark.parametrize("nb", [3, 9, 16, 17, 24, 33, 40, 65, 70])
 def test_cholesky_plan_orders_every_conflicting_pair_of_launches(lib, nb):
     """Static race check of the multi-stream Cholesky: any two launches whose tile footprints conflict (write/write or
     read/write) must be ordered by stream order or by an event record -> wait pair."""
